@@ -1,0 +1,399 @@
+// propagate.cu -- normalized-adjacency propagation for graph-CF encoders on B200.
+//
+//   agcf_norm_adj_csr      values of D^-1/2 A D^-1/2 (bit-exact association)
+//   agcf_spmm_csr_f32      Y = A X with fused layer-sum / addend / noise epilogue
+//   agcf_sddmm_csr_f32     pattern-masked dL/dA
+//   agcf_concat_rows_f32   [user_emb; item_emb] packing
+//
+// Reference call sites: recommender/LightGCN.py:230-240 (forward), its autograd
+// (backward), recommender/SimGCL.py:198-210, XSimGCL.py:205-223 (noise),
+// attack/White/PGA.py:97-117 (adjacency gradient), util/DataLoader.py:73-87 and
+// recommender/LightGCN.py:212-215 (normalization).
+//
+// SpMM design (HBM/L2-bound gather, no tensor cores -- see DESIGN.md):
+//   * a row of X is d fp32 = d/4 float4; LPR = min(d/4, 32) lanes own one row and
+//     each lane loads 16 B, so one warp-level LDG.128 fetches whole 128 B lines of
+//     32/LPR different neighbour rows (fully coalesced sectors);
+//   * rows are processed in `row_order` (degree descending): the two rows sharing a
+//     warp have ~equal length, long rows start first, the tail is 1-nnz rows;
+//   * col/val of a row are read 16/32 at a time, coalesced, streaming (no L1
+//     allocation) and broadcast by shuffle; up to LPR independent row gathers are
+//     in flight per lane before the FMA chain consumes them;
+//   * the first n_long rows (degree > a threshold chosen by the host) get a whole
+//     CTA: 256/LPR lane groups stride over the row, partials are reduced through
+//     shared memory in a fixed order (no atomics, deterministic);
+//   * epilogue fuses: + addend (backward's G/(L+1)), SimGCL noise, Y store, and
+//     the running layer sum / mean (acc_out = (acc_in + t) / acc_div).
+#include "common.cuh"
+
+namespace agcf {
+
+struct SpmmParams {
+  const int32_t* rowptr;
+  const int32_t* col;
+  const float* val;
+  const float4* X;
+  float4* Y;
+  const float4* addend;
+  const float4* acc_in;
+  float4* acc_out;
+  float acc_div;
+  const float4* noise;
+  float eps;
+  const int32_t* row_order;
+  int32_t n_long;
+  int32_t n_rows;
+};
+
+template <int D>
+struct RowCfg {
+  static constexpr int V4 = D / 4;                    // float4 per row
+  static constexpr int LPR = V4 < 32 ? V4 : 32;       // lanes per row
+  static constexpr int VPL = V4 / LPR;                // float4 per lane
+  static constexpr int RPW = 32 / LPR;                // rows per warp
+  static constexpr int THREADS = 256;
+  static constexpr int RPB = (THREADS / 32) * RPW;    // rows per block (short path)
+  static constexpr int GROUPS = THREADS / LPR;        // lane groups per block (long path)
+};
+
+__device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
+
+template <int D, bool NOISE>
+__device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool valid,
+                                              float4 (&t)[RowCfg<D>::VPL], int gl) {
+  using C = RowCfg<D>;
+  const size_t rbase = (size_t)row * C::V4;
+  if (p.addend != nullptr && valid) {
+#pragma unroll
+    for (int v = 0; v < C::VPL; ++v) t[v] = add4(t[v], ld_stream_f4(p.addend + rbase + v * C::LPR + gl));
+  }
+  if (NOISE) {
+    float4 nz[C::VPL];
+    float ss = 0.f;
+#pragma unroll
+    for (int v = 0; v < C::VPL; ++v) {
+      nz[v] = valid ? ld_stream_f4(p.noise + rbase + v * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss += dot4(nz[v], nz[v]);
+    }
+    ss = group_sum<C::LPR>(ss);
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);   // F.normalize(dim=-1, eps=1e-12)
+#pragma unroll
+    for (int v = 0; v < C::VPL; ++v) {
+      t[v].x = t[v].x + __fmul_rn(__fmul_rn(sgnf(t[v].x), __fdiv_rn(nz[v].x, nrm)), p.eps);
+      t[v].y = t[v].y + __fmul_rn(__fmul_rn(sgnf(t[v].y), __fdiv_rn(nz[v].y, nrm)), p.eps);
+      t[v].z = t[v].z + __fmul_rn(__fmul_rn(sgnf(t[v].z), __fdiv_rn(nz[v].z, nrm)), p.eps);
+      t[v].w = t[v].w + __fmul_rn(__fmul_rn(sgnf(t[v].w), __fdiv_rn(nz[v].w, nrm)), p.eps);
+    }
+  }
+  if (!valid) return;
+  if (p.Y != nullptr) {
+#pragma unroll
+    for (int v = 0; v < C::VPL; ++v) p.Y[rbase + v * C::LPR + gl] = t[v];
+  }
+  if (p.acc_out != nullptr) {
+#pragma unroll
+    for (int v = 0; v < C::VPL; ++v) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.acc_in != nullptr) a = ld_stream_f4(p.acc_in + rbase + v * C::LPR + gl);
+      float4 o = add4(a, t[v]);
+      if (p.acc_div != 1.0f) {
+        o.x = __fdiv_rn(o.x, p.acc_div); o.y = __fdiv_rn(o.y, p.acc_div);
+        o.z = __fdiv_rn(o.z, p.acc_div); o.w = __fdiv_rn(o.w, p.acc_div);
+      }
+      p.acc_out[rbase + v * C::LPR + gl] = o;
+    }
+  }
+}
+
+// accumulate nnz [s + first, s + first + stride*k ...) chunk-wise; `len` = row length,
+// `first`/`stride` = this lane group's starting offset and per-iteration advance,
+// `iters` = WARP-UNIFORM trip count (shuffles use the full mask).
+template <int D>
+__device__ __forceinline__ void spmm_accumulate(const SpmmParams& p, int s, int len, int first, int stride,
+                                                int iters, int gl, float4 (&acc)[RowCfg<D>::VPL]) {
+  using C = RowCfg<D>;
+  int c_next = 0;
+  float v_next = 0.f;
+  if (first + gl < len) {
+    c_next = ld_stream_i32(p.col + s + first + gl);
+    v_next = ld_stream_f32(p.val + s + first + gl);
+  }
+  int off = first;
+  for (int it = 0; it < iters; ++it, off += stride) {
+    const int c = c_next;
+    const float v = v_next;
+    int n = len - off;
+    n = n < 0 ? 0 : (n > C::LPR ? C::LPR : n);
+    c_next = 0;
+    v_next = 0.f;
+    if (off + stride + gl < len) {                       // prefetch the next chunk's indices
+      c_next = ld_stream_i32(p.col + s + off + stride + gl);
+      v_next = ld_stream_f32(p.val + s + off + stride + gl);
+    }
+#pragma unroll
+    for (int t = 0; t < C::LPR; ++t) {
+      const int ct = __shfl_sync(0xffffffffu, c, t, C::LPR);
+      const float vt = __shfl_sync(0xffffffffu, v, t, C::LPR);
+      if (t < n) {
+        const float4* xr = p.X + (size_t)ct * C::V4 + gl;
+#pragma unroll
+        for (int vv = 0; vv < C::VPL; ++vv) fma4(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
+      }
+    }
+  }
+}
+
+template <int D, bool NOISE>
+__global__ void __launch_bounds__(256) spmm_csr_kernel(const SpmmParams p) {
+  using C = RowCfg<D>;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gl = lane & (C::LPR - 1);
+  float4 acc[C::VPL];
+#pragma unroll
+  for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if ((int)blockIdx.x < p.n_long) {
+    // ---- long row: the whole CTA cooperates on one row --------------------------
+    __shared__ float4 part[C::GROUPS][C::V4];
+    const int row = p.row_order[blockIdx.x];
+    const int s = p.rowptr[row];
+    const int len = p.rowptr[row + 1] - s;
+    const int g = threadIdx.x / C::LPR;
+    const int stride = C::GROUPS * C::LPR;
+    const int iters = (len + stride - 1) / stride;       // block-uniform
+    spmm_accumulate<D>(p, s, len, g * C::LPR, stride, iters, gl, acc);
+#pragma unroll
+    for (int v = 0; v < C::VPL; ++v) part[g][v * C::LPR + gl] = acc[v];
+    __syncthreads();
+    if (warp == 0) {
+      const bool valid = lane < C::LPR;
+      float4 t[C::VPL];
+#pragma unroll
+      for (int v = 0; v < C::VPL; ++v) {
+        t[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+          for (int gg = 0; gg < C::GROUPS; ++gg) t[v] = add4(t[v], part[gg][v * C::LPR + gl]);
+        }
+      }
+      spmm_epilogue<D, NOISE>(p, row, valid, t, gl);
+    }
+    return;
+  }
+
+  // ---- short rows: one lane group per row ----------------------------------------
+  const int grp = lane / C::LPR;
+  const long long slot = (long long)p.n_long + ((long long)(blockIdx.x - p.n_long) * (C::THREADS / 32) + warp) * C::RPW + grp;
+  const bool valid = slot < p.n_rows;
+  int row = 0, s = 0, len = 0;
+  if (valid) {
+    row = p.row_order != nullptr ? p.row_order[slot] : (int)slot;
+    s = p.rowptr[row];
+    len = p.rowptr[row + 1] - s;
+  }
+  int maxlen = len;
+#pragma unroll
+  for (int o = C::LPR; o < 32; o <<= 1) {
+    const int other = __shfl_xor_sync(0xffffffffu, maxlen, o);
+    maxlen = other > maxlen ? other : maxlen;
+  }
+  const int iters = (maxlen + C::LPR - 1) / C::LPR;      // warp-uniform
+  spmm_accumulate<D>(p, s, len, 0, C::LPR, iters, gl, acc);
+  spmm_epilogue<D, NOISE>(p, row, valid, acc, gl);
+}
+
+template <int D>
+static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
+  using C = RowCfg<D>;
+  const long long short_rows = (long long)p.n_rows - p.n_long;
+  const long long blocks = p.n_long + (short_rows + C::RPB - 1) / C::RPB;
+  if (blocks <= 0) return AGCF_OK;
+  if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
+  if (p.noise != nullptr)
+    spmm_csr_kernel<D, true><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+  else
+    spmm_csr_kernel<D, false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+// ------------------------------------------------------------------------ SDDMM
+template <int D>
+__global__ void __launch_bounds__(256) sddmm_csr_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                        const float4* __restrict__ H, const float4* __restrict__ E,
+                                                        float* __restrict__ gval, int accumulate,
+                                                        const int32_t* __restrict__ row_order, int n_rows) {
+  using C = RowCfg<D>;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gl = lane & (C::LPR - 1);
+  const int grp = lane / C::LPR;
+  const long long slot = ((long long)blockIdx.x * (C::THREADS / 32) + warp) * C::RPW + grp;
+  const bool valid = slot < n_rows;
+  int row = 0, s = 0, len = 0;
+  if (valid) {
+    row = row_order != nullptr ? row_order[slot] : (int)slot;
+    s = rowptr[row];
+    len = rowptr[row + 1] - s;
+  }
+  int maxlen = len;
+#pragma unroll
+  for (int o = C::LPR; o < 32; o <<= 1) {
+    const int other = __shfl_xor_sync(0xffffffffu, maxlen, o);
+    maxlen = other > maxlen ? other : maxlen;
+  }
+  float4 h[C::VPL];
+#pragma unroll
+  for (int v = 0; v < C::VPL; ++v)
+    h[v] = valid ? __ldg(H + (size_t)row * C::V4 + v * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int off = 0; off < maxlen; off += C::LPR) {
+    int c = 0;
+    if (off + gl < len) c = ld_stream_i32(col + s + off + gl);
+    int n = len - off;
+    n = n < 0 ? 0 : (n > C::LPR ? C::LPR : n);
+    float mine = 0.f;
+#pragma unroll
+    for (int t = 0; t < C::LPR; ++t) {
+      const int ct = __shfl_sync(0xffffffffu, c, t, C::LPR);
+      float partial = 0.f;
+      if (t < n) {
+#pragma unroll
+        for (int vv = 0; vv < C::VPL; ++vv)
+          partial += dot4(h[vv], ld_gather_f4(E + (size_t)ct * C::V4 + vv * C::LPR + gl));
+      }
+      partial = group_sum<C::LPR>(partial);
+      if (gl == t) mine = partial;
+    }
+    if (off + gl < len) {
+      float* dst = gval + s + off + gl;
+      *dst = accumulate ? (*dst + mine) : mine;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ normalization
+__global__ void __launch_bounds__(256) norm_adj_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                       const float* __restrict__ w, const float* __restrict__ d_row,
+                                                       const float* __restrict__ d_col, float* __restrict__ val,
+                                                       int32_t* __restrict__ row_of, int n_rows, long long nnz) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  // row of nnz p: largest i with rowptr[i] <= p (empty rows are skipped by the search)
+  int lo = 0, hi = n_rows;           // invariant: rowptr[lo] <= p < rowptr[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)__ldg(rowptr + mid) <= p) lo = mid; else hi = mid;
+  }
+  if (row_of != nullptr) row_of[p] = lo;
+  if (val != nullptr) val[p] = __fmul_rn(__fmul_rn(d_row[lo], w[p]), d_col[col[p]]);
+}
+
+__global__ void __launch_bounds__(256) concat_rows_kernel(const float4* __restrict__ a, long long na4,
+                                                          const float4* __restrict__ b, long long nb4,
+                                                          float4* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < na4 + nb4; k += stride)
+    out[k] = k < na4 ? ld_stream_f4(a + k) : ld_stream_f4(b + (k - na4));
+}
+
+}  // namespace agcf
+
+using namespace agcf;
+
+extern "C" int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val,
+                                 const float* X, float* Y, const float* addend,
+                                 const float* acc_in, float* acc_out, float acc_div,
+                                 const float* noise, float eps,
+                                 const int32_t* row_order, int32_t n_long,
+                                 int32_t n_rows, int32_t d, agcf_stream_t stream) {
+  if (!rowptr || !col || !val || !X || n_rows < 0 || (Y == nullptr && acc_out == nullptr)) return AGCF_EINVAL;
+  if (!supported_d(d)) return AGCF_EUNSUPPORTED;
+  if (n_long < 0 || n_long > n_rows || (n_long > 0 && row_order == nullptr)) return AGCF_EINVAL;
+  if (!aligned16(X) || !aligned16(Y) || !aligned16(addend) || !aligned16(acc_in) || !aligned16(acc_out) || !aligned16(noise))
+    return AGCF_EINVAL;
+  if (X == Y || X == acc_out) return AGCF_EINVAL;        // rows of X are read by other CTAs
+  if (acc_div == 0.f) return AGCF_EINVAL;
+  SpmmParams p;
+  p.rowptr = rowptr; p.col = col; p.val = val;
+  p.X = reinterpret_cast<const float4*>(X);
+  p.Y = reinterpret_cast<float4*>(Y);
+  p.addend = reinterpret_cast<const float4*>(addend);
+  p.acc_in = reinterpret_cast<const float4*>(acc_in);
+  p.acc_out = reinterpret_cast<float4*>(acc_out);
+  p.acc_div = acc_div;
+  p.noise = reinterpret_cast<const float4*>(noise);
+  p.eps = eps;
+  p.row_order = row_order; p.n_long = n_long; p.n_rows = n_rows;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d) {
+    case 32: return launch_spmm<32>(p, st);
+    case 64: return launch_spmm<64>(p, st);
+    case 128: return launch_spmm<128>(p, st);
+    case 256: return launch_spmm<256>(p, st);
+  }
+  return AGCF_EUNSUPPORTED;
+}
+
+extern "C" int agcf_sddmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* H, const float* E,
+                                  float* gval, int32_t accumulate, const int32_t* row_order,
+                                  int32_t n_rows, int32_t d, agcf_stream_t stream) {
+  if (!rowptr || !col || !H || !E || !gval || n_rows < 0) return AGCF_EINVAL;
+  if (!supported_d(d)) return AGCF_EUNSUPPORTED;
+  if (!aligned16(H) || !aligned16(E)) return AGCF_EINVAL;
+  if (n_rows == 0) return AGCF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float4* H4 = reinterpret_cast<const float4*>(H);
+  const float4* E4 = reinterpret_cast<const float4*>(E);
+#define AGCF_SDDMM(DD)                                                                          \
+  {                                                                                             \
+    const unsigned blocks = (unsigned)((n_rows + RowCfg<DD>::RPB - 1) / RowCfg<DD>::RPB);        \
+    sddmm_csr_kernel<DD><<<blocks, 256, 0, st>>>(rowptr, col, H4, E4, gval, accumulate, row_order, n_rows); \
+  }
+  switch (d) {
+    case 32: AGCF_SDDMM(32) break;
+    case 64: AGCF_SDDMM(64) break;
+    case 128: AGCF_SDDMM(128) break;
+    case 256: AGCF_SDDMM(256) break;
+  }
+#undef AGCF_SDDMM
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+static int norm_or_expand(const int32_t* rowptr, const int32_t* col, const float* w, const float* d_row,
+                          const float* d_col, float* val, int32_t* row_of, int32_t n_rows, int64_t nnz,
+                          cudaStream_t st) {
+  if (n_rows == 0 || nnz == 0) return AGCF_OK;
+  if (nnz < 0 || nnz > 0x7fffffffLL) return AGCF_EINVAL;
+  const unsigned blocks = (unsigned)(((long long)nnz + 255) / 256);
+  norm_adj_kernel<<<blocks, 256, 0, st>>>(rowptr, col, w, d_row, d_col, val, row_of, n_rows, nnz);
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+extern "C" int agcf_norm_adj_csr(const int32_t* rowptr, const int32_t* col, const float* w,
+                                 const float* d_row, const float* d_col, float* val,
+                                 int32_t n_rows, int64_t nnz, agcf_stream_t stream) {
+  if (!rowptr || !col || !w || !d_row || !d_col || !val || n_rows < 0) return AGCF_EINVAL;
+  return norm_or_expand(rowptr, col, w, d_row, d_col, val, nullptr, n_rows, nnz, (cudaStream_t)stream);
+}
+
+extern "C" int agcf_csr_expand_rows(const int32_t* rowptr, int32_t* row_of, int32_t n_rows, int64_t nnz,
+                                    agcf_stream_t stream) {
+  if (!rowptr || !row_of || n_rows < 0) return AGCF_EINVAL;
+  return norm_or_expand(rowptr, nullptr, nullptr, nullptr, nullptr, nullptr, row_of, n_rows, nnz, (cudaStream_t)stream);
+}
+
+extern "C" int agcf_concat_rows_f32(const float* a, int64_t n_a, const float* b, int64_t n_b,
+                                    float* out, int32_t d, agcf_stream_t stream) {
+  if (!out || n_a < 0 || n_b < 0 || (n_a > 0 && !a) || (n_b > 0 && !b) || d <= 0 || (d & 3)) return AGCF_EINVAL;
+  if (!aligned16(a) || !aligned16(b) || !aligned16(out)) return AGCF_EINVAL;
+  const long long na4 = n_a * (d / 4), nb4 = n_b * (d / 4);
+  if (na4 + nb4 == 0) return AGCF_OK;
+  long long blocks = (na4 + nb4 + 255) / 256;
+  if (blocks > kSMs * 16) blocks = kSMs * 16;
+  concat_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(a), na4, reinterpret_cast<const float4*>(b), nb4, reinterpret_cast<float4*>(out));
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}

@@ -1,0 +1,643 @@
+// score.cu -- full-rank evaluation: user x item scoring fused with masked top-K.
+//
+// Reference: recommender/LightGCN.py:86-90 (predict: one GEMV per user + D2H),
+// :148-156 (test loop: mask train items with -10e8, find_k_largest),
+// util/algorithm.py:155-167 (heap top-K), util/metrics.py:9-85 (hits / NDCG).
+//
+// Pipeline (scores are never written to HBM):
+//   stage 0  mask bits    : [n_u, ceil(I/32)] words from the train-item CSR
+//   stage 1  group maxima : S = U_tile . I^T ; per (user, 32-item group) the max of
+//                           the masked scores.  impl 0: fp32 CUDA-core GEMM whose
+//                           per-score FMA chain is bit-identical to stage 2's;
+//                           impl 1: TF32 tcgen05 GEMM (score_tc.cu), approximate.
+//   stage 2  per user     : R = K-th largest group max  ->  candidate groups are
+//                           those with max >= R - margin (margin = 2*delta bounds the
+//                           stage-1 error, 0 for impl 0) -- every true top-K item is in
+//                           one of them (DESIGN.md "top-K exactness");  candidates are
+//                           re-scored in exact fp32 (k ascending, fmaf), the K-th
+//                           largest exact score s* is radix-selected, ties at s* are
+//                           resolved with the reference heap's rule, and the K
+//                           survivors are sorted by (score desc, item asc).
+#include "common.cuh"
+#include <float.h>
+
+namespace agcf {
+
+constexpr float kMasked = -1.0e9f;         // -10e8, recommender/LightGCN.py:153
+constexpr int kGroup = 32;                 // items per group
+
+__device__ __forceinline__ uint32_t f2key(float f) {          // order-preserving float -> uint
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// exact reference score: fp32, k ascending, fused multiply-add, start from 0
+template <int D>
+__device__ __forceinline__ float exact_dot(const float* __restrict__ urow_smem, const float4* __restrict__ irow) {
+  float acc = 0.f;
+#pragma unroll 4
+  for (int k4 = 0; k4 < D / 4; ++k4) {
+    const float4 v = __ldg(irow + k4);
+    acc = fmaf(urow_smem[4 * k4 + 0], v.x, acc);
+    acc = fmaf(urow_smem[4 * k4 + 1], v.y, acc);
+    acc = fmaf(urow_smem[4 * k4 + 2], v.z, acc);
+    acc = fmaf(urow_smem[4 * k4 + 3], v.w, acc);
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------ stage 0: mask
+__global__ void __launch_bounds__(256) mask_bits_kernel(const int32_t* __restrict__ user_rows, int n_u,
+                                                        const int32_t* __restrict__ mask_rowptr,
+                                                        const int32_t* __restrict__ mask_items, int n_items,
+                                                        int n_groups, uint32_t* __restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_u) return;
+  const int uid = user_rows != nullptr ? user_rows[r] : r;
+  const int s = mask_rowptr[uid], e = mask_rowptr[uid + 1];
+  for (int k = s + lane; k < e; k += 32) {
+    const int it = mask_items[k];
+    if (it >= 0 && it < n_items) atomicOr(bits + (size_t)r * n_groups + (it >> 5), 1u << (it & 31));
+  }
+}
+
+// max L2 norm over item rows (for the TF32 error margin)
+template <int D>
+__global__ void __launch_bounds__(256) max_row_norm_kernel(const float4* __restrict__ T, int n_rows, float* __restrict__ out) {
+  // out must be zeroed; norms are >= 0 so uint ordering of the bit pattern is monotone
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float ss = 0.f;
+  if (r < n_rows) {
+    for (int k = 0; k < D / 4; ++k) { const float4 v = __ldg(T + (size_t)r * (D / 4) + k); ss += dot4(v, v); }
+  }
+  float m = sqrtf(ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+
+// ------------------------------------------------- stage 1 (impl 0): fp32 GEMM
+// CTA = 64 users x (loop over 128-item tiles of its item split); 256 threads, each
+// owns 4 users x 8 items (items tx + 16*ii, so that the 16 tx-lanes read 16
+// consecutive item rows with LDS.128 at a 68-float stride: conflict-free).
+constexpr int S1_TU = 64, S1_TI = 128, S1_LD = 68;
+template <int D>
+struct S1Smem { static constexpr int LD = D + 4; static constexpr size_t bytes = (size_t)(S1_TU + S1_TI) * LD * sizeof(float); };
+
+template <int D>
+__global__ void __launch_bounds__(256) group_max_fp32_kernel(const float4* __restrict__ Uemb, const int32_t* __restrict__ user_rows,
+                                                             int n_u, const float4* __restrict__ Iemb, int n_items,
+                                                             const uint32_t* __restrict__ bits, int n_groups,
+                                                             int tiles_per_split, float* __restrict__ gmax) {
+  constexpr int LD = D + 4;                 // padded row stride in floats (multiple of 4)
+  constexpr int V4 = D / 4;
+  extern __shared__ __align__(16) float smem[];
+  float* Us = smem;                         // [64][LD]
+  float* Is = smem + S1_TU * LD;            // [128][LD]
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;   // ty: 0..15 -> users ty*4..ty*4+3
+  const int u0 = blockIdx.x * S1_TU;
+  // load the user tile once
+  for (int k = tid; k < S1_TU * V4; k += 256) {
+    const int r = k / V4, c = k - r * V4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u0 + r < n_u) {
+      const int uid = user_rows != nullptr ? user_rows[u0 + r] : (u0 + r);
+      v = __ldg(Uemb + (size_t)uid * V4 + c);
+    }
+    *reinterpret_cast<float4*>(Us + r * LD + 4 * c) = v;
+  }
+  const int n_tiles = (n_items + S1_TI - 1) / S1_TI;
+  const int t_begin = blockIdx.y * tiles_per_split;
+  const int t_end = min(n_tiles, t_begin + tiles_per_split);
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int i0 = tile * S1_TI;
+    __syncthreads();                        // previous tile fully consumed (and Us visible)
+    for (int k = tid; k < S1_TI * V4; k += 256) {
+      const int r = k / V4, c = k - r * V4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i0 + r < n_items) v = __ldg(Iemb + (size_t)(i0 + r) * V4 + c);
+      *reinterpret_cast<float4*>(Is + r * LD + 4 * c) = v;
+    }
+    __syncthreads();
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+#pragma unroll 2
+    for (int k4 = 0; k4 < V4; ++k4) {
+      float4 uu[4], vv[8];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) uu[a] = *reinterpret_cast<const float4*>(Us + (ty * 4 + a) * LD + 4 * k4);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) vv[b] = *reinterpret_cast<const float4*>(Is + (tx + 16 * b) * LD + 4 * k4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {       // k ascending: x, y, z, w
+          acc[a][b] = fmaf(uu[a].x, vv[b].x, acc[a][b]);
+          acc[a][b] = fmaf(uu[a].y, vv[b].y, acc[a][b]);
+          acc[a][b] = fmaf(uu[a].z, vv[b].z, acc[a][b]);
+          acc[a][b] = fmaf(uu[a].w, vv[b].w, acc[a][b]);
+        }
+    }
+    // masked group maxima: group gq (q=0..3) of this tile = items i0 + 32q .. +31 = {tx + 16*(2q), tx + 16*(2q+1)}
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int ur = u0 + ty * 4 + a;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int g = (i0 >> 5) + q;
+        uint32_t w = 0u;
+        if (ur < n_u && g < n_groups) w = __ldg(bits + (size_t)ur * n_groups + g);
+        float m = -FLT_MAX;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int b = 2 * q + h;
+          const int item = i0 + tx + 16 * b;
+          float sc = acc[a][b];
+          if ((w >> ((tx + 16 * h) & 31)) & 1u) sc = kMasked;
+          if (item >= n_items) sc = -FLT_MAX;
+          m = fmaxf(m, sc);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (tx == 0 && ur < n_u && g < n_groups) gmax[(size_t)ur * n_groups + g] = m;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------- stage 2 helpers
+// block-wide radix select of the R-th largest (R >= 1) among n keys produced by
+// keyfn(k); returns the key (uniform).  4 passes of 8 bits, smem histogram.
+struct SelectSmem {
+  unsigned int hist[256];
+  unsigned int prefix;
+  unsigned int remaining;
+};
+
+template <typename KeyFn>
+__device__ uint32_t block_radix_select(SelectSmem& sm, int n, unsigned int R, KeyFn keyfn) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (tid == 0) { sm.prefix = 0u; sm.remaining = R; }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int k = tid; k < 256; k += nthr) sm.hist[k] = 0u;
+    __syncthreads();
+    const uint32_t prefix = sm.prefix;
+    const uint32_t pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int k = tid; k < n; k += nthr) {
+      const uint32_t key = keyfn(k);
+      if ((key & pmask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // lane l owns bins [8l, 8l+8); find the digit where the count from the top reaches `remaining`
+      unsigned int mine = 0u;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) mine += sm.hist[tid * 8 + b];
+      unsigned int above = 0u;           // sum over lanes > tid
+      unsigned int run = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_down_sync(0xffffffffu, run, o);
+        if (tid + o < 32) run += y;
+      }
+      above = run - mine;                // inclusive suffix minus own
+      const unsigned int rem = sm.remaining;
+      const bool here = above < rem && rem <= above + mine;
+      if (here) {
+        unsigned int acc = above;
+        int digit = tid * 8;
+        for (int b = 7; b >= 0; --b) {
+          const unsigned int c = sm.hist[tid * 8 + b];
+          if (acc + c >= rem) { digit = tid * 8 + b; break; }
+          acc += c;
+        }
+        sm.prefix = prefix | ((uint32_t)digit << shift);
+        sm.remaining = rem - acc;
+      }
+    }
+    __syncthreads();
+  }
+  return sm.prefix;
+}
+
+// block-wide exclusive scan of one int per thread (256 threads); returns exclusive prefix, total via ref
+__device__ __forceinline__ int block_excl_scan_256(int v, int* warp_buf /*[9]*/, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  __syncthreads();                       // protect warp_buf reuse across calls
+  if (lane == 31) warp_buf[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int w = 0; w < 8; ++w) { const int t = warp_buf[w]; warp_buf[w] = run; run += t; }
+    warp_buf[8] = run;
+  }
+  __syncthreads();
+  total = warp_buf[8];
+  return warp_buf[warp] + incl - v;
+}
+
+struct Stage2Params {
+  const float4* Uemb;
+  const int32_t* user_rows;
+  int n_u;
+  const float4* Iemb;
+  int n_items;
+  const uint32_t* bits;
+  const float* gmax;
+  int n_groups;
+  int K;
+  int item_offset;
+  float margin_scale;          // 0 for impl 0; 2 * 1.01 * 2^-9 for TF32
+  const float* max_item_norm;  // scalar (device) or null
+  float* out_val;
+  int32_t* out_idx;
+  int32_t* out_flags;
+  // per-CTA scratch (global, L2-resident)
+  int32_t* cand_groups;        // [grid][n_groups]
+  float* cand_val;             // [grid][n_groups*32]
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) topk_select_kernel(const Stage2Params p) {
+  __shared__ SelectSmem sel;
+  __shared__ int warp_buf[9];
+  __shared__ float urow[D];
+  __shared__ int sh_p_pos, sh_gp;
+  extern __shared__ __align__(16) unsigned char dyn[];   // K-sized sort buffers
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int kpow2 = 1;
+  while (kpow2 < p.K) kpow2 <<= 1;
+  unsigned long long* sort_keys = reinterpret_cast<unsigned long long*>(dyn);   // [kpow2]
+  int32_t* my_groups = p.cand_groups + (size_t)blockIdx.x * p.n_groups;
+  float* my_val = p.cand_val + (size_t)blockIdx.x * p.n_groups * kGroup;
+
+  for (int r = blockIdx.x; r < p.n_u; r += gridDim.x) {
+    const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
+    const float* grow = p.gmax + (size_t)r * p.n_groups;
+    const uint32_t* brow = p.bits + (size_t)r * p.n_groups;
+    __syncthreads();
+    if (tid < D / 4) reinterpret_cast<float4*>(urow)[tid] = __ldg(p.Uemb + (size_t)uid * (D / 4) + tid);
+    __syncthreads();
+    // ---- 1. threshold on the group maxima
+    const unsigned int R = (unsigned int)min(p.K, p.n_groups);
+    const uint32_t tkey = block_radix_select(sel, p.n_groups, R, [&](int k) { return f2key(grow[k]); });
+    float thr = key2f(tkey);
+    if (p.margin_scale > 0.f) {
+      float ss = 0.f;
+      for (int k = 0; k < D; ++k) ss = fmaf(urow[k], urow[k], ss);
+      thr -= p.margin_scale * sqrtf(ss) * __ldg(p.max_item_norm);
+    }
+    // ---- 2. ordered compaction of candidate groups
+    int n_cg = 0;
+    for (int base = 0; base < p.n_groups; base += 256) {
+      const int g = base + tid;
+      const int flag = (g < p.n_groups && grow[g] >= thr) ? 1 : 0;
+      int total;
+      const int pos = block_excl_scan_256(flag, warp_buf, total);
+      if (flag) my_groups[n_cg + pos] = g;
+      n_cg += total;
+    }
+    __syncthreads();
+    // ---- 3. exact re-scoring of the candidates (warp per group, lane per item)
+    for (int c = warp; c < n_cg; c += 8) {
+      const int g = my_groups[c];
+      const int item = g * kGroup + lane;
+      float sc = -FLT_MAX;
+      if (item < p.n_items) {
+        sc = exact_dot<D>(urow, p.Iemb + (size_t)item * (D / 4));
+        if ((__ldg(brow + g) >> lane) & 1u) sc = kMasked;
+      }
+      my_val[c * kGroup + lane] = sc;
+    }
+    __syncthreads();
+    const int nc = n_cg * kGroup;
+    // number of real items among the candidates (only the last group can be partial)
+    int n_valid = nc;
+    if (n_cg > 0 && my_groups[n_cg - 1] == p.n_groups - 1) n_valid = nc - (p.n_groups * kGroup - p.n_items);
+    const int Keff = min(p.K, n_valid);
+    // ---- 4. K-th largest exact score, then the reference heap's tie rule
+    //   s* = K-th largest; m = #(> s*); walking items in index order, pos_p = first
+    //   position where #(>= s*) reaches K, g_p = #(> s*) at positions <= pos_p; the ties
+    //   kept are those with tie-rank in [m - g_p, K - g_p)   (SURVEY.md 8a-11).
+    int n_sel = 0;
+    if (Keff > 0) {
+      const uint32_t skey = block_radix_select(sel, nc, (unsigned int)Keff, [&](int k) { return f2key(my_val[k]); });
+      const float sstar = key2f(skey);
+      // pass A: m, pos_p, g_p
+      if (tid == 0) { sh_p_pos = -1; sh_gp = 0; }
+      int m = 0, run_ge = 0, run_gt = 0;
+      for (int base = 0; base < nc; base += 256) {
+        const int k = base + tid;
+        const float v = k < nc ? my_val[k] : -FLT_MAX;
+        const bool real = k < nc && (k < n_valid || v > -FLT_MAX);
+        const int gt = (real && v > sstar) ? 1 : 0;
+        const int ge = (real && v >= sstar) ? 1 : 0;
+        int tot_ge, tot_gt;
+        const int ex_ge = block_excl_scan_256(ge, warp_buf, tot_ge);
+        const int ex_gt = block_excl_scan_256(gt, warp_buf, tot_gt);
+        if (ge && run_ge + ex_ge + 1 == Keff) { sh_p_pos = k; sh_gp = run_gt + ex_gt + gt; }
+        run_ge += tot_ge;
+        run_gt += tot_gt;
+      }
+      m = run_gt;
+      __syncthreads();
+      const int gp = sh_gp;
+      const int tie_lo = m - gp, tie_hi = Keff - gp;
+      // pass B: select (ordered), pack (score key desc, idx asc) into 64-bit sort keys
+      for (int k = tid; k < kpow2; k += 256) sort_keys[k] = ~0ull;
+      __syncthreads();
+      int run_eq = 0, run_sel = 0;
+      for (int base = 0; base < nc; base += 256) {
+        const int k = base + tid;
+        const float v = k < nc ? my_val[k] : -FLT_MAX;
+        const bool real = k < nc && (k < n_valid || v > -FLT_MAX);
+        const int eq = (real && v == sstar) ? 1 : 0;
+        int tot_eq, tot_sel;
+        const int ex_eq = block_excl_scan_256(eq, warp_buf, tot_eq);
+        const int trank = run_eq + ex_eq;
+        const int take = (real && (v > sstar || (eq && trank >= tie_lo && trank < tie_hi))) ? 1 : 0;
+        const int ex_sel = block_excl_scan_256(take, warp_buf, tot_sel);
+        if (take) {
+          const int item = my_groups[k >> 5] * kGroup + (k & 31);
+          // ascending sort of (~scorekey, item) == score desc, item asc
+          sort_keys[run_sel + ex_sel] = ((unsigned long long)(~f2key(v)) << 32) | (uint32_t)item;
+        }
+        run_eq += tot_eq;
+        run_sel += tot_sel;
+      }
+      n_sel = run_sel;
+      __syncthreads();
+      for (int kk = 2; kk <= kpow2; kk <<= 1)
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+          for (int idx = tid; idx < (kpow2 >> 1); idx += 256) {
+            const int a = ((idx & ~(jj - 1)) << 1) | (idx & (jj - 1));
+            const int c = a | jj;
+            const bool up = (a & kk) == 0;
+            const unsigned long long ka = sort_keys[a], kc = sort_keys[c];
+            if ((ka > kc) == up) { sort_keys[a] = kc; sort_keys[c] = ka; }
+          }
+          __syncthreads();
+        }
+    }
+    for (int k = tid; k < p.K; k += 256) {
+      float v = -INFINITY;
+      int idx = -1;
+      if (k < n_sel) {
+        const unsigned long long key = sort_keys[k];
+        v = key2f(~(uint32_t)(key >> 32));
+        idx = (int)(uint32_t)key + p.item_offset;
+      }
+      p.out_val[(size_t)r * p.K + k] = v;
+      p.out_idx[(size_t)r * p.K + k] = idx;
+    }
+    if (tid == 0 && p.out_flags != nullptr) p.out_flags[r] = n_cg;   // diagnostics: candidate groups examined
+  }
+}
+
+// --------------------------------------------------------------------- predict
+template <int D>
+__global__ void __launch_bounds__(256) score_rows_kernel(const float4* __restrict__ Uemb, const int32_t* __restrict__ user_rows,
+                                                         const float4* __restrict__ Iemb, int n_items, float* __restrict__ out) {
+  __shared__ float urow[D];
+  const int r = blockIdx.y;
+  const int uid = user_rows != nullptr ? user_rows[r] : r;
+  if (threadIdx.x < D / 4) reinterpret_cast<float4*>(urow)[threadIdx.x] = __ldg(Uemb + (size_t)uid * (D / 4) + threadIdx.x);
+  __syncthreads();
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item < n_items) out[(size_t)r * n_items + item] = exact_dot<D>(urow, Iemb + (size_t)item * (D / 4));
+}
+
+// ------------------------------------------------------------------ top-K merge
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict__ vals, const int32_t* __restrict__ idx,
+                                                         int P, int n_u, int K, int pow2,
+                                                         float* __restrict__ out_val, int32_t* __restrict__ out_idx) {
+  extern __shared__ unsigned long long mk[];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  for (int k = tid; k < pow2; k += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (k < P * K) {
+      const int pp = k / K, kk = k - pp * K;
+      const size_t src = ((size_t)pp * n_u + r) * K + kk;
+      const int id = idx[src];
+      if (id >= 0) key = ((unsigned long long)(~f2key(vals[src])) << 32) | (uint32_t)id;
+    }
+    mk[k] = key;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= pow2; kk <<= 1)
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      for (int i2 = tid; i2 < (pow2 >> 1); i2 += blockDim.x) {
+        const int a = ((i2 & ~(jj - 1)) << 1) | (i2 & (jj - 1));
+        const int c = a | jj;
+        const bool up = (a & kk) == 0;
+        const unsigned long long ka = mk[a], kc = mk[c];
+        if ((ka > kc) == up) { mk[a] = kc; mk[c] = ka; }
+      }
+      __syncthreads();
+    }
+  for (int k = tid; k < K; k += blockDim.x) {
+    const unsigned long long key = mk[k];
+    const bool ok = key != ~0ull;
+    out_val[(size_t)r * K + k] = ok ? key2f(~(uint32_t)(key >> 32)) : -INFINITY;
+    out_idx[(size_t)r * K + k] = ok ? (int)(uint32_t)key : -1;
+  }
+}
+
+// ---------------------------------------------------------------------- metrics
+__global__ void __launch_bounds__(128) rank_metrics_kernel(const int32_t* __restrict__ topk_idx, int K,
+                                                           const int32_t* __restrict__ t_rowptr, const int32_t* __restrict__ t_items,
+                                                           const int32_t* __restrict__ test_total, int n_u,
+                                                           const int32_t* __restrict__ cutoffs, int nc,
+                                                           const double* __restrict__ inv_log, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_u) return;
+  const int s = t_rowptr[r], e = t_rowptr[r + 1];
+  for (int c = 0; c < nc; ++c) {
+    const int n = min(cutoffs[c], K);
+    double hits = 0.0, dcg = 0.0, idcg = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const int it = topk_idx[(size_t)r * K + k];
+      if (it < 0) continue;
+      int lo = s, hi = e;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (t_items[mid] < it) lo = mid + 1; else hi = mid; }
+      if (lo < e && t_items[lo] == it) { hits += 1.0; dcg += inv_log[k]; }
+    }
+    const int ni = min(test_total[r], cutoffs[c]);
+    for (int k = 0; k < ni; ++k) idcg += inv_log[k];
+    double* o = out + ((size_t)r * nc + c) * 3;
+    o[0] = hits; o[1] = dcg; o[2] = idcg;
+  }
+}
+
+// provided by score_tc.cu (tcgen05 TF32 group-max GEMM)
+int launch_group_max_tc(const float* Uemb, const int32_t* user_rows, int n_u, const float* Iemb, int n_items, int d,
+                        const uint32_t* bits, int n_groups, float* gmax, cudaStream_t st);
+
+struct WsLayout {
+  size_t bits_off, gmax_off, norm_off, groups_off, cval_off, total;
+  int n_groups, grid2;
+};
+
+static WsLayout ws_layout(int n_u, int n_items) {
+  WsLayout L;
+  L.n_groups = (n_items + kGroup - 1) / kGroup;
+  L.grid2 = n_u < 2 * kSMs ? (n_u > 0 ? n_u : 1) : 2 * kSMs;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  L.bits_off = off; off = up(off + (size_t)n_u * L.n_groups * 4);
+  L.gmax_off = off; off = up(off + (size_t)n_u * L.n_groups * 4);
+  L.norm_off = off; off = up(off + 256);
+  L.groups_off = off; off = up(off + (size_t)L.grid2 * L.n_groups * 4);
+  L.cval_off = off; off = up(off + (size_t)L.grid2 * L.n_groups * kGroup * 4);
+  L.total = off;
+  return L;
+}
+
+}  // namespace agcf
+
+using namespace agcf;
+
+extern "C" int64_t agcf_score_topk_ws_bytes(int32_t n_u, int32_t n_items, int32_t d, int32_t K) {
+  if (n_u < 0 || n_items <= 0 || K <= 0) return AGCF_EINVAL;
+  if (!supported_d(d) || K > 1024) return AGCF_EUNSUPPORTED;
+  return (int64_t)ws_layout(n_u, n_items).total;
+}
+
+extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int32_t n_u,
+                               const float* Iemb, int32_t n_items, int32_t d,
+                               const int32_t* mask_rowptr, const int32_t* mask_items,
+                               int32_t K, int32_t item_offset, int32_t impl,
+                               float* out_val, int32_t* out_idx, int32_t* out_flags,
+                               void* ws, int64_t ws_bytes, agcf_stream_t stream) {
+  if (!Uemb || !Iemb || !out_val || !out_idx || !ws || n_u < 0 || n_items <= 0 || K <= 0) return AGCF_EINVAL;
+  if ((mask_rowptr == nullptr) != (mask_items == nullptr)) return AGCF_EINVAL;
+  if (!supported_d(d) || K > 1024 || (impl != 0 && impl != 1)) return AGCF_EUNSUPPORTED;
+  if (!aligned16(Uemb) || !aligned16(Iemb) || (reinterpret_cast<uintptr_t>(ws) & 255u)) return AGCF_EINVAL;
+  if (n_u == 0) return AGCF_OK;
+  const WsLayout L = ws_layout(n_u, n_items);
+  if ((int64_t)L.total > ws_bytes) return AGCF_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+  uint32_t* bits = reinterpret_cast<uint32_t*>(base + L.bits_off);
+  float* gmax = reinterpret_cast<float*>(base + L.gmax_off);
+  float* norm = reinterpret_cast<float*>(base + L.norm_off);
+  const float4* U4 = reinterpret_cast<const float4*>(Uemb);
+  const float4* I4 = reinterpret_cast<const float4*>(Iemb);
+
+  // stage 0
+  AGCF_CUDA_OK(cudaMemsetAsync(bits, 0, (size_t)n_u * L.n_groups * 4, st));
+  if (mask_rowptr != nullptr) {
+    mask_bits_kernel<<<(unsigned)((n_u + 7) / 8), 256, 0, st>>>(user_rows, n_u, mask_rowptr, mask_items, n_items, L.n_groups, bits);
+    AGCF_LAUNCH_OK();
+  }
+  // stage 1
+  float margin_scale = 0.f;
+  if (impl == 1) {
+    AGCF_CUDA_OK(cudaMemsetAsync(norm, 0, 4, st));
+#define AGCF_NORM(DD) max_row_norm_kernel<DD><<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(I4, n_items, norm);
+    switch (d) { case 32: AGCF_NORM(32) break; case 64: AGCF_NORM(64) break; case 128: AGCF_NORM(128) break; case 256: AGCF_NORM(256) break; }
+#undef AGCF_NORM
+    AGCF_LAUNCH_OK();
+    const int rc = launch_group_max_tc(Uemb, user_rows, n_u, Iemb, n_items, d, bits, L.n_groups, gmax, st);
+    if (rc != AGCF_OK) return rc;
+    margin_scale = 2.0f * 1.01f * 0.001953125f;      // 2 * delta, delta = 1.01 * 2^-9 * |u| * max|v|
+  } else {
+    const int n_tiles = (n_items + S1_TI - 1) / S1_TI;
+    const int u_tiles = (n_u + S1_TU - 1) / S1_TU;
+    int splits = (4 * kSMs * 3 + u_tiles - 1) / u_tiles;          // aim at >= 3 waves of 4 CTAs/SM
+    if (splits < 1) splits = 1;
+    if (splits > n_tiles) splits = n_tiles;
+    if (splits > 65535) splits = 65535;
+    const int tps = (n_tiles + splits - 1) / splits;
+    splits = (n_tiles + tps - 1) / tps;
+    dim3 grid((unsigned)u_tiles, (unsigned)splits);
+#define AGCF_S1(DD)                                                                                           \
+  {                                                                                                           \
+    AGCF_CUDA_OK(cudaFuncSetAttribute(group_max_fp32_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)S1Smem<DD>::bytes));                                               \
+    group_max_fp32_kernel<DD><<<grid, 256, S1Smem<DD>::bytes, st>>>(U4, user_rows, n_u, I4, n_items, bits,    \
+                                                                    L.n_groups, tps, gmax);                   \
+  }
+    switch (d) { case 32: AGCF_S1(32) break; case 64: AGCF_S1(64) break; case 128: AGCF_S1(128) break; case 256: AGCF_S1(256) break; }
+#undef AGCF_S1
+    AGCF_LAUNCH_OK();
+  }
+  // stage 2
+  Stage2Params p;
+  p.Uemb = U4; p.user_rows = user_rows; p.n_u = n_u; p.Iemb = I4; p.n_items = n_items;
+  p.bits = bits; p.gmax = gmax; p.n_groups = L.n_groups; p.K = K; p.item_offset = item_offset;
+  p.margin_scale = margin_scale; p.max_item_norm = norm;
+  p.out_val = out_val; p.out_idx = out_idx; p.out_flags = out_flags;
+  p.cand_groups = reinterpret_cast<int32_t*>(base + L.groups_off);
+  p.cand_val = reinterpret_cast<float*>(base + L.cval_off);
+  int kpow2 = 1;
+  while (kpow2 < K) kpow2 <<= 1;
+  const size_t dyn = (size_t)kpow2 * 8;
+#define AGCF_S2(DD) topk_select_kernel<DD><<<(unsigned)L.grid2, 256, dyn, st>>>(p);
+  switch (d) { case 32: AGCF_S2(32) break; case 64: AGCF_S2(64) break; case 128: AGCF_S2(128) break; case 256: AGCF_S2(256) break; }
+#undef AGCF_S2
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+extern "C" int agcf_topk_merge(const float* vals, const int32_t* idx, int32_t P, int32_t n_u, int32_t K,
+                               float* out_val, int32_t* out_idx, agcf_stream_t stream) {
+  if (!vals || !idx || !out_val || !out_idx || P <= 0 || n_u < 0 || K <= 0) return AGCF_EINVAL;
+  if ((long long)P * K > 8192) return AGCF_EUNSUPPORTED;
+  if (n_u == 0) return AGCF_OK;
+  int pow2 = 2;
+  while (pow2 < P * K) pow2 <<= 1;
+  if (pow2 * 8 > 48 * 1024) {
+    AGCF_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pow2 * 8));
+  }
+  topk_merge_kernel<<<(unsigned)n_u, 128, (size_t)pow2 * 8, (cudaStream_t)stream>>>(vals, idx, P, n_u, K, pow2, out_val, out_idx);
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+extern "C" int agcf_score_rows(const float* Uemb, const int32_t* user_rows, int32_t n_u,
+                               const float* Iemb, int32_t n_items, int32_t d, float* out, agcf_stream_t stream) {
+  if (!Uemb || !Iemb || !out || n_u < 0 || n_items <= 0) return AGCF_EINVAL;
+  if (!supported_d(d)) return AGCF_EUNSUPPORTED;
+  if (!aligned16(Uemb) || !aligned16(Iemb)) return AGCF_EINVAL;
+  if (n_u == 0) return AGCF_OK;
+  if (n_u > 65535) return AGCF_EUNSUPPORTED;
+  dim3 grid((unsigned)((n_items + 255) / 256), (unsigned)n_u);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float4* U4 = reinterpret_cast<const float4*>(Uemb);
+  const float4* I4 = reinterpret_cast<const float4*>(Iemb);
+  switch (d) {
+    case 32: score_rows_kernel<32><<<grid, 256, 0, st>>>(U4, user_rows, I4, n_items, out); break;
+    case 64: score_rows_kernel<64><<<grid, 256, 0, st>>>(U4, user_rows, I4, n_items, out); break;
+    case 128: score_rows_kernel<128><<<grid, 256, 0, st>>>(U4, user_rows, I4, n_items, out); break;
+    case 256: score_rows_kernel<256><<<grid, 256, 0, st>>>(U4, user_rows, I4, n_items, out); break;
+  }
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+extern "C" int agcf_rank_metrics(const int32_t* topk_idx, int32_t K, const int32_t* t_rowptr, const int32_t* t_items,
+                                 const int32_t* test_total, int32_t n_u, const int32_t* cutoffs, int32_t nc,
+                                 const double* inv_log, double* out, agcf_stream_t stream) {
+  if (!topk_idx || !t_rowptr || !test_total || !cutoffs || !inv_log || !out || K <= 0 || n_u < 0 || nc <= 0) return AGCF_EINVAL;
+  if (n_u == 0) return AGCF_OK;
+  rank_metrics_kernel<<<(unsigned)((n_u + 127) / 128), 128, 0, (cudaStream_t)stream>>>(topk_idx, K, t_rowptr, t_items, test_total,
+                                                                                        n_u, cutoffs, nc, inv_log, out);
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}

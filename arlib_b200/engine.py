@@ -1,0 +1,229 @@
+"""Fused LightGCN BPR training engine: the body of LightGCN.train()
+(recommender/LightGCN.py:46-64) as a fixed sequence of agcf kernels per batch,
+replayed from a CUDA graph.
+
+per step (L layers): L x spmm (forward, layer-mean fused) -> bpr_forward ->
+bpr_backward (atomic-free rows of G) -> L x spmm (backward, A^T = A) -> zero_rows ->
+adam -> step counter            = 2L + 5 kernel launches, no host sync.
+
+per epoch: one Philox sampling launch (all E triples) + one grouping launch (all
+batches), then the step graph(s).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .graph import DeviceGraph
+
+
+class DeviceTrainSet:
+    """Device mirror of what util/sampler.py:4-30 reads from ``data``: the edge list
+    (data.training_data through data.user / data.item) and, per user, the sorted item
+    ids of data.training_set_u[user] (the rejection set; users without an entry --
+    injected fake users, SURVEY.md App. B -- reject nothing)."""
+
+    def __init__(self, data, device):
+        n = len(data.training_data)
+        user, item = data.user, data.item
+        eu = np.fromiter((user[r[0]] for r in data.training_data), dtype=np.int32, count=n)
+        ei = np.fromiter((item[r[1]] for r in data.training_data), dtype=np.int32, count=n)
+        n_users = max(data.user_num, int(eu.max()) + 1 if n else 0)
+        counts = np.zeros(n_users, dtype=np.int64)
+        chunks = []
+        tsu = data.training_set_u
+        for name, uid in user.items():
+            if uid < n_users and name in tsu:
+                ids = np.fromiter((item[i] for i in tsu[name] if i in item), dtype=np.int32)
+                ids.sort()
+                counts[uid] = ids.shape[0]
+                chunks.append((uid, ids))
+        rowptr = np.zeros(n_users + 1, dtype=np.int64)
+        np.cumsum(counts, out=rowptr[1:])
+        items = np.zeros(max(int(rowptr[-1]), 1), dtype=np.int32)
+        for uid, ids in chunks:
+            items[rowptr[uid]:rowptr[uid + 1]] = ids
+        self.n_edges, self.n_users, self.n_items = n, n_users, data.item_num
+        self.e_user = torch.from_numpy(eu).to(device)
+        self.e_item = torch.from_numpy(ei).to(device)
+        self.rej_rowptr = torch.from_numpy(rowptr.astype(np.int32)).to(device)
+        self.rej_items = torch.from_numpy(items).to(device)
+
+    @classmethod
+    def from_arrays(cls, e_user, e_item, n_users, n_items, device):
+        """Directly from integer edge arrays (benchmark / tests): rejection set = the
+        user's own train items."""
+        self = cls.__new__(cls)
+        eu = np.asarray(e_user, dtype=np.int32)
+        ei = np.asarray(e_item, dtype=np.int32)
+        order = np.lexsort((ei, eu))
+        su, si = eu[order], ei[order]
+        keep = np.ones(su.shape[0], dtype=bool)
+        keep[1:] = (su[1:] != su[:-1]) | (si[1:] != si[:-1])
+        su, si = su[keep], si[keep]
+        rowptr = np.zeros(n_users + 1, dtype=np.int64)
+        np.cumsum(np.bincount(su, minlength=n_users), out=rowptr[1:])
+        self.n_edges, self.n_users, self.n_items = eu.shape[0], n_users, n_items
+        self.e_user = torch.from_numpy(eu).to(device)
+        self.e_item = torch.from_numpy(ei).to(device)
+        self.rej_rowptr = torch.from_numpy(rowptr.astype(np.int32)).to(device)
+        self.rej_items = torch.from_numpy(si if si.size else np.zeros(1, np.int32)).to(device)
+        return self
+
+
+class LightGCNEngine:
+    def __init__(self, graph: DeviceGraph, table: torch.Tensor, n_users: int, n_layers: int,
+                 lr: float, reg: float, batch_size: int, max_triples: int,
+                 betas=(0.9, 0.999), adam_eps=1e-8):
+        if 3 * batch_size > 16384:
+            raise ValueError("batch_size %d too large for the single-CTA batch grouping (max 5461)" % batch_size)
+        if n_layers < 1:
+            raise ValueError("n_layers must be >= 1")
+        self.g, self.E0 = graph, table
+        self.N, self.d = table.shape
+        self.U, self.L = int(n_users), int(n_layers)
+        self.lr, self.reg, self.B = float(lr), float(reg), int(batch_size)
+        self.betas, self.adam_eps = betas, adam_eps
+        dev = table.device
+        f = lambda: torch.empty_like(table)
+        self.F = f()
+        self.fw = [f(), f()] if self.L > 1 else []
+        self.G = torch.zeros_like(table)
+        self.bw = [f(), f()] if self.L > 1 else []
+        self.dE0 = f()
+        self.m = torch.zeros_like(table)
+        self.v = torch.zeros_like(table)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.T = 0
+        self.cap = int(max_triples)
+        nbmax = (self.cap + self.B - 1) // self.B
+        i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        self.tu, self.ti, self.tj = i32(self.cap), i32(self.cap), i32(self.cap)
+        self.occ = i32(nbmax * 3 * self.B)
+        self.seg_off = i32(nbmax * (3 * self.B + 1))
+        self.seg_node = i32(nbmax * 3 * self.B)
+        self.n_seg = i32(nbmax)
+        self.out4 = torch.zeros((nbmax, 4), dtype=torch.float32, device=dev)
+        self.coef = torch.empty(self.B, dtype=torch.float32, device=dev)
+        self.ws = torch.zeros(ops.bpr_ws_bytes(self.B), dtype=torch.uint8, device=dev)
+        self._graphs = {}
+        self.launches_per_step = 2 * self.L + 5
+
+    # ------------------------------------------------------------ epoch set-up
+    @property
+    def n_batches(self):
+        return (self.T + self.B - 1) // self.B
+
+    def sample_epoch(self, ts: DeviceTrainSet, seed: int, epoch: int):
+        """Philox on-device sampling of one epoch (replaces util/sampler.py:4-30)."""
+        if ts.n_edges > self.cap:
+            raise ValueError("engine capacity %d < %d edges" % (self.cap, ts.n_edges))
+        ops.bpr_sample_epoch(ts.e_user, ts.e_item, ts.rej_rowptr, ts.rej_items, ts.n_items, seed, epoch,
+                             self.tu, self.ti, self.tj)
+        self.T = ts.n_edges
+        self._group(0, self.T)
+
+    def set_triples(self, u, i, j):
+        """External triples for the whole epoch (device int32 tensors or host arrays)."""
+        n = len(u)
+        if n > self.cap:
+            raise ValueError("engine capacity %d < %d triples" % (self.cap, n))
+        for dst, src in ((self.tu, u), (self.ti, i), (self.tj, j)):
+            src = torch.as_tensor(src, dtype=torch.int32)
+            dst[:n].copy_(src, non_blocking=True)
+        self.T = n
+        self._group(0, n)
+
+    def _group(self, first_triple, n):
+        b0 = first_triple // self.B
+        ops.bpr_group_batches(self.tu[first_triple:], self.ti[first_triple:], self.tj[first_triple:], n, self.B, self.U,
+                              self.occ[b0 * 3 * self.B:], self.seg_off[b0 * (3 * self.B + 1):],
+                              self.seg_node[b0 * 3 * self.B:], self.n_seg[b0:])
+
+    # --------------------------------------------------------------- one step
+    def forward_table(self, out=None):
+        """F = mean_k A^k E0 into self.F (or ``out``): the encoder forward alone
+        (recommender/LightGCN.py:230-240), e.g. for the end-of-epoch embeddings."""
+        F = self.F if out is None else out
+        x = self.E0
+        for k in range(1, self.L + 1):
+            last = k == self.L
+            y = None if last else self.fw[(k - 1) % 2]
+            ops.spmm(self.g, x, Y=y, acc_in=self.E0 if k == 1 else F, acc_out=F,
+                     acc_div=float(self.L + 1) if last else 1.0)
+            x = y
+        return F
+
+    def _launch_step(self, b):
+        B, L = self.B, self.L
+        t0 = b * B
+        nb = min(B, self.T - t0)
+        u, i, j = self.tu[t0:], self.ti[t0:], self.tj[t0:]
+        occ = self.occ[b * 3 * B:]
+        seg_off = self.seg_off[b * (3 * B + 1):]
+        seg_node = self.seg_node[b * 3 * B:]
+        n_seg = self.n_seg[b:]
+        out4 = self.out4[b]
+        F = self.forward_table()
+        ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)
+        ops.bpr_backward(F, u, i, j, nb, self.U, self.reg, 1.0, out4, self.coef, occ, seg_off, seg_node, n_seg, self.G)
+        H = self.G
+        for k in range(L, 0, -1):
+            if k > 1:
+                nxt = self.bw[k % 2]
+                ops.spmm(self.g, H, Y=nxt, addend=self.G)
+                H = nxt
+            else:
+                ops.spmm(self.g, H, acc_in=self.G, acc_out=self.dE0, acc_div=float(L + 1))
+        ops.zero_rows(seg_node, n_seg, 3 * nb, self.G)
+        ops.adam_step(self.E0, self.dE0, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.adam_eps,
+                      step_dev=self.step_dev)
+        ops.increment(self.step_dev)
+
+    # ------------------------------------------------------------------ running
+    def run_steps(self, first_batch=0, n_steps=None, use_graph=True):
+        """Run batches [first_batch, first_batch + n_steps) of the current epoch.
+        With use_graph the launch sequence is captured once per (first, n, T) and
+        replayed.  Returns the [n_steps, 4] loss rows (device view)."""
+        if n_steps is None:
+            n_steps = self.n_batches - first_batch
+        if first_batch + n_steps > self.n_batches:
+            raise ValueError("not enough batches")
+        if n_steps <= 0:
+            return self.out4[0:0]
+        if not use_graph:
+            for b in range(first_batch, first_batch + n_steps):
+                self._launch_step(b)
+        else:
+            key = (first_batch, n_steps, self.T)
+            g = self._graphs.get(key)
+            if g is None:
+                # warm-up outside capture is NOT needed for correctness of our kernels (no lazy
+                # allocation), but the one-time cudaFuncSetAttribute of the grouping kernel and
+                # module loading must not happen inside a capture: callers run sample_epoch /
+                # set_triples (eager) before the first run_steps, which covers both.
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                state = (self.E0.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone())
+                self._launch_step(first_batch)        # eager warm-up of every kernel in the step
+                self.E0.copy_(state[0]); self.m.copy_(state[1]); self.v.copy_(state[2]); self.step_dev.copy_(state[3])
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    for b in range(first_batch, first_batch + n_steps):
+                        self._launch_step(b)
+                self._graphs[key] = g
+                # capture does not execute: fall through to the replay below
+            g.replay()
+        return self.out4[first_batch:first_batch + n_steps]
+
+    def step_external(self, host_triples: torch.Tensor, nb: int, dev_staging=None):
+        """One step on triples supplied by the HOST (pinned int32 [3, B]): H2D copy,
+        grouping, the step kernels.  The loss row stays on device (self.out4[0])."""
+        self.tu[:nb].copy_(host_triples[0, :nb], non_blocking=True)
+        self.ti[:nb].copy_(host_triples[1, :nb], non_blocking=True)
+        self.tj[:nb].copy_(host_triples[2, :nb], non_blocking=True)
+        self.T = nb
+        self._group(0, nb)
+        self._launch_step(0)
+        return self.out4[0]

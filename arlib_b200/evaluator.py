@@ -1,0 +1,160 @@
+"""Full-rank evaluation on device: scoring + masked top-K + ranking metrics.
+
+Reference: recommender/LightGCN.py:137-161 (test), :86-90 (predict),
+util/algorithm.py:155-167, util/metrics.py:87-114.  One agcf_score_topk call (per
+user chunk) replaces the per-user GEMV + D2H + Python mask loop + numba heap; one
+agcf_rank_metrics call replaces the per-user Python metric loops.  Only the final
+per-user numbers cross to the host, where the reference's own summation order and
+string format are reproduced.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+from .util.metrics import format_measure
+
+USER_CHUNK = int(os.environ.get("ARLIB_B200_EVAL_CHUNK", "16384"))
+DEFAULT_IMPL = int(os.environ.get("ARLIB_B200_SCORE_IMPL", "0"))
+
+
+def _csr_from_lists(lists, n_rows_hint=None):
+    counts = np.fromiter((len(x) for x in lists), dtype=np.int64, count=len(lists))
+    rowptr = np.zeros(len(lists) + 1, dtype=np.int64)
+    np.cumsum(counts, out=rowptr[1:])
+    flat = np.zeros(max(int(rowptr[-1]), 1), dtype=np.int32)
+    for k, x in enumerate(lists):
+        if len(x):
+            flat[rowptr[k]:rowptr[k + 1]] = x
+    return rowptr.astype(np.int32), flat
+
+
+class FullRankEvaluator:
+    """Device-side view of (data.test_set, data.training_set_u) for test()."""
+
+    def __init__(self, data, device):
+        self.device = device
+        item = data.item
+        self.users = list(data.test_set.keys())                       # reference iteration order
+        uid = np.array([data.user[u] for u in self.users], dtype=np.int32)
+        # mask CSR indexed by GLOBAL user id: sorted train item ids (data.user_rated, LightGCN.py:151-153)
+        n_users = max(data.user_num, int(uid.max()) + 1 if len(uid) else 0)
+        mask_lists = [()] * n_users
+        for u in self.users:
+            ids = np.fromiter((item[i] for i in data.training_set_u[u]), dtype=np.int32)
+            ids.sort()
+            mask_lists[data.user[u]] = ids
+        mrp, mit = _csr_from_lists(mask_lists)
+        # test CSR indexed by test-user POSITION: sorted ids of test items that exist in train
+        t_lists, totals = [], []
+        for u in self.users:
+            names = data.test_set[u]
+            ids = np.fromiter((item[i] for i in names if i in item), dtype=np.int32)
+            ids.sort()
+            t_lists.append(ids)
+            totals.append(len(names))
+        trp, tit = _csr_from_lists(t_lists)
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.user_rows = to(uid)
+        self.mask_rowptr, self.mask_items = to(mrp), to(mit)
+        self.t_rowptr, self.t_items = to(trp), to(tit)
+        self.test_total = to(np.array(totals, dtype=np.int32))
+        self.test_total_host = totals
+        self.id2item = np.array([data.id2item[k] for k in range(len(data.id2item))], dtype=object)
+        self._ws = None
+
+    @classmethod
+    def from_arrays(cls, n_users, n_items, train_u, train_i, test_u, test_i, device):
+        """Benchmark / test constructor from integer arrays (names = str(id))."""
+        self = cls.__new__(cls)
+        self.device = device
+
+        def csr(rows, cols, n):
+            order = np.lexsort((cols, rows))
+            r, c = np.asarray(rows)[order], np.asarray(cols)[order]
+            rp = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(np.bincount(r, minlength=n), out=rp[1:])
+            return rp.astype(np.int32), (c.astype(np.int32) if c.size else np.zeros(1, np.int32))
+
+        tusers = np.unique(test_u)
+        pos = np.full(n_users, -1, dtype=np.int64)
+        pos[tusers] = np.arange(tusers.shape[0])
+        mrp, mit = csr(train_u, train_i, n_users)
+        trp, tit = csr(pos[test_u], test_i, tusers.shape[0])
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.users = [str(int(u)) for u in tusers]
+        self.user_rows = to(tusers.astype(np.int32))
+        self.mask_rowptr, self.mask_items = to(mrp), to(mit)
+        self.t_rowptr, self.t_items = to(trp), to(tit)
+        totals = np.diff(trp).astype(np.int32)
+        self.test_total = to(totals)
+        self.test_total_host = totals.tolist()
+        self.id2item = np.array([str(k) for k in range(n_items)], dtype=object)
+        self._ws = None
+        return self
+
+    # ---------------------------------------------------------------- kernels
+    def topk(self, user_emb, item_emb, K, impl=None):
+        """(values, ids) [n_test_users, K] on device, reference selection rule."""
+        impl = DEFAULT_IMPL if impl is None else impl
+        user_emb = user_emb.detach().contiguous()
+        item_emb = item_emb.detach().contiguous()
+        n = self.user_rows.numel()
+        vals = torch.empty((n, K), dtype=torch.float32, device=self.device)
+        idx = torch.empty((n, K), dtype=torch.int32, device=self.device)
+        for lo in range(0, n, USER_CHUNK):
+            hi = min(n, lo + USER_CHUNK)
+            need = ops._lib.load().agcf_score_topk_ws_bytes(hi - lo, item_emb.shape[0], item_emb.shape[1], K)
+            if need < 0:
+                ops._lib.check(int(need), "agcf_score_topk_ws_bytes")
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+            v, i = ops.score_topk(user_emb, item_emb, K, user_rows=self.user_rows[lo:hi], mask_rowptr=self.mask_rowptr,
+                                  mask_items=self.mask_items, impl=impl, ws=self._ws)
+            vals[lo:hi] = v
+            idx[lo:hi] = i
+        return vals, idx
+
+    def per_user_metrics(self, idx, cutoffs):
+        """[n_users, n_cutoffs, 3] float64 (hits, dcg, idcg) on device."""
+        K = idx.shape[1]
+        inv_log = torch.tensor([1.0 / math.log(r + 2) for r in range(max(K, max(cutoffs)))], dtype=torch.float64,
+                               device=self.device)
+        cut = torch.tensor(list(cutoffs), dtype=torch.int32, device=self.device)
+        return ops.rank_metrics(idx, self.t_rowptr, self.t_items, self.test_total, cut, inv_log)
+
+    # ------------------------------------------------------------- reference API
+    def measure(self, idx, cutoffs):
+        """The reference's list of metric strings (util/metrics.py:87-114), summed on the
+        host in the reference's order from the per-user device results."""
+        per = self.per_user_metrics(idx, cutoffs).cpu().numpy()
+        totals = self.test_total_host
+        total_num = sum(totals)
+        out = []
+        n_users = len(totals)
+        for c, n in enumerate(cutoffs):
+            hits = per[:, c, 0].astype(np.int64).tolist()
+            hit_ratio = sum(hits) / total_num
+            precision = sum(hits) / (n_users * n)
+            rec = [h / t for h, t in zip(hits, totals)]
+            recall = sum(rec) / len(rec)
+            ratio = (per[:, c, 1] / per[:, c, 2]).tolist()
+            total = 0
+            for r in ratio:
+                total += r
+            out += format_measure(n, hit_ratio, precision, recall, total / n_users)
+        return out
+
+    def rec_list(self, vals, idx):
+        """{user: [(item_name, score), ...]} like recommender/LightGCN.py:155-156"""
+        names = self.id2item[idx.cpu().numpy().astype(np.int64)]
+        scores = vals.cpu().numpy()
+        return {u: list(zip(names[k].tolist(), scores[k].tolist())) for k, u in enumerate(self.users)}
+
+    def test(self, user_emb, item_emb, top_n, max_n, impl=None):
+        vals, idx = self.topk(user_emb, item_emb, max_n, impl)
+        return self.rec_list(vals, idx), self.measure(idx, top_n)

@@ -1,0 +1,141 @@
+"""Device mirror of the normalized adjacency: int32 CSR + fp32 values + the row
+processing plan of the SpMM kernel.
+
+Reference objects this mirrors: ``data.norm_adj`` (scipy, util/DataLoader.py:73-87),
+``LGCN_Encoder.sparse_norm_adj`` (torch sparse COO, recommender/LightGCN.py:210,
+212-215, 247-252).  Bit-exactness contract: the degree vectors are
+computed on the host with the reference's own numpy expression; the O(nnz) products
+``fl(fl(d_i*w)*d_j)`` run on device (agcf_norm_adj_csr) and reproduce scipy's
+``(D.A).D`` association bit for bit.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _lib
+
+LONG_ROW_THRESHOLD = int(os.environ.get("ARLIB_B200_LONG_ROW", "256"))
+
+
+def _plan_rows(indptr: np.ndarray):
+    """row_order = rows by degree descending (stable); n_long = #rows above the
+    long-row threshold (those get a whole CTA in the SpMM kernel)."""
+    deg = np.diff(indptr)
+    order = np.argsort(-deg, kind="stable").astype(np.int32)
+    n_long = int(np.count_nonzero(deg > LONG_ROW_THRESHOLD))
+    return order, n_long
+
+
+class DeviceGraph:
+    """CSR (rowptr, col, val) on the device + SpMM plan.  Immutable after build."""
+
+    def __init__(self, rowptr, col, val, n_rows, row_order, n_long):
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.n_rows = int(n_rows)
+        self.nnz = int(col.numel())
+        self.row_order, self.n_long = row_order, int(n_long)
+        self._coo_idx = None
+
+    @property
+    def device(self):
+        return self.val.device
+
+    # ---------------------------------------------------------------- builders
+    @classmethod
+    def _from_csr_host(cls, csr: sp.csr_matrix, device, values=None):
+        if csr.shape[0] != csr.shape[1]:
+            raise ValueError("adjacency must be square")
+        if csr.nnz >= 2 ** 31 or csr.shape[0] >= 2 ** 31:
+            raise ValueError("graph exceeds int32 indexing")
+        order, n_long = _plan_rows(csr.indptr)
+        dev = torch.device(device)
+        rowptr = torch.from_numpy(csr.indptr.astype(np.int32)).to(dev)
+        col = torch.from_numpy(csr.indices.astype(np.int32)).to(dev)
+        if values is None:
+            val = torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float32)).to(dev)
+        else:
+            val = values
+        return cls(rowptr, col, val, csr.shape[0], torch.from_numpy(order).to(dev), n_long)
+
+    @classmethod
+    def from_scipy(cls, mat, device="cuda"):
+        """Upload an already-normalized scipy matrix as is (values untouched)."""
+        csr = sp.csr_matrix(mat)
+        csr.sum_duplicates()
+        csr.sort_indices()
+        return cls._from_csr_host(csr, device)
+
+    @classmethod
+    def normalized(cls, adj, d_row, d_col, device="cuda"):
+        """values = fl(fl(d_row[i]*w)*d_col[j]) computed ON DEVICE from the raw
+        weights of ``adj`` (scipy, canonical CSR) and host-computed degree vectors."""
+        csr = sp.csr_matrix(adj)
+        csr.sum_duplicates()
+        csr.sort_indices()
+        dev = torch.device(device)
+        w = torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float32)).to(dev)
+        dr = torch.from_numpy(np.ascontiguousarray(d_row, dtype=np.float32)).to(dev)
+        dc = torch.from_numpy(np.ascontiguousarray(d_col, dtype=np.float32)).to(dev)
+        val = torch.empty_like(w)
+        g = cls._from_csr_host(csr, device, values=val)
+        lib = _lib.load()
+        _lib.check(lib.agcf_norm_adj_csr(g.rowptr.data_ptr(), g.col.data_ptr(), w.data_ptr(), dr.data_ptr(),
+                                         dc.data_ptr(), val.data_ptr(), g.n_rows, g.nnz, _lib.stream_ptr()),
+                   "agcf_norm_adj_csr")
+        return g
+
+    @classmethod
+    def from_ui_adj(cls, ui_adj, device="cuda"):
+        """``_init_uiAdj`` (recommender/LightGCN.py:212-215): 1/np.sqrt of row AND
+        column sums, no inf guard, fractional weights allowed."""
+        d_row = np.array((1 / np.sqrt(ui_adj.sum(1)))).flatten()
+        d_col = np.array((1 / np.sqrt(ui_adj.sum(0)))).flatten()
+        return cls.normalized(ui_adj, d_row, d_col, device)
+
+    @classmethod
+    def from_dataloader_adj(cls, adj, device="cuda"):
+        """``DataLoader.normalize_graph_mat`` (util/DataLoader.py:73-81): np.power(rowsum,
+        -0.5) with inf -> 0, the same vector on both sides."""
+        rowsum = np.array(adj.sum(1))
+        d = np.power(rowsum, -0.5).flatten()
+        d[np.isinf(d)] = 0.
+        return cls.normalized(adj, d, d, device)
+
+    @classmethod
+    def from_coo_tensor(cls, t: torch.Tensor):
+        """From a torch sparse COO tensor (someone assigned model.sparse_norm_adj)."""
+        t = t.detach().coalesce()
+        idx = t.indices()
+        n = t.shape[0]
+        counts = torch.bincount(idx[0], minlength=n)
+        rowptr = torch.zeros(n + 1, dtype=torch.int64, device=t.device)
+        rowptr[1:] = torch.cumsum(counts, 0)
+        order, n_long = _plan_rows(rowptr.cpu().numpy())
+        return cls(rowptr.to(torch.int32), idx[1].to(torch.int32).contiguous(), t.values().float().contiguous(),
+                   n, torch.from_numpy(order).to(t.device), n_long)
+
+    # ------------------------------------------------------------------ views
+    def coo_indices(self):
+        """int64 [2, nnz] COO indices (row-major order) -- built once on demand."""
+        if self._coo_idx is None:
+            lib = _lib.load()
+            row = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            _lib.check(lib.agcf_csr_expand_rows(self.rowptr.data_ptr(), row.data_ptr(), self.n_rows, self.nnz,
+                                                _lib.stream_ptr()), "agcf_csr_expand_rows")
+            self._coo_idx = torch.stack([row.long(), self.col.long()])
+        return self._coo_idx
+
+    def to_coo_tensor(self):
+        """torch sparse COO tensor sharing ``val`` -- the ``sparse_norm_adj`` attribute
+        attacks touch (attack/White/PGA.py:98,117).  Unlike the reference's it IS
+        coalesced (it is built from canonical CSR)."""
+        return torch.sparse_coo_tensor(self.coo_indices(), self.val, (self.n_rows, self.n_rows),
+                                       is_coalesced=True)
+
+    def to_scipy(self):
+        return sp.csr_matrix((self.val.cpu().numpy(), self.col.cpu().numpy(), self.rowptr.cpu().numpy()),
+                             shape=(self.n_rows, self.n_rows))

@@ -1,0 +1,186 @@
+"""Tensor-level wrappers over the C-ABI (one python function per agcf_* entry point).
+
+All tensors must live on one CUDA device, be contiguous, fp32 / int32.  Launches go
+to torch's CURRENT stream, so they compose with torch ops and are capturable in
+``torch.cuda.graph``.  No function here has a CPU implementation.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .graph import DeviceGraph
+
+
+def _f32(t, name):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous fp32 CUDA tensor (got %s %s %s)" % (name, t.device, t.dtype, t.is_contiguous()))
+    return t
+
+
+def _i32(t, name):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.int32 and t.is_contiguous()):
+        raise TypeError("%s must be a contiguous int32 CUDA tensor" % name)
+    return t
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_div=1.0, noise=None, eps=0.0):
+    """agcf_spmm_csr_f32: t = A X (+addend) (+noise perturbation); Y = t;
+    acc_out = (acc_in + t) / acc_div."""
+    lib = _lib.load()
+    _f32(X, "X"); _f32(Y, "Y"); _f32(addend, "addend"); _f32(acc_in, "acc_in"); _f32(acc_out, "acc_out"); _f32(noise, "noise")
+    if X.shape[0] != g.n_rows:
+        raise ValueError("X has %d rows, graph has %d" % (X.shape[0], g.n_rows))
+    d = X.shape[1]
+    for t in (Y, addend, acc_in, acc_out, noise):
+        if t is not None and tuple(t.shape) != (g.n_rows, d):
+            raise ValueError("operand shape mismatch")
+    _lib.check(lib.agcf_spmm_csr_f32(g.rowptr.data_ptr(), g.col.data_ptr(), g.val.data_ptr(), X.data_ptr(), _p(Y),
+                                     _p(addend), _p(acc_in), _p(acc_out), float(acc_div), _p(noise), float(eps),
+                                     g.row_order.data_ptr(), g.n_long, g.n_rows, d, _lib.stream_ptr()),
+               "agcf_spmm_csr_f32")
+
+
+def sddmm(g: DeviceGraph, H, E, gval, accumulate=False):
+    """agcf_sddmm_csr_f32: gval[p] (+)= <H[i], E[col[p]]> over the stored pattern."""
+    lib = _lib.load()
+    _f32(H, "H"); _f32(E, "E"); _f32(gval, "gval")
+    _lib.check(lib.agcf_sddmm_csr_f32(g.rowptr.data_ptr(), g.col.data_ptr(), H.data_ptr(), E.data_ptr(), gval.data_ptr(),
+                                      1 if accumulate else 0, g.row_order.data_ptr(), g.n_rows, H.shape[1],
+                                      _lib.stream_ptr()), "agcf_sddmm_csr_f32")
+
+
+def concat_rows(a, b, out=None):
+    """agcf_concat_rows_f32: [a; b] into one table."""
+    lib = _lib.load()
+    _f32(a, "a"); _f32(b, "b")
+    d = a.shape[1]
+    if out is None:
+        out = torch.empty((a.shape[0] + b.shape[0], d), dtype=torch.float32, device=a.device)
+    _lib.check(lib.agcf_concat_rows_f32(a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], out.data_ptr(), d,
+                                        _lib.stream_ptr()), "agcf_concat_rows_f32")
+    return out
+
+
+def bpr_sample_epoch(e_user, e_item, rej_rowptr, rej_items, n_items, seed, epoch, out_u, out_i, out_j):
+    lib = _lib.load()
+    for t, n in ((e_user, "e_user"), (e_item, "e_item"), (rej_rowptr, "rej_rowptr"), (rej_items, "rej_items"),
+                 (out_u, "out_u"), (out_i, "out_i"), (out_j, "out_j")):
+        _i32(t, n)
+    _lib.check(lib.agcf_bpr_sample_epoch(e_user.data_ptr(), e_item.data_ptr(), e_user.numel(), rej_rowptr.data_ptr(),
+                                         rej_items.data_ptr(), int(n_items), int(seed) & (2 ** 64 - 1), int(epoch),
+                                         out_u.data_ptr(), out_i.data_ptr(), out_j.data_ptr(), _lib.stream_ptr()),
+               "agcf_bpr_sample_epoch")
+
+
+def bpr_group_batches(u, i, j, n_triples, batch, n_users, occ, seg_off, seg_node, n_seg):
+    lib = _lib.load()
+    _lib.check(lib.agcf_bpr_group_batches(u.data_ptr(), i.data_ptr(), j.data_ptr(), int(n_triples), int(batch),
+                                          int(n_users), occ.data_ptr(), seg_off.data_ptr(), seg_node.data_ptr(),
+                                          n_seg.data_ptr(), _lib.stream_ptr()), "agcf_bpr_group_batches")
+
+
+def bpr_ws_bytes(nb):
+    return int(_lib.load().agcf_bpr_ws_bytes(int(nb)))
+
+
+def bpr_forward(F, u, i, j, nb, n_users, reg, out4, coef, ws):
+    lib = _lib.load()
+    _lib.check(lib.agcf_bpr_forward(F.data_ptr(), u.data_ptr(), i.data_ptr(), j.data_ptr(), int(nb), int(n_users),
+                                    F.shape[1], float(reg), out4.data_ptr(), coef.data_ptr(), ws.data_ptr(),
+                                    _lib.stream_ptr()), "agcf_bpr_forward")
+
+
+def bpr_backward(F, u, i, j, nb, n_users, reg, scale, out4, coef, occ, seg_off, seg_node, n_seg, G):
+    lib = _lib.load()
+    _lib.check(lib.agcf_bpr_backward(F.data_ptr(), u.data_ptr(), i.data_ptr(), j.data_ptr(), int(nb), int(n_users),
+                                     F.shape[1], float(reg), float(scale), out4.data_ptr(), coef.data_ptr(),
+                                     occ.data_ptr(), seg_off.data_ptr(), seg_node.data_ptr(), n_seg.data_ptr(),
+                                     G.data_ptr(), _lib.stream_ptr()), "agcf_bpr_backward")
+
+
+def zero_rows(seg_node, n_seg, max_seg, G):
+    lib = _lib.load()
+    _lib.check(lib.agcf_zero_rows(seg_node.data_ptr(), n_seg.data_ptr(), int(max_seg), G.data_ptr(), G.shape[1],
+                                  _lib.stream_ptr()), "agcf_zero_rows")
+
+
+def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0, step_dev=None):
+    lib = _lib.load()
+    _f32(p, "p"); _f32(g, "g"); _f32(m, "m"); _f32(v, "v")
+    _lib.check(lib.agcf_adam_step_f32(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr),
+                                      float(beta1), float(beta2), float(eps), int(step), _p(step_dev),
+                                      _lib.stream_ptr()), "agcf_adam_step_f32")
+
+
+def increment(counter):
+    _lib.check(_lib.load().agcf_increment_i32(counter.data_ptr(), _lib.stream_ptr()), "agcf_increment_i32")
+
+
+def score_topk(user_emb, item_emb, K, user_rows=None, mask_rowptr=None, mask_items=None, item_offset=0, impl=0,
+               n_u=None, ws=None, return_flags=False):
+    """agcf_score_topk over users ``user_rows`` (or the first n_u rows).  Returns
+    (values [n_u,K] fp32, item ids [n_u,K] int32) sorted by (score desc, id asc)."""
+    lib = _lib.load()
+    _f32(user_emb, "user_emb"); _f32(item_emb, "item_emb"); _i32(user_rows, "user_rows")
+    _i32(mask_rowptr, "mask_rowptr"); _i32(mask_items, "mask_items")
+    if n_u is None:
+        n_u = user_rows.numel() if user_rows is not None else user_emb.shape[0]
+    n_items, d = item_emb.shape
+    need = int(lib.agcf_score_topk_ws_bytes(n_u, n_items, d, K))
+    if need < 0:
+        _lib.check(need, "agcf_score_topk_ws_bytes")
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=user_emb.device)
+    out_val = torch.empty((n_u, K), dtype=torch.float32, device=user_emb.device)
+    out_idx = torch.empty((n_u, K), dtype=torch.int32, device=user_emb.device)
+    flags = torch.empty(n_u, dtype=torch.int32, device=user_emb.device) if return_flags else None
+    _lib.check(lib.agcf_score_topk(user_emb.data_ptr(), _p(user_rows), n_u, item_emb.data_ptr(), n_items, d,
+                                   _p(mask_rowptr), _p(mask_items), int(K), int(item_offset), int(impl),
+                                   out_val.data_ptr(), out_idx.data_ptr(), _p(flags), ws.data_ptr(), ws.numel(),
+                                   _lib.stream_ptr()), "agcf_score_topk")
+    if return_flags:
+        return out_val, out_idx, flags
+    return out_val, out_idx
+
+
+def topk_merge(vals, idx):
+    """agcf_topk_merge: vals/idx [P, n_u, K] -> [n_u, K]."""
+    lib = _lib.load()
+    P, n_u, K = vals.shape
+    out_val = torch.empty((n_u, K), dtype=torch.float32, device=vals.device)
+    out_idx = torch.empty((n_u, K), dtype=torch.int32, device=vals.device)
+    _lib.check(lib.agcf_topk_merge(vals.data_ptr(), idx.data_ptr(), P, n_u, K, out_val.data_ptr(), out_idx.data_ptr(),
+                                   _lib.stream_ptr()), "agcf_topk_merge")
+    return out_val, out_idx
+
+
+def score_rows(user_emb, user_rows, item_emb):
+    """agcf_score_rows: un-masked scores of a few users against all items."""
+    lib = _lib.load()
+    n_u = user_rows.numel()
+    out = torch.empty((n_u, item_emb.shape[0]), dtype=torch.float32, device=item_emb.device)
+    _lib.check(lib.agcf_score_rows(user_emb.data_ptr(), user_rows.data_ptr(), n_u, item_emb.data_ptr(),
+                                   item_emb.shape[0], item_emb.shape[1], out.data_ptr(), _lib.stream_ptr()),
+               "agcf_score_rows")
+    return out
+
+
+def rank_metrics(topk_idx, t_rowptr, t_items, test_total, cutoffs, inv_log):
+    """agcf_rank_metrics -> [n_u, nc, 3] float64 (hits, dcg, idcg)."""
+    lib = _lib.load()
+    n_u, K = topk_idx.shape
+    nc = cutoffs.numel()
+    out = torch.empty((n_u, nc, 3), dtype=torch.float64, device=topk_idx.device)
+    _lib.check(lib.agcf_rank_metrics(topk_idx.data_ptr(), K, t_rowptr.data_ptr(), t_items.data_ptr(),
+                                     test_total.data_ptr(), n_u, cutoffs.data_ptr(), nc, inv_log.data_ptr(),
+                                     out.data_ptr(), _lib.stream_ptr()), "agcf_rank_metrics")
+    return out

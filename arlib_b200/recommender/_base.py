@@ -1,0 +1,157 @@
+"""Trainer / evaluator shell shared by the four graph-CF recommenders.
+
+Reference: recommender/LightGCN.py:17-161 -- ``save / predict / evaluate / test`` are
+byte-identical across the reference's recommenders, so they live here
+once.  Public surface kept: ``X(args, data)`` (re-callable on a live instance),
+``train(requires_adjgrad, requires_embgrad, gradIterationNum, Epoch, optimizer,
+evalNum)``, ``model``, ``user_emb / item_emb / best_user_emb / best_item_emb``,
+``predict(user) -> np.ndarray``, ``test() -> (rec_list, [str])``, ``evaluate(epoch)``,
+``save()``, ``data / args / topN / max_N / bestPerformance / recOutput``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+from .. import ops
+from ..evaluator import FullRankEvaluator
+
+
+class GraphRecommender(object):
+    model_name = "GraphRecommender"
+
+    def __init__(self, args, data):
+        print("Recommender: " + self.model_name)
+        self.data = data
+        self.args = args
+        self.bestPerformance = []
+        self.recOutput = []
+        self.topN = [int(num) for num in self.args.topK.split(',')]
+        self.max_N = max(self.topN)
+        self._evaluator = None
+        self.model = self._build_model()
+
+    def _build_model(self):
+        raise NotImplementedError
+
+    # the evaluator holds device mirrors of data.test_set / training_set_u; it is
+    # rebuilt whenever the data object changed shape (attacks mutate it in place)
+    def _get_evaluator(self):
+        key = (id(self.data), len(self.data.test_set), len(self.data.training_data), self.data.user_num,
+               self.data.item_num)
+        ev = self._evaluator
+        if ev is None or ev[0] != key:
+            dev = self.model.embedding_dict['user_emb'].device
+            ev = (key, FullRankEvaluator(self.data, dev))
+            self._evaluator = ev
+        return ev[1]
+
+    def __getstate__(self):           # device mirrors are derived data: keep pickles / deepcopies lean
+        st = dict(self.__dict__)
+        st['_evaluator'] = None
+        return st
+
+    def _sampler_mode(self):
+        return str(getattr(self.args, 'sampler', os.environ.get('ARLIB_B200_SAMPLER', 'device'))).lower()
+
+    # ------------------------------------------------------------------ reference API
+    def save(self):
+        """recommender/LightGCN.py:82-84"""
+        with torch.no_grad():
+            self.best_user_emb, self.best_item_emb = self.model.forward()
+
+    def predict(self, u):
+        """recommender/LightGCN.py:86-90 -- un-masked fp32 scores of one user, on the host."""
+        with torch.no_grad():
+            uid = self.data.get_user_id(u)
+            rows = torch.tensor([uid], dtype=torch.int32, device=self.item_emb.device)
+            score = ops.score_rows(self.user_emb.detach().contiguous(), rows, self.item_emb.detach().contiguous())
+            return score[0].cpu().numpy()
+
+    def evaluate(self, epoch):
+        """recommender/LightGCN.py:92-135 -- keep-best by majority vote over the 4 metrics."""
+        print('Evaluating the model...')
+        ev = self._get_evaluator()
+        with torch.no_grad():
+            _, idx = ev.topk(self.user_emb, self.item_emb, self.max_N)
+        measure = ev.measure(idx, [self.max_N])
+        performance = {}
+        for m in measure[1:]:
+            k, v = m.strip().split(':')
+            performance[k] = float(v)
+        if len(self.bestPerformance) > 0:
+            count = 0
+            for k in self.bestPerformance[1]:
+                if self.bestPerformance[1][k] > performance[k]:
+                    count += 1
+                else:
+                    count -= 1
+            if count < 0:
+                self.bestPerformance[1] = performance
+                self.bestPerformance[0] = epoch + 1
+                self.save()
+        else:
+            self.bestPerformance.append(epoch + 1)
+            self.bestPerformance.append(performance)
+            self.save()
+        print('-' * 120)
+        print('Real-Time Ranking Performance ' + ' (Top-' + str(self.max_N) + ' Item Recommendation)')
+        measure = [m.strip() for m in measure[1:]]
+        print('*Current Performance*')
+        print('Epoch:', str(epoch + 1) + ',', '  |  '.join(measure))
+        bp = ''
+        bp += 'Hit Ratio' + ':' + str(self.bestPerformance[1]['Hit Ratio']) + '  |  '
+        bp += 'Precision' + ':' + str(self.bestPerformance[1]['Precision']) + '  |  '
+        bp += 'Recall' + ':' + str(self.bestPerformance[1]['Recall']) + '  |  '
+        bp += 'NDCG' + ':' + str(self.bestPerformance[1]['NDCG'])
+        print('*Best Performance* ')
+        print('Epoch:', str(self.bestPerformance[0]) + ',', bp)
+        print('-' * 120)
+        return measure
+
+    def test(self):
+        """recommender/LightGCN.py:137-161 -> (rec_list, metric strings)."""
+        ev = self._get_evaluator()
+        with torch.no_grad():
+            rec_list, measure = ev.test(self.user_emb, self.item_emb, self.topN, self.max_N)
+        sys.stdout.write('\rProgress: [{}]100%\n'.format('+' * 50))
+        return rec_list, measure
+
+    # ------------------------------------------------------------------ training
+    def _grad_buffers(self, requires_adjgrad, requires_embgrad, model):
+        """recommender/LightGCN.py:36-43.  The reference allocates a DENSE N x N Matgrad
+        (20 GB at Gowalla shape); here the adjacency gradient is accumulated on the stored
+        pattern and only densified on return."""
+        if requires_embgrad:
+            model.requires_grad = True
+            dev = model.embedding_dict['user_emb'].device
+            self.usergrad = torch.zeros((self.data.user_num, self.args.emb_size), device=dev)
+            self.itemgrad = torch.zeros((self.data.item_num, self.args.emb_size), device=dev)
+        elif requires_adjgrad:
+            self.model.sparse_norm_adj.requires_grad = True
+            self.Matgrad = None
+
+    def _accumulate_grads(self, requires_adjgrad, requires_embgrad, maxEpoch, epoch, gradIterationNum):
+        """recommender/LightGCN.py:58-62"""
+        if requires_adjgrad and maxEpoch - epoch < gradIterationNum:
+            g = self.model.sparse_norm_adj.grad
+            self.Matgrad = g.clone() if self.Matgrad is None else self.Matgrad + g
+        elif requires_embgrad and maxEpoch - epoch < gradIterationNum:
+            self.usergrad += self.model.embedding_dict["user_emb"].grad
+            self.itemgrad += self.model.embedding_dict["item_emb"].grad
+
+    def _train_returns(self, requires_adjgrad, requires_embgrad):
+        """recommender/LightGCN.py:74-80"""
+        if requires_adjgrad:
+            n = self.data.user_num + self.data.item_num
+            dense = self.Matgrad.to_dense() if self.Matgrad is not None else \
+                torch.zeros((n, n), device=self.user_emb.device)
+            mat = (dense + dense.T)[:self.data.user_num, self.data.user_num:]
+        if requires_adjgrad and requires_embgrad:
+            return mat, self.user_emb, self.item_emb, self.usergrad, self.itemgrad
+        elif requires_adjgrad:
+            return mat
+        elif requires_embgrad:
+            return self.user_emb, self.item_emb, self.usergrad, self.itemgrad

@@ -1,0 +1,33 @@
+"""Differentiable losses with the reference's signatures (util/loss.py:5-9,25-29,42-49).
+
+These are the torch-level entry points attacks import (attack/Black/GTA.py:205,
+attack/White/DLAttack.py).  The recommender's own training loop does not come
+through here when it owns the optimizer: it runs the fused CUDA kernels
+(agcf_bpr_forward / agcf_bpr_backward).  ``bpr_l2_fused`` exposes those kernels
+as one autograd function for callers that hand in their own optimizer.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def bpr_loss(user_emb, pos_item_emb, neg_item_emb):
+    """util/loss.py:5-9"""
+    pos = (user_emb * pos_item_emb).sum(dim=1)
+    neg = (user_emb * neg_item_emb).sum(dim=1)
+    return (-torch.log(10e-8 + torch.sigmoid(pos - neg))).mean()
+
+
+def l2_reg_loss(reg, *args):
+    """util/loss.py:25-29 -- un-squared Frobenius norms."""
+    total = 0
+    for emb in args:
+        total = total + torch.norm(emb, p=2)
+    return total * reg
+
+
+def InfoNCE(view1, view2, temperature):
+    """util/loss.py:42-49"""
+    view1, view2 = F.normalize(view1, dim=1), F.normalize(view2, dim=1)
+    pos = torch.exp((view1 * view2).sum(dim=-1) / temperature)
+    ttl = torch.exp(torch.matmul(view1, view2.transpose(0, 1)) / temperature).sum(dim=1)
+    return (-torch.log(pos / ttl)).mean()

@@ -1,0 +1,202 @@
+/* agcf.h -- C-ABI of libagcf.so: the B200 (sm_100a) graph-CF hot path.
+ *
+ * The reference (CoderWZW/ARLib) has NO FFI: its hot path is Python calling
+ * PyTorch.  These entry points are what a binding for that path would bind; the
+ * Python surface in arlib_b200/ (drop-in recommender.* / util.*) sits strictly on
+ * top of them via ctypes.  Each function cites the reference code it replaces
+ * (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch
+ *     in this repo) unless the name ends in _host; the library allocates nothing
+ *     and keeps no global state; workspace sizes come from *_ws_bytes queries;
+ *   - every call takes an explicit stream (a cudaStream_t passed as void*), only
+ *     enqueues work on it and is capturable in a CUDA graph;
+ *   - return value: 0 = ok, <0 = AGCF_E* below; nothing throws;
+ *   - fp32 everywhere, int32 indices; tables are row-major [rows, d], 16-byte
+ *     aligned, d in {32, 64, 128, 256};
+ *   - a "node" id is a row of the stacked table [users; items] (N = U + I); item
+ *     ids handed to the loss / sampler / eval calls are item-local (0..I-1).
+ */
+#ifndef AGCF_H_
+#define AGCF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGCF_OK            0
+#define AGCF_EINVAL       (-1)  /* bad argument (null pointer, size, alignment)      */
+#define AGCF_EUNSUPPORTED (-2)  /* shape outside the compiled set (d, K, B limits)   */
+#define AGCF_ECUDA        (-3)  /* a CUDA runtime call failed; see agcf_last_cuda_error */
+#define AGCF_EWORKSPACE   (-4)  /* workspace too small                               */
+
+typedef void* agcf_stream_t;    /* cudaStream_t */
+
+int         agcf_abi_version(void);
+const char* agcf_strerror(int code);
+int         agcf_last_cuda_error(void);   /* cudaError_t of the last AGCF_ECUDA on this thread */
+int         agcf_device_sm_count(void);
+
+/* ------------------------------------------------------------------ adjacency
+ * val[p] = fl(fl(d_row[i] * w[p]) * d_col[col[p]])  for p in row i, no FMA
+ * contraction -- the association of (D.A).D in scipy.
+ * Replaces: util/DataLoader.py:73-87 (normalize_graph_mat) and
+ * recommender/LightGCN.py:212-215 (_init_uiAdj); d_row/d_col are computed on the
+ * host with the reference's own numpy expression (bit-exactness). */
+int agcf_norm_adj_csr(const int32_t* rowptr, const int32_t* col, const float* w,
+                      const float* d_row, const float* d_col, float* val,
+                      int32_t n_rows, int64_t nnz, agcf_stream_t stream);
+
+/* row -> COO expansion helper: row_of[p] = i for p in [rowptr[i], rowptr[i+1]) */
+int agcf_csr_expand_rows(const int32_t* rowptr, int32_t* row_of, int32_t n_rows, int64_t nnz,
+                         agcf_stream_t stream);
+
+/* ---------------------------------------------------------------- propagation
+ * One normalized-adjacency propagation Y = A X with a fused epilogue, CSR fp32.
+ *   t[i,:]       = sum_p val[p] * X[col[p],:]  (+ addend[i,:] if addend)
+ *   if noise:      t[i,:] += sign(t[i,:]) * noise[i,:]/max(||noise[i,:]||,1e-12) * eps
+ *   if Y:          Y[i,:] = t[i,:]
+ *   if acc_out:    acc_out[i,:] = ((acc_in ? acc_in[i,:] : 0) + t[i,:]) / acc_div
+ * row_order (nullable) is a permutation of rows giving the processing order
+ * (longest rows first); n_long leading entries of it are rows handled by a whole
+ * CTA.  Forward AND backward of the encoder: A is symmetric so A^T = A.
+ * Replaces: torch.sparse.mm + stack + mean in recommender/LightGCN.py:230-240,
+ * the noise lines of recommender/SimGCL.py:202-206 / XSimGCL.py:211-215, and the
+ * autograd of those (transposed SpMM + mean backward). */
+int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val,
+                      const float* X, float* Y,
+                      const float* addend,
+                      const float* acc_in, float* acc_out, float acc_div,
+                      const float* noise, float eps,
+                      const int32_t* row_order, int32_t n_long,
+                      int32_t n_rows, int32_t d, agcf_stream_t stream);
+
+/* gval[p] (+)= <H[i,:], E[col[p],:]> for p in row i (accumulate != 0 adds).
+ * Replaces: autograd of torch.sparse.mm w.r.t. the sparse operand, restricted to
+ * the stored pattern -- attack/White/PGA.py:97-117, recommender/LightGCN.py:40-43,58-59. */
+int agcf_sddmm_csr_f32(const int32_t* rowptr, const int32_t* col,
+                       const float* H, const float* E, float* gval, int32_t accumulate,
+                       const int32_t* row_order, int32_t n_rows, int32_t d, agcf_stream_t stream);
+
+/* pack [user_emb; item_emb] into one [N,d] table (torch.cat of LightGCN.py:231)
+ * and the inverse split-add used by its backward. */
+int agcf_concat_rows_f32(const float* a, int64_t n_a, const float* b, int64_t n_b,
+                         float* out, int32_t d, agcf_stream_t stream);
+
+/* -------------------------------------------------------------------- sampler
+ * One epoch of BPR triples on device (Philox4x32-10, counter-based):
+ *   position t of the epoch takes edge perm(t) of (e_user, e_item) where perm is a
+ *   keyed bijection of [0,E) (every edge exactly once per epoch), and a negative
+ *   item drawn uniformly from [0,I) and re-drawn while it is in the user's
+ *   rejection set rej_items[rej_rowptr[u] .. rej_rowptr[u+1]) (sorted ascending).
+ * Replaces: util/sampler.py:4-30 (next_batch_pairwise): shuffle + per-row
+ * rejection sampling; batches are consecutive slices [b*B, min((b+1)*B, E)). */
+int agcf_bpr_sample_epoch(const int32_t* e_user, const int32_t* e_item, int32_t n_edges,
+                          const int32_t* rej_rowptr, const int32_t* rej_items, int32_t n_items,
+                          uint64_t seed, uint64_t epoch,
+                          int32_t* out_u, int32_t* out_i, int32_t* out_j, agcf_stream_t stream);
+
+/* ----------------------------------------------------------------------- loss
+ * Group the 3*B node occurrences of each batch by node (atomic-free scatter
+ * plan).  For batch b (triples [b*B, min((b+1)*B,T)) ), nb = its triple count:
+ *   occ   [b*3B + k]   k < 3*nb : occurrence ids role*nb + t, sorted by (node, id);
+ *                                 role 0 = user, 1 = positive, 2 = negative
+ *   seg_off[b*(3B+1)+s] s <= n_seg: start of segment s in occ (one segment = one node)
+ *   seg_node[b*3B + s] : the node (users 0..U-1, items U..U+I-1)
+ *   n_seg[b]
+ * 3*B must be <= 16384. One CTA per batch; all batches of an epoch in one call. */
+int agcf_bpr_group_batches(const int32_t* u, const int32_t* i, const int32_t* j,
+                           int32_t n_triples, int32_t batch, int32_t n_users,
+                           int32_t* occ, int32_t* seg_off, int32_t* seg_node, int32_t* n_seg,
+                           agcf_stream_t stream);
+
+/* Fused gather - score - BPR - L2 forward for one batch of nb triples on the
+ * propagated table F [N,d]:
+ *   x_t = <F[u],F[U+i]> - <F[u],F[U+j]>
+ *   out[0] = loss = mean_t -log(1e-7 + sigmoid(x_t)) + reg*(||F[u_.]||_F + ||F[U+i_.]||_F)
+ *   out[1] = bpr term, out[2] = ||F[u_.]||_F, out[3] = ||F[U+i_.]||_F
+ *   coef[t] = d loss / d x_t
+ * ws: agcf_bpr_ws_bytes(nb) bytes.  Deterministic (fixed-order reductions).
+ * Replaces: util/loss.py:5-9 (bpr_loss), :25-29 (l2_reg_loss) and the three
+ * index gathers of recommender/LightGCN.py:51-54. */
+int64_t agcf_bpr_ws_bytes(int32_t nb);
+int agcf_bpr_forward(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
+                     int32_t nb, int32_t n_users, int32_t d, float reg,
+                     float* out4, float* coef, void* ws, agcf_stream_t stream);
+
+/* Backward of the above into the dense gradient of F, atomic-free: one
+ * half-warp per node segment sums that node's contributions in occurrence order
+ *   user : coef*(F[i]-F[j]) + reg*F[u]/||F[u_.]||     positive: coef*F[u] + reg*F[i]/||F[i_.]||
+ *   negative: -coef*F[u]
+ * and writes G[node,:] = scale * sum (scale folds the 1/(L+1) of the layer mean
+ * and any upstream grad).  Rows of G not named by a segment are NOT touched (the
+ * caller zeroes G, or passes touched rows to agcf_zero_rows afterwards).
+ * Replaces: autograd of util/loss.py:5-9,25-29 + index_put_(accumulate) backward. */
+int agcf_bpr_backward(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
+                      int32_t nb, int32_t n_users, int32_t d, float reg, float scale,
+                      const float* out4, const float* coef,
+                      const int32_t* occ, const int32_t* seg_off, const int32_t* seg_node,
+                      const int32_t* n_seg, float* G, agcf_stream_t stream);
+
+/* G[seg_node[s],:] = 0 for s < *n_seg (undo of agcf_bpr_backward's writes) */
+int agcf_zero_rows(const int32_t* seg_node, const int32_t* n_seg, int32_t max_seg,
+                   float* G, int32_t d, agcf_stream_t stream);
+
+/* ------------------------------------------------------------------ optimizer
+ * torch.optim.Adam step (defaults: amsgrad=False, weight_decay=0, maximize=False)
+ * over n contiguous fp32 elements:
+ *   m += (g-m)*(1-b1); v = v*b2 + (1-b2)*g*g;
+ *   p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * t = *step_dev + 1 if step_dev (device int32, NOT modified) else step (>=1).
+ * Replaces: optimizer.step() of recommender/LightGCN.py:32-35,64 when the caller
+ * did not hand in its own optimizer. */
+int agcf_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n,
+                       float lr, float beta1, float beta2, float eps,
+                       int32_t step, const int32_t* step_dev, agcf_stream_t stream);
+int agcf_increment_i32(int32_t* counter, agcf_stream_t stream);
+
+/* ----------------------------------------------------------------- evaluation
+ * Full-rank scoring + masked top-K for n_u users (rows user_rows[0..n_u) of Uemb,
+ * or rows 0..n_u-1 if user_rows is null) against items [0,n_items) of Iemb:
+ *   s[u,i] = <Uemb[u,:], Iemb[i,:]>  (fp32, k ascending, fused multiply-add);
+ *   s[u, mask_items[mask_rowptr[u]..]] = -1e9;  top-K by the reference's rule
+ *   (util/algorithm.py:155-167 incl. its tie rule), output
+ *   sorted by (score desc, item asc).  item_offset is added to output ids (item
+ *   shards).  Stage 1 is a TF32 tcgen05 GEMM (impl=1) or an fp32 CUDA-core GEMM
+ *   (impl=0) that only emits per-32-item group maxima; stage 2 selects candidate
+ *   groups with a rigorous error margin; stage 3 re-scores candidates in exact
+ *   fp32 -- so the result does not depend on impl.
+ * Replaces: recommender/LightGCN.py:86-90 (predict) + :148-156 (test loop) +
+ * util/algorithm.py:155-167 (find_k_largest). */
+int64_t agcf_score_topk_ws_bytes(int32_t n_u, int32_t n_items, int32_t d, int32_t K);
+int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int32_t n_u,
+                    const float* Iemb, int32_t n_items, int32_t d,
+                    const int32_t* mask_rowptr, const int32_t* mask_items,
+                    int32_t K, int32_t item_offset, int32_t impl,
+                    float* out_val, int32_t* out_idx, int32_t* out_flags,
+                    void* ws, int64_t ws_bytes, agcf_stream_t stream);
+
+/* merge P per-shard top-K lists (vals/idx: [P, n_u, K]) into one, same ordering */
+int agcf_topk_merge(const float* vals, const int32_t* idx, int32_t P, int32_t n_u, int32_t K,
+                    float* out_val, int32_t* out_idx, agcf_stream_t stream);
+
+/* plain scores for a few users (predict): out[r,:] = Uemb[user_rows[r],:] . Iemb^T */
+int agcf_score_rows(const float* Uemb, const int32_t* user_rows, int32_t n_u,
+                    const float* Iemb, int32_t n_items, int32_t d, float* out, agcf_stream_t stream);
+
+/* per-user hits / DCG / IDCG for nc cutoffs from top-K ids and the (sorted) test
+ * CSR: out is [n_u, nc, 3] doubles (hits, dcg, idcg); inv_log[r] = 1/ln(r+2) is
+ * supplied by the host so that sums are bit-identical to math.log's.
+ * test_total[u] counts ALL test items of u incl. those unseen in train.
+ * Replaces: util/metrics.py:9-15 (hits), :72-85 (NDCG) per-user loops. */
+int agcf_rank_metrics(const int32_t* topk_idx, int32_t K, const int32_t* t_rowptr, const int32_t* t_items,
+                      const int32_t* test_total, int32_t n_u, const int32_t* cutoffs, int32_t nc,
+                      const double* inv_log, double* out, agcf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGCF_H_ */
