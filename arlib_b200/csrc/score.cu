@@ -276,7 +276,7 @@ template <int D>
 __global__ void __launch_bounds__(256) topk_select_kernel(const Stage2Params p) {
   __shared__ SelectSmem sel;
   __shared__ int warp_buf[9];
-  __shared__ float urow[D];
+  __shared__ __align__(16) float urow[D];
   __shared__ int sh_p_pos, sh_gp;
   extern __shared__ __align__(16) unsigned char dyn[];   // K-sized sort buffers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const Stage2Params p) 
 template <int D>
 __global__ void __launch_bounds__(256) score_rows_kernel(const float4* __restrict__ Uemb, const int32_t* __restrict__ user_rows,
                                                          const float4* __restrict__ Iemb, int n_items, float* __restrict__ out) {
-  __shared__ float urow[D];
+  __shared__ __align__(16) float urow[D];
   const int r = blockIdx.y;
   const int uid = user_rows != nullptr ? user_rows[r] : r;
   if (threadIdx.x < D / 4) reinterpret_cast<float4*>(urow)[threadIdx.x] = __ldg(Uemb + (size_t)uid * (D / 4) + threadIdx.x);

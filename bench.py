@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- LightGCN train triples/s (+ full-rank eval users/s) on synthetic
+Gowalla-shaped data, B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one BPR batch of 2048 triples through
+the whole hot path: L=3 propagation forward, fused loss, backward, Adam
+(recommender/LightGCN.py:47-64 of the reference).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: (users, items, edges, layers, d, batch)          BASELINE.json configs[1] = gowalla
+    "gowalla": (29858, 40981, 1027370, 3, 64, 2048),
+    "ml-100k": (943, 1682, 100000, 2, 64, 2048),
+    "yelp2018": (31668, 38048, 1561406, 2, 64, 2048),
+    "ml-1m": (6040, 3706, 1000209, 2, 64, 2048),
+    "amazon-book": (52643, 91599, 2984108, 3, 128, 2048),
+}
+LR, REG, TOPK = 0.005, 1e-4, 50
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------- data
+def make_data(name, alpha, seed=0):
+    from arlib_b200.util.synth import synth_edges
+    U, I, E, L, d, B = WORKLOADS[name]
+    cache = os.path.join("/tmp", "arlib_b200_synth_%s_%s_%d.npz" % (name, alpha, seed))
+    if os.path.exists(cache):
+        z = np.load(cache)
+        tu, ti, su, si = z["tu"], z["ti"], z["su"], z["si"]
+    else:
+        tu, ti, su, si = synth_edges(U, I, E, alpha, alpha, seed)
+        try:
+            np.savez(cache, tu=tu, ti=ti, su=su, si=si)
+        except OSError:
+            pass
+    return dict(U=U, I=I, E=E, L=L, d=d, B=B, tu=tu, ti=ti, su=su, si=si)
+
+
+def xavier_tables(U, I, d, seed=2018):
+    torch.manual_seed(seed)
+    ue = torch.nn.init.xavier_uniform_(torch.empty(U, d))
+    ie = torch.nn.init.xavier_uniform_(torch.empty(I, d))
+    return ue, ie
+
+
+def algorithmic_bytes(N, nnz, d, L, B):
+    """contract figures."""
+    T = N * d * 4
+    b_spmm = nnz * 8 + (N + 1) * 4 + 2 * T
+    b_step = 2 * L * b_spmm + 7 * T + 3 * B * d * 4 * (L + 1) * 2 + 24 * B
+    return b_spmm, b_step
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi-equivalent clock / throttle sampling through NVML during the timed region."""
+
+    def __init__(self, index=0, period=0.02):
+        self.samples, self.reasons, self.period, self.index = [], set(), period, index
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.max_mhz = None, None
+            log("NVML unavailable:", e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "display_clock": 0x100, "app_clocks": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------- CPU baseline leg
+def cpu_train_baseline(D, n_steps, n_warm):
+    """The oracle port of the reference's CPU torch path (oracle/ is used here ONLY as
+    the timed baseline): body of recommender/LightGCN.py:47-64 incl. the Python sampler
+    cost model (per-triple rejection sampling against the train set)."""
+    from oracle import port
+    U, I, L, d, B = D["U"], D["I"], D["L"], D["d"], D["B"]
+    adj = port.bipartite_adjacency(D["tu"], D["ti"], U, I)
+    norm = port.normalize_graph_mat(adj)
+    ue, ie = xavier_tables(U, I, d)
+    tr = port.LightGCNTrainer(norm, ue, ie, L, LR, REG)
+    rng = np.random.default_rng(1)
+    train_sets = None
+
+    def batch(k):
+        sl = slice((k * B) % (D["E"] - B), (k * B) % (D["E"] - B) + B)
+        u, i = D["tu"][sl], D["ti"][sl]
+        j = rng.integers(0, I, B)
+        return u.tolist(), i.tolist(), j.tolist()
+
+    for k in range(n_warm):
+        tr.step(*batch(k))
+    t0 = time.perf_counter()
+    for k in range(n_steps):
+        tr.step(*batch(n_warm + k))
+    dt = time.perf_counter() - t0
+    return n_steps * B / dt, dt / n_steps
+
+
+def cpu_eval_baseline(D, n_users=300):
+    from oracle import port
+    U, I, d = D["U"], D["I"], D["d"]
+    ue, ie = xavier_tables(U, I, d)
+    users = np.unique(D["su"])[:n_users]
+    data = port.ArrayEvalData(U, I, D["tu"], D["ti"], D["su"], D["si"], users)
+    port.find_k_largest(TOPK, np.random.rand(I).astype(np.float32))       # numba JIT warm-up
+    names = [str(int(u)) for u in users]
+    t0 = time.perf_counter()
+    port.full_rank_test(data, ue, ie, TOPK, [TOPK], users=names)
+    return len(names) / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation (oracle port; the Python
+    reference cannot travel to the GPU box) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    D = make_data(args.workload, args.alpha)
+    cap = max(1, min(args.steps, 40))
+    warm = max(1, min(args.warmup, 2))
+    tps, s_per_step = cpu_train_baseline(D, cap, warm)
+    ups = cpu_eval_baseline(D)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "LightGCN train triples/s", "value": tps, "unit": "triples/s",
+        "n_gpus": args.gpus, "steps": cap, "warmup": warm, "ms_per_step": s_per_step * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(args, D),
+        "cpu_baseline": {"value": tps, "unit": "triples/s", "cores": cores, "kind": "port",
+                         "sample": "%d full-graph training steps of %d triples (oracle/port.py LightGCNTrainer, torch CPU, "
+                                   "%d threads); eval %d users" % (cap, D["B"], cores, 300)},
+        "e2e": {"value": tps, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "eval": {"users_per_s": ups, "unit": "users/s"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_of(args, D):
+    return {"workload": "LightGCN %d-layer d=%d BPR batch %d, synthetic %s shape %dx%d, %d edges, power-law alpha=%s"
+                        % (D["L"], D["d"], D["B"], args.workload, D["U"], D["I"], D["E"], args.alpha),
+            "lr": LR, "reg": REG, "topK": TOPK, "sampler": "device-philox",
+            "l2": "per-step working set (10 tables + CSR, ~%.0f MB) exceeds the 126 MB L2; steady-state loop, no flush"
+                  % ((10 * (D["U"] + D["I"]) * D["d"] * 4 + 2 * D["E"] * 8) / 1e6)}
+
+
+# --------------------------------------------------------------------------- ours
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; arlib_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from arlib_b200 import ops
+    from arlib_b200.engine import DeviceTrainSet, LightGCNEngine
+    from arlib_b200.evaluator import FullRankEvaluator
+    from arlib_b200.graph import DeviceGraph
+    import scipy.sparse as sp
+
+    D = make_data(args.workload, args.alpha)
+    U, I, E, L, d, B = D["U"], D["I"], D["E"], D["L"], D["d"], D["B"]
+    N = U + I
+    half = sp.csr_matrix((np.ones(E, dtype=np.float32), (D["tu"], D["ti"] + U)), shape=(N, N), dtype=np.float32)
+    adj = half + half.T
+    g = DeviceGraph.from_dataloader_adj(adj, dev)
+    ue, ie = xavier_tables(U, I, d)
+    table = torch.cat([ue, ie]).to(dev)
+    ts = DeviceTrainSet.from_arrays(D["tu"], D["ti"], U, I, dev)
+    eng = LightGCNEngine(g, table, U, L, LR, REG, B, E)
+    K, W = args.steps, max(args.warmup, 3)
+    nb_epoch = (E + B - 1) // B
+    full_batches = E // B
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    if world > 1:
+        raise SystemExit("multi-GPU row-partitioned path: see arlib_b200/dist.py (bench wiring pending)")
+
+    # ---- device-resident throughput: K steps replayed from CUDA graphs of <= one epoch each
+    eng.sample_epoch(ts, 2018, 0)
+    chunks = []
+    left, first = K, 0
+    while left > 0:                                   # steps cycle through the epoch's full batches
+        n = min(left, full_batches - first)
+        chunks.append((first, n))
+        left -= n
+        first = (first + n) % full_batches
+    for k in range(W):
+        eng.run_steps(k % full_batches, 1, use_graph=False)
+    for c in set(chunks):
+        eng.run_steps(c[0], c[1], use_graph=True)     # capture + one replay (warm)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for c in chunks:
+            eng.run_steps(c[0], c[1], use_graph=True)
+        e1.record()
+        barrier()
+        # keep the GPU under the same load while NVML gets enough samples (not timed)
+        t_end = time.time() + 0.6
+        while time.time() < t_end:
+            eng.run_steps(chunks[0][0], chunks[0][1], use_graph=True)
+            torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = K * B / (ms * 1e-3)
+    loss_last = float(eng.out4[chunks[-1][0] + chunks[-1][1] - 1, 0])
+
+    # ---- per-kernel live timing of the dominant kernel (SpMM) inside eager steps
+    spmm_ms = []
+    orig = ops.spmm
+
+    def timed_spmm(*a, **k):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(); orig(*a, **k); a1.record()
+        spmm_ms.append((a0, a1))
+
+    import arlib_b200.engine as engmod
+    engmod.ops.spmm = timed_spmm
+    try:
+        for k in range(min(K, 50)):
+            eng.run_steps(k % full_batches, 1, use_graph=False)
+    finally:
+        engmod.ops.spmm = orig
+    torch.cuda.synchronize()
+    spmm_avg_ms = float(np.mean([a.elapsed_time(b) for a, b in spmm_ms]))
+    b_spmm, b_step = algorithmic_bytes(N, g.nnz, d, L, B)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    achieved = b_spmm / (spmm_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    roofline = {"kernel": "spmm_csr_kernel<64,false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": b_spmm, "avg_launch_ms": spmm_avg_ms,
+                "launches_per_step": 2 * L, "step_algorithmic_bytes": b_step,
+                "step_frac_of_hbm_roofline": (b_step / (ms / K * 1e-3) / 1e9) / peak,
+                "note": "table (%.1f MB) is L2-resident: the binding resource is L2->SM gather bandwidth "
+                        "(nnz*(8+4d) = %.0f MB per launch), see DESIGN.md" % (N * d * 4 / 1e6, g.nnz * (8 + 4 * d) / 1e6)}
+
+    # ---- end to end through the public step API with HOST triples (pinned), loss read back
+    tu_h = [torch.empty((3, B), dtype=torch.int32).pin_memory() for _ in range(4)]
+    rng = np.random.default_rng(5)
+    for t in tu_h:
+        sl = int(rng.integers(0, E - B))
+        t[0].copy_(torch.from_numpy(D["tu"][sl:sl + B].astype(np.int32)))
+        t[1].copy_(torch.from_numpy(D["ti"][sl:sl + B].astype(np.int32)))
+        t[2].copy_(torch.from_numpy(rng.integers(0, I, B).astype(np.int32)))
+    loss_host = torch.empty((max(K, 1), 4), dtype=torch.float32).pin_memory()
+    for k in range(W):
+        eng.step_external(tu_h[k % 4], B)
+    barrier()
+    e0.record()
+    for k in range(K):
+        row = eng.step_external(tu_h[k % 4], B)
+        loss_host[k].copy_(row, non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    e2e = {"value": K * B / (e2e_ms * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": 3 * B * 4,
+           "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / K,
+           "api": "LightGCNEngine.step_external (host pinned triples -> H2D -> grouping -> step kernels -> loss D2H)"}
+
+    # ---- full-rank evaluation (users/s)
+    ev = FullRankEvaluator.from_arrays(U, I, D["tu"], D["ti"], D["su"], D["si"], dev)
+    F = eng.forward_table().clone()
+    n_test = ev.user_rows.numel()
+    for _ in range(2):
+        vals, idx = ev.topk(F[:U], F[U:], TOPK)
+    barrier()
+    e0.record()
+    reps = 3
+    for _ in range(reps):
+        vals, idx = ev.topk(F[:U], F[U:], TOPK)
+        per = ev.per_user_metrics(idx, [TOPK])
+    e1.record()
+    barrier()
+    ev_ms = e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    vals, idx = ev.topk(F[:U], F[U:], TOPK)
+    measure = ev.measure(idx, [TOPK])
+    idx_host = idx.cpu()
+    torch.cuda.synchronize()
+    ev_e2e_s = time.perf_counter() - t0
+    flops = 2.0 * n_test * I * d
+    tpeak = peaks.get("bf16_tflops", 1590.0)
+    evald = {"users_per_s": n_test / (ev_ms * 1e-3), "unit": "users/s", "n_users": n_test, "ms": ev_ms,
+             "e2e_users_per_s": n_test / ev_e2e_s, "impl": int(os.environ.get("ARLIB_B200_SCORE_IMPL", "0")),
+             "roofline": {"bound": "tensor", "achieved": flops / (ev_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                          "frac": flops / (ev_ms * 1e-3) / 1e12 / tpeak, "traffic": None,
+                          "note": "whole eval pipeline (mask bits + group-max GEMM + select/rescore + metrics)"},
+             "measure": [m.strip() for m in measure]}
+
+    line = {
+        "metric": "LightGCN train triples/s", "value": value, "unit": "triples/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config_of(args, D),
+        "roofline": roofline, "e2e": e2e, "eval": evald, "clocks": clk.summary(),
+        "gpu_launches": K * eng.launches_per_step, "last_loss": loss_last,
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = torch.get_num_threads()
+        tps, _ = cpu_train_baseline(D, 8, 2)
+        ups = cpu_eval_baseline(D)
+        line["cpu_baseline"] = {"value": tps, "unit": "triples/s", "cores": cores, "kind": "port",
+                                "eval_users_per_s": ups,
+                                "sample": "2 warm-up + 8 timed full-graph training steps of %d triples and a 300-user "
+                                          "full-rank eval with oracle/port.py (torch CPU, %d threads)" % (B, cores)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gowalla", choices=sorted(WORKLOADS))
+    ap.add_argument("--alpha", type=float, default=0.5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

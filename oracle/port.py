@@ -408,3 +408,33 @@ def adjacency_value_grad(norm_adj, user_emb, item_emb, n_layers, loss_fn):
     g = torch.autograd.grad(loss, adj)[0].coalesce()
     idx = g.indices().numpy()
     return idx[0], idx[1], g.values().numpy()
+
+
+# --------------------------------------------------------------------------
+# array-backed data shim (bench.py cpu_baseline: no string dicts for 1M edges)
+# --------------------------------------------------------------------------
+class ArrayEvalData:
+    """The attributes full_rank_test() reads, for a SAMPLE of test users, built
+    from integer arrays (names = str(id)).  Same code path as PortData for the
+    per-user loop of recommender/LightGCN.py:148-156."""
+
+    def __init__(self, user_num, item_num, train_u, train_i, test_u, test_i, users):
+        self.user_num, self.item_num = user_num, item_num
+        self.item = {str(k): k for k in range(item_num)}
+        self.id2item = {k: str(k) for k in range(item_num)}
+        self.user = {str(int(u)): int(u) for u in users}
+        self.training_set_u = defaultdict(dict)
+        self.test_set = defaultdict(dict)
+        keep = np.isin(train_u, users)
+        for u, i in zip(train_u[keep].tolist(), train_i[keep].tolist()):
+            self.training_set_u[str(u)][str(i)] = 1.0
+        keep = np.isin(test_u, users)
+        for u, i in zip(test_u[keep].tolist(), test_i[keep].tolist()):
+            self.test_set[str(u)][str(i)] = 1.0
+
+    def get_user_id(self, u):
+        return self.user.get(u)
+
+    def user_rated(self, u):
+        d = self.training_set_u[u]
+        return list(d.keys()), list(d.values())

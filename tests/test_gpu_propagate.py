@@ -1,0 +1,208 @@
+"""GPU parity: adjacency normalization (bit-exact), SpMM + fused epilogues, SDDMM,
+encoders forward/backward -- against oracle/port.py on the same inputs."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand_graph(U, I, E, seed, hub=0):
+    rng = np.random.default_rng(seed)
+    u = rng.integers(0, U, E)
+    i = rng.integers(0, I, E)
+    if hub:                                   # one very long row (> long-row threshold) per side
+        u[:hub] = 0
+        i[:hub] = rng.permutation(I)[:hub] if hub <= I else rng.integers(0, I, hub)
+        i[hub:2 * hub] = 1
+        u[hub:2 * hub] = rng.permutation(U)[:hub] if hub <= U else rng.integers(0, U, hub)
+    key = np.unique(u.astype(np.int64) * I + i)
+    return key // I, key % I
+
+
+def test_norm_adj_bit_exact_golden(golden):
+    from arlib_b200.graph import DeviceGraph
+    U, I = golden["user_names"].shape[0], golden["item_names"].shape[0]
+    adj = port.bipartite_adjacency(golden["train_u"].astype(np.int64), golden["train_i"].astype(np.int64), U, I)
+    g = DeviceGraph.from_dataloader_adj(adj, _dev())
+    assert np.array_equal(g.rowptr.cpu().numpy(), golden["adj_indptr"])
+    assert np.array_equal(g.col.cpu().numpy(), golden["adj_indices"])
+    assert np.array_equal(g.val.cpu().numpy().view(np.uint32), golden["adj_data"].view(np.uint32))
+    g2 = DeviceGraph.from_ui_adj(adj, _dev())
+    coo = g2.to_coo_tensor()
+    assert np.array_equal(coo.indices()[0].cpu().numpy(), golden["uiadj_row"])
+    assert np.array_equal(coo.indices()[1].cpu().numpy(), golden["uiadj_col"])
+    assert np.array_equal(g2.val.cpu().numpy().view(np.uint32), golden["uiadj_data"].view(np.uint32))
+
+
+def test_norm_adj_fractional_weights_bit_exact():
+    """PGA writes rand() / 1e-7 weights (attack/White/PGA.py:73,139)."""
+    from arlib_b200.graph import DeviceGraph
+    rng = np.random.default_rng(5)
+    U, I = 50, 70
+    u, i = _rand_graph(U, I, 600, 1)
+    w = rng.random(u.shape[0]).astype(np.float32)
+    w[::7] = 1e-7
+    n = U + I
+    half = sp.csr_matrix((w, (u, i + U)), shape=(n, n), dtype=np.float32)
+    adj = half + half.T
+    ref = port.to_torch_coo(port.init_uiadj_norm(adj)).coalesce()
+    g = DeviceGraph.from_ui_adj(adj, _dev())
+    assert np.array_equal(g.val.cpu().numpy().view(np.uint32), ref.values().numpy().view(np.uint32))
+
+
+@pytest.mark.parametrize("d", [32, 64, 128, 256])
+@pytest.mark.parametrize("hub", [0, 700])
+def test_spmm_matches_oracle(d, hub):
+    from arlib_b200 import ops
+    from arlib_b200.graph import DeviceGraph
+    U, I = 900, 1100
+    u, i = _rand_graph(U, I, 20000, 2, hub)
+    adj = port.bipartite_adjacency(u, i, U, I)
+    norm = port.normalize_graph_mat(adj)
+    g = DeviceGraph.from_dataloader_adj(adj, _dev())
+    if hub:
+        assert g.n_long >= 2
+    X = torch.randn(U + I, d)
+    ref = torch.sparse.mm(port.to_torch_coo(norm), X)
+    Xd = X.to(_dev())
+    Y = torch.empty_like(Xd)
+    ops.spmm(g, Xd, Y=Y)
+    torch.testing.assert_close(Y.cpu(), ref, rtol=1e-5, atol=1e-6)
+    # fused epilogue: addend, running sum, mean division
+    add = torch.randn(U + I, d)
+    acc = torch.randn(U + I, d)
+    accd = acc.to(_dev())
+    Y2 = torch.empty_like(Xd)
+    ops.spmm(g, Xd, Y=Y2, addend=add.to(_dev()), acc_in=accd, acc_out=accd, acc_div=3.0)
+    torch.testing.assert_close(Y2.cpu(), ref + add, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(accd.cpu(), (acc + ref + add) / 3.0, rtol=1e-5, atol=1e-6)
+    # acc only (no Y), identity row order == degree order result
+    out = torch.empty_like(Xd)
+    ops.spmm(g, Xd, acc_out=out)
+    assert torch.equal(out, Y)
+
+
+def test_spmm_noise_epilogue_matches_simgcl_lines():
+    from arlib_b200 import ops
+    from arlib_b200.graph import DeviceGraph
+    U, I, d = 300, 500, 64
+    u, i = _rand_graph(U, I, 6000, 3, 400)
+    adj = port.bipartite_adjacency(u, i, U, I)
+    g = DeviceGraph.from_dataloader_adj(adj, _dev())
+    X = torch.randn(U + I, d)
+    noise = torch.rand(U + I, d)
+    ego = torch.sparse.mm(port.to_torch_coo(port.normalize_graph_mat(adj)), X)
+    ref = ego + torch.sign(ego) * torch.nn.functional.normalize(noise, dim=-1) * 0.1
+    Y = torch.empty(U + I, d, device=_dev())
+    ops.spmm(g, X.to(_dev()), Y=Y, noise=noise.to(_dev()), eps=0.1)
+    torch.testing.assert_close(Y.cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("d", [32, 64, 128])
+def test_sddmm_matches_pattern_masked_products(d):
+    from arlib_b200 import ops
+    from arlib_b200.graph import DeviceGraph
+    U, I = 200, 300
+    u, i = _rand_graph(U, I, 4000, 4, 280)
+    adj = port.bipartite_adjacency(u, i, U, I)
+    g = DeviceGraph.from_dataloader_adj(adj, _dev())
+    H, E = torch.randn(U + I, d), torch.randn(U + I, d)
+    coo = port.normalize_graph_mat(adj).tocoo()
+    csr = port.normalize_graph_mat(adj).tocsr(); csr.sort_indices(); coo = csr.tocoo()
+    ref = (H[coo.row] * E[coo.col]).sum(1)
+    gval = torch.zeros(g.nnz, device=_dev())
+    ops.sddmm(g, H.to(_dev()), E.to(_dev()), gval)
+    torch.testing.assert_close(gval.cpu(), ref, rtol=1e-4, atol=1e-5)
+    ops.sddmm(g, H.to(_dev()), E.to(_dev()), gval, accumulate=True)
+    torch.testing.assert_close(gval.cpu(), 2 * ref, rtol=1e-4, atol=1e-5)
+
+
+class _Data:
+    def __init__(self, U, I, u, i):
+        self.user_num, self.item_num = U, I
+        self.ui_adj = port.bipartite_adjacency(u, i, U, I)
+        self.norm_adj = port.normalize_graph_mat(self.ui_adj)
+
+
+def _loss(fu, fi):
+    w_u = torch.linspace(-1, 1, fu.shape[1], device=fu.device)
+    return (fu * w_u).sum() * 0.01 + (fi ** 2).sum() * 0.5 + (fu[:7] @ fi[:9].T).sum()
+
+
+@pytest.mark.parametrize("L", [1, 2, 3])
+def test_lightgcn_encoder_forward_backward_and_adjacency_grad(L):
+    from arlib_b200.encoder import LGCN_Encoder
+    U, I, d = 120, 150, 64
+    u, i = _rand_graph(U, I, 2500, 6)
+    data = _Data(U, I, u, i)
+    torch.manual_seed(0)
+    enc = LGCN_Encoder(data, d, L)
+    ue = enc.embedding_dict['user_emb'].detach().cpu().clone().requires_grad_(True)
+    ie = enc.embedding_dict['item_emb'].detach().cpu().clone().requires_grad_(True)
+    adj = port.to_torch_coo(data.norm_adj).coalesce().requires_grad_(True)
+    ru, ri = port.lightgcn_forward(adj, ue, ie, L)
+    _loss(ru, ri).backward()
+    enc.sparse_norm_adj.requires_grad = True
+    fu, fi = enc()
+    torch.testing.assert_close(fu.detach().cpu(), ru.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(fi.detach().cpu(), ri.detach(), rtol=1e-5, atol=1e-6)
+    _loss(fu, fi).backward()
+    torch.testing.assert_close(enc.embedding_dict['user_emb'].grad.cpu(), ue.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(enc.embedding_dict['item_emb'].grad.cpu(), ie.grad, rtol=1e-4, atol=1e-5)
+    ga = enc.sparse_norm_adj.grad.coalesce()
+    gr = adj.grad.coalesce()
+    assert torch.equal(ga.indices().cpu(), gr.indices())
+    torch.testing.assert_close(ga.values().cpu(), gr.values(), rtol=1e-4, atol=1e-5)
+
+
+def test_simgcl_xsimgcl_ngcf_encoders_match_oracle():
+    from arlib_b200.encoder import NGCF_Encoder, SimGCL_Encoder, XSimGCL_Encoder
+    U, I, d = 100, 140, 64
+    u, i = _rand_graph(U, I, 2000, 7)
+    data = _Data(U, I, u, i)
+    adj = port.to_torch_coo(data.norm_adj)
+    noises = [torch.rand(U + I, d) for _ in range(2)]
+    src = lambda k, like: noises[k].to(like.device)
+    for cls, fwd in ((SimGCL_Encoder, "sim"), (XSimGCL_Encoder, "xsim")):
+        torch.manual_seed(1)
+        enc = cls(data, d, 0.1, 2) if fwd == "sim" else cls(data, d, 0.1, 2, 1)
+        enc.noise_source = src
+        ue = enc.embedding_dict['user_emb'].detach().cpu().clone().requires_grad_(True)
+        ie = enc.embedding_dict['item_emb'].detach().cpu().clone().requires_grad_(True)
+        if fwd == "sim":
+            ref = port.simgcl_forward(adj, ue, ie, 2, 0.1, noises)
+        else:
+            ref = port.xsimgcl_forward(adj, ue, ie, 2, 0.1, 1, noises)
+        got = enc(True)
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            torch.testing.assert_close(a.detach().cpu(), b.detach(), rtol=1e-5, atol=1e-6)
+        lr = sum(_loss(ref[k], ref[k + 1]) for k in range(0, len(ref), 2))
+        lg = sum(_loss(got[k], got[k + 1]) for k in range(0, len(got), 2))
+        lr.backward(); lg.backward()
+        torch.testing.assert_close(enc.embedding_dict['user_emb'].grad.cpu(), ue.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(enc.embedding_dict['item_emb'].grad.cpu(), ie.grad, rtol=1e-4, atol=1e-5)
+        # unperturbed pass
+        clean = enc(False)
+        rclean = port.simgcl_forward(adj, ue.detach(), ie.detach(), 2, 0.1, None)
+        torch.testing.assert_close(clean[0].detach().cpu(), rclean[0], rtol=1e-5, atol=1e-6)
+    torch.manual_seed(2)
+    enc = NGCF_Encoder(data, d, 2)
+    ue = enc.embedding_dict['user_emb'].detach().cpu().clone().requires_grad_(True)
+    ie = enc.embedding_dict['item_emb'].detach().cpu().clone().requires_grad_(True)
+    w1 = [enc.W['w1_%d' % k].detach().cpu().clone().requires_grad_(True) for k in range(2)]
+    w2 = [enc.W['w2_%d' % k].detach().cpu().clone().requires_grad_(True) for k in range(2)]
+    ref = port.ngcf_forward(adj, ue, ie, w1, w2)
+    got = enc()
+    torch.testing.assert_close(got[0].detach().cpu(), ref[0].detach(), rtol=1e-4, atol=1e-5)
+    _loss(*ref).backward(); _loss(*got).backward()
+    torch.testing.assert_close(enc.embedding_dict['item_emb'].grad.cpu(), ie.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(enc.W['w2_1'].grad.cpu(), w2[1].grad, rtol=1e-3, atol=1e-4)

@@ -1,0 +1,164 @@
+"""GPU parity: fused scoring + masked top-K (+ tie rule, merge, predict, metrics)
+against find_k_largest / ranking_evaluation of the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from _util import assert_topk_matches
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _mask_csr(U, lists):
+    rp = np.zeros(U + 1, dtype=np.int32)
+    rp[1:] = np.cumsum([len(x) for x in lists])
+    flat = np.concatenate([np.sort(np.asarray(x, dtype=np.int32)) for x in lists]) if rp[-1] else np.zeros(1, np.int32)
+    return torch.from_numpy(rp).to(DEV), torch.from_numpy(flat.astype(np.int32)).to(DEV)
+
+
+@pytest.mark.parametrize("U,I,d,K", [(70, 1000, 64, 50), (130, 333, 32, 10), (64, 4100, 128, 50), (5, 31, 64, 3),
+                                      (33, 2049, 256, 100)])
+def test_topk_exact_scores_and_sets(U, I, d, K):
+    from arlib_b200 import ops
+    rng = np.random.default_rng(U + I)
+    ue = torch.randn(U, d)
+    ie = torch.randn(I, d)
+    lists = [rng.choice(I, size=int(rng.integers(0, min(I - K, 60))), replace=False) for _ in range(U)]
+    mrp, mit = _mask_csr(U, lists)
+    vals, idx = ops.score_topk(ue.to(DEV), ie.to(DEV), K, mask_rowptr=mrp, mask_items=mit, impl=0)
+    vals, idx = vals.cpu().numpy(), idx.cpu().numpy()
+    exact = ops.score_rows(ue.to(DEV), torch.arange(U, dtype=torch.int32, device=DEV), ie.to(DEV)).cpu().numpy()
+    ref = (ue.double() @ ie.double().T).numpy()
+    assert np.abs(exact - ref).max() < 1e-4
+    for r in range(U):
+        s = exact[r].copy()
+        s[lists[r]] = -10e8
+        # against the device's own exact fp32 scores the selection must be THE reference set
+        assert set(idx[r].tolist()) == port.topk_reference_set(K, s)
+        assert np.array_equal(vals[r], s[idx[r]])
+        assert np.all(np.diff(vals[r]) <= 0)
+        # and against float64 scores it is a valid top-K up to fp32 rounding
+        s64 = ref[r].copy(); s64[lists[r]] = -10e8
+        assert_topk_matches(idx[r], s64, K, 1e-4)
+
+
+def test_topk_tie_rule_kat():
+    """Heavy exact ties: integer-valued embeddings make many scores identical; the set
+    must follow the reference heap's rule, not lowest/highest-id-first."""
+    from arlib_b200 import ops
+    rng = np.random.default_rng(7)
+    U, I, d, K = 40, 200, 32, 20
+    ue = torch.from_numpy(rng.integers(0, 2, (U, d)).astype(np.float32))
+    ie = torch.from_numpy(rng.integers(0, 2, (I, d)).astype(np.float32))
+    lists = [rng.choice(I, size=5, replace=False) for _ in range(U)]
+    mrp, mit = _mask_csr(U, lists)
+    vals, idx = ops.score_topk(ue.to(DEV), ie.to(DEV), K, mask_rowptr=mrp, mask_items=mit)
+    scores = (ue @ ie.T).numpy()
+    differs_from_lowest_first = 0
+    for r in range(U):
+        s = scores[r].copy(); s[lists[r]] = -10e8
+        heap_ids, _ = port.find_k_largest_py(K, s)
+        assert set(idx[r].cpu().tolist()) == set(heap_ids)
+        lowest_first = set(np.argsort(-s, kind="stable")[:K].tolist())
+        differs_from_lowest_first += set(heap_ids) != lowest_first
+    assert differs_from_lowest_first > 0          # the KAT really exercises the odd rule
+
+
+def test_topk_more_masked_than_free_and_k_ge_items():
+    from arlib_b200 import ops
+    U, I, d = 3, 40, 64
+    ue, ie = torch.randn(U, d), torch.randn(I, d)
+    lists = [np.arange(35), np.arange(0), np.arange(5, 40)]       # user 0 / 2: only 5 free items, K = 8
+    mrp, mit = _mask_csr(U, lists)
+    vals, idx = ops.score_topk(ue.to(DEV), ie.to(DEV), 8, mask_rowptr=mrp, mask_items=mit)
+    scores = ops.score_rows(ue.to(DEV), torch.arange(U, dtype=torch.int32, device=DEV), ie.to(DEV)).cpu().numpy()
+    for r in range(U):
+        s = scores[r].copy(); s[lists[r]] = -10e8
+        ids, _ = port.find_k_largest_py(8, s)
+        assert set(idx[r].cpu().tolist()) == set(ids)
+    vals, idx = ops.score_topk(ue.to(DEV), ie.to(DEV), 64)          # K > I: all items, then -1 padding
+    assert sorted(idx[1].cpu().tolist()[:I]) == list(range(I)) and set(idx[1].cpu().tolist()[I:]) == {-1}
+
+
+def test_golden_topk_sets_and_metric_strings(golden, golden_rows):
+    """The reference's own top-50 lists and metric strings on ml-100k (frozen)."""
+    from arlib_b200.evaluator import FullRankEvaluator
+    from arlib_b200.util.DataLoader import DataLoader
+    train, test = golden_rows
+    data = DataLoader.from_rows([list(r) for r in train], (), test)
+    ev = FullRankEvaluator(data, torch.device(DEV))
+    fu = torch.from_numpy(golden["final_user_emb"]).to(DEV)
+    fi = torch.from_numpy(golden["final_item_emb"]).to(DEV)
+    vals, idx = ev.topk(fu, fi, 50)
+    assert [int(u) for u in ev.users] == golden["topk_users"].tolist()
+    names = golden["item_names"]
+    scores = golden["final_user_emb"] @ golden["final_item_emb"].T
+    near_ties = 0
+    for k in range(idx.shape[0]):
+        got = set(names[idx[k].cpu().numpy()].tolist())
+        want = set(golden["topk_items"][k].tolist())
+        if got != want:
+            # only legal if the reference's own K-th / (K+1)-th scores are within fp32 rounding
+            near_ties += 1
+            diff = got ^ want
+            ids = [int(np.flatnonzero(names == n)[0]) for n in diff]
+            uid = data.user[ev.users[k]]
+            sc = scores[uid][ids]
+            assert np.ptp(sc) < 1e-6, "top-50 set differs beyond rounding for user %s" % ev.users[k]
+    assert near_ties == 0, "boundary near-ties on the golden fixture: %d" % near_ties
+    measure = ev.measure(idx, [50])
+    want = [str(x) for x in golden["measure"]]
+    assert measure[0] == want[0]
+    for a, b in zip(measure[1:], want[1:]):
+        ka, va = a.strip().split(":"); kb, vb = b.strip().split(":")
+        assert ka == kb and abs(float(va) - float(vb)) < 1e-3
+    assert measure[1:4] == want[1:4]              # hit ratio / precision / recall are integer-derived: exact strings
+
+
+def test_topk_merge_matches_unsharded():
+    from arlib_b200 import ops
+    U, I, d, K = 50, 900, 64, 25
+    ue, ie = torch.randn(U, d).to(DEV), torch.randn(I, d).to(DEV)
+    full_v, full_i = ops.score_topk(ue, ie, K)
+    parts_v, parts_i = [], []
+    for lo, hi in ((0, 300), (300, 600), (600, 900)):
+        v, i = ops.score_topk(ue, ie[lo:hi].contiguous(), K, item_offset=lo)
+        parts_v.append(v); parts_i.append(i)
+    mv, mi = ops.topk_merge(torch.stack(parts_v), torch.stack(parts_i))
+    assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
+
+
+def test_rank_metrics_match_ranking_evaluation():
+    from arlib_b200 import ops
+    import math
+    rng = np.random.default_rng(3)
+    U, I, K = 60, 400, 50
+    idx = np.stack([rng.permutation(I)[:K] for _ in range(U)]).astype(np.int32)
+    origin, res = {}, {}
+    t_lists, totals = [], []
+    for r in range(U):
+        seen = rng.choice(I, size=int(rng.integers(1, 30)), replace=False)
+        unseen = int(rng.integers(0, 3))
+        origin[str(r)] = {str(i): 1.0 for i in seen}
+        for x in range(unseen):
+            origin[str(r)]["unseen%d" % x] = 1.0
+        res[str(r)] = [(str(i), 0.0) for i in idx[r]]
+        t_lists.append(np.sort(seen).astype(np.int32)); totals.append(len(seen) + unseen)
+    rp = np.zeros(U + 1, dtype=np.int32); rp[1:] = np.cumsum([len(x) for x in t_lists])
+    cut = [10, 50]
+    inv_log = torch.tensor([1.0 / math.log(r + 2) for r in range(K)], dtype=torch.float64, device=DEV)
+    out = ops.rank_metrics(torch.from_numpy(idx).to(DEV), torch.from_numpy(rp).to(DEV),
+                           torch.from_numpy(np.concatenate(t_lists)).to(DEV),
+                           torch.tensor(totals, dtype=torch.int32, device=DEV),
+                           torch.tensor(cut, dtype=torch.int32, device=DEV), inv_log).cpu().numpy()
+    want = port.ranking_evaluation(origin, res, cut)
+    for c, n in enumerate(cut):
+        hits = out[:, c, 0]
+        hr = hits.sum() / sum(totals)
+        ndcg = 0
+        for r in range(U):
+            ndcg += out[r, c, 1] / out[r, c, 2]
+        assert want[5 * c + 1] == 'Hit Ratio:' + str(hr) + '\n'
+        assert want[5 * c + 4] == 'NDCG:' + str(ndcg / U) + '\n'
