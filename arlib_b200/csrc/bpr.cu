@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(1024) bpr_group_kernel(const int32_t* __restri
                                                          const int32_t* __restrict__ j, int n_triples, int batch,
                                                          int n_users, int pow2, int32_t* __restrict__ occ,
                                                          int32_t* __restrict__ seg_off, int32_t* __restrict__ seg_node,
-                                                         int32_t* __restrict__ n_seg) {
+                                                         int32_t* __restrict__ n_seg, int mask_words,
+                                                         uint32_t* __restrict__ node_mask) {
   extern __shared__ unsigned long long keys[];
   __shared__ int warp_tot[32];
   __shared__ int block_total;
@@ -98,6 +99,9 @@ __global__ void __launch_bounds__(1024) bpr_group_kernel(const int32_t* __restri
   const int nb = min(batch, n_triples - t0);
   const int n_occ = 3 * nb;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  uint32_t* mask_b = node_mask != nullptr ? node_mask + (size_t)b * mask_words : nullptr;
+  if (mask_b != nullptr)
+    for (int k = tid; k < mask_words; k += nthr) mask_b[k] = 0u;      // visible block-wide after the sort's barriers
   for (int k = tid; k < pow2; k += nthr) {
     unsigned long long key = ~0ull;
     if (k < n_occ) {
@@ -163,6 +167,7 @@ __global__ void __launch_bounds__(1024) bpr_group_kernel(const int32_t* __restri
     if (k == 0 || node != (uint32_t)(keys[k - 1] >> 32)) {
       off_b[seg] = k;
       node_b[seg] = (int32_t)node;
+      if (mask_b != nullptr) atomicOr(mask_b + (node >> 5), 1u << (node & 31));
       ++seg;
     }
   }
@@ -400,8 +405,9 @@ extern "C" int agcf_bpr_sample_epoch(const int32_t* e_user, const int32_t* e_ite
 extern "C" int agcf_bpr_group_batches(const int32_t* u, const int32_t* i, const int32_t* j,
                                       int32_t n_triples, int32_t batch, int32_t n_users,
                                       int32_t* occ, int32_t* seg_off, int32_t* seg_node, int32_t* n_seg,
-                                      agcf_stream_t stream) {
+                                      int32_t n_nodes, uint32_t* node_mask, agcf_stream_t stream) {
   if (!u || !i || !j || !occ || !seg_off || !seg_node || !n_seg || n_triples < 0 || batch <= 0 || n_users < 0) return AGCF_EINVAL;
+  if (node_mask != nullptr && n_nodes <= 0) return AGCF_EINVAL;
   if (n_triples == 0) return AGCF_OK;
   if (3 * (long long)batch > 16384) return AGCF_EUNSUPPORTED;
   int pow2 = 1024;
@@ -414,7 +420,7 @@ extern "C" int agcf_bpr_group_batches(const int32_t* u, const int32_t* i, const 
   }
   const unsigned blocks = (unsigned)((n_triples + batch - 1) / batch);
   bpr_group_kernel<<<blocks, 1024, smem, (cudaStream_t)stream>>>(u, i, j, n_triples, batch, n_users, pow2,
-                                                                 occ, seg_off, seg_node, n_seg);
+                                                                 occ, seg_off, seg_node, n_seg, (n_nodes + 31) / 32, node_mask);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
 }

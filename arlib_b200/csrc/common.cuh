@@ -61,6 +61,20 @@ __device__ __forceinline__ void fma4(float4& acc, float a, const float4& x) {
   acc.z = fmaf(a, x.z, acc.z);
   acc.w = fmaf(a, x.w, acc.w);
 }
+// packed fp32x2 FMA (sm_100 FFMA2): two IEEE fused multiply-adds per instruction --
+// bit-identical to two fmaf() calls, half the issue slots
+__device__ __forceinline__ void fma4_packed(float4& acc, float a, const float4& x) {
+  unsigned long long lo, hi, xl, xh, aa;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(lo) : "f"(acc.x), "f"(acc.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(hi) : "f"(acc.z), "f"(acc.w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xl) : "f"(x.x), "f"(x.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xh) : "f"(x.z), "f"(x.w));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(lo) : "l"(aa), "l"(xl));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(hi) : "l"(aa), "l"(xh));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(lo));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(hi));
+}
 __device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }

@@ -75,7 +75,7 @@ class DeviceTrainSet:
 class LightGCNEngine:
     def __init__(self, graph: DeviceGraph, table: torch.Tensor, n_users: int, n_layers: int,
                  lr: float, reg: float, batch_size: int, max_triples: int,
-                 betas=(0.9, 0.999), adam_eps=1e-8):
+                 betas=(0.9, 0.999), adam_eps=1e-8, sparse_layers=True):
         if 3 * batch_size > 16384:
             raise ValueError("batch_size %d too large for the single-CTA batch grouping (max 5461)" % batch_size)
         if n_layers < 1:
@@ -104,6 +104,11 @@ class LightGCNEngine:
         self.seg_off = i32(nbmax * (3 * self.B + 1))
         self.seg_node = i32(nbmax * 3 * self.B)
         self.n_seg = i32(nbmax)
+        # per-batch node bitmaps drive the batch-sparse layers (last forward layer only computes the batch's
+        # rows, first backward layer only gathers the batch's gradient rows); skipped if they would be huge
+        self.mask_words = (self.N + 31) // 32
+        self.sparse_layers = bool(sparse_layers) and nbmax * self.mask_words * 4 <= (1 << 29)
+        self.node_mask = i32(nbmax * self.mask_words) if self.sparse_layers else None
         self.out4 = torch.zeros((nbmax, 4), dtype=torch.float32, device=dev)
         self.coef = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.ws = torch.zeros(ops.bpr_ws_bytes(self.B), dtype=torch.uint8, device=dev)
@@ -139,19 +144,21 @@ class LightGCNEngine:
         b0 = first_triple // self.B
         ops.bpr_group_batches(self.tu[first_triple:], self.ti[first_triple:], self.tj[first_triple:], n, self.B, self.U,
                               self.occ[b0 * 3 * self.B:], self.seg_off[b0 * (3 * self.B + 1):],
-                              self.seg_node[b0 * 3 * self.B:], self.n_seg[b0:])
+                              self.seg_node[b0 * 3 * self.B:], self.n_seg[b0:], self.N,
+                              None if self.node_mask is None else self.node_mask[b0 * self.mask_words:])
 
     # --------------------------------------------------------------- one step
-    def forward_table(self, out=None):
+    def forward_table(self, out=None, row_mask=None):
         """F = mean_k A^k E0 into self.F (or ``out``): the encoder forward alone
-        (recommender/LightGCN.py:230-240), e.g. for the end-of-epoch embeddings."""
+        (recommender/LightGCN.py:230-240), e.g. for the end-of-epoch embeddings.  With
+        ``row_mask`` the LAST layer only computes (and F is only valid on) the masked rows."""
         F = self.F if out is None else out
         x = self.E0
         for k in range(1, self.L + 1):
             last = k == self.L
             y = None if last else self.fw[(k - 1) % 2]
             ops.spmm(self.g, x, Y=y, acc_in=self.E0 if k == 1 else F, acc_out=F,
-                     acc_div=float(self.L + 1) if last else 1.0)
+                     acc_div=float(self.L + 1) if last else 1.0, row_mask=row_mask if last else None)
             x = y
         return F
 
@@ -165,17 +172,19 @@ class LightGCNEngine:
         seg_node = self.seg_node[b * 3 * B:]
         n_seg = self.n_seg[b:]
         out4 = self.out4[b]
-        F = self.forward_table()
+        mask = self.node_mask[b * self.mask_words:] if self.sparse_layers else None
+        F = self.forward_table(row_mask=mask)
         ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)
         ops.bpr_backward(F, u, i, j, nb, self.U, self.reg, 1.0, out4, self.coef, occ, seg_off, seg_node, n_seg, self.G)
         H = self.G
         for k in range(L, 0, -1):
             if k > 1:
                 nxt = self.bw[k % 2]
-                ops.spmm(self.g, H, Y=nxt, addend=self.G)
+                ops.spmm(self.g, H, Y=nxt, addend=self.G, col_mask=mask if k == L else None)
                 H = nxt
             else:
-                ops.spmm(self.g, H, acc_in=self.G, acc_out=self.dE0, acc_div=float(L + 1))
+                ops.spmm(self.g, H, acc_in=self.G, acc_out=self.dE0, acc_div=float(L + 1),
+                         col_mask=mask if k == L else None)
         ops.zero_rows(seg_node, n_seg, 3 * nb, self.G)
         ops.adam_step(self.E0, self.dE0, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.adam_eps,
                       step_dev=self.step_dev)

@@ -39,6 +39,28 @@ class DeviceGraph:
         self.nnz = int(col.numel())
         self.row_order, self.n_long = row_order, int(n_long)
         self._coo_idx = None
+        self._build_plan()
+
+    def _build_plan(self):
+        """Slot-ordered copy of the CSR for the SpMM kernel: rows physically permuted into
+        processing order (degree descending), so a task's rowptr / col / val reads are
+        contiguous and independent of the row-id lookup (no dependent-load chain)."""
+        order = self.row_order.long()
+        deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
+        pdeg = deg[order]
+        prowptr = torch.zeros(self.n_rows + 1, dtype=torch.int64, device=self.device)
+        prowptr[1:] = torch.cumsum(pdeg, 0)
+        # source position of every nnz in slot order: start of its row + offset inside the row
+        starts = self.rowptr[:-1].long()[order]
+        src = torch.repeat_interleave(starts - prowptr[:-1], pdeg) + torch.arange(self.nnz, device=self.device)
+        self.p_rowptr = prowptr.to(torch.int32)
+        self.p_src = src
+        self.p_col = self.col[src].contiguous()
+        self.p_val = self.val[src].contiguous()
+
+    def refresh_plan_values(self):
+        """re-gather the slot-ordered values after ``val`` was modified in place"""
+        self.p_val = self.val[self.p_src].contiguous()
 
     @property
     def device(self):
@@ -86,6 +108,7 @@ class DeviceGraph:
         _lib.check(lib.agcf_norm_adj_csr(g.rowptr.data_ptr(), g.col.data_ptr(), w.data_ptr(), dr.data_ptr(),
                                          dc.data_ptr(), val.data_ptr(), g.n_rows, g.nnz, _lib.stream_ptr()),
                    "agcf_norm_adj_csr")
+        g.refresh_plan_values()
         return g
 
     @classmethod

@@ -32,7 +32,8 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_div=1.0, noise=None, eps=0.0):
+def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_div=1.0, noise=None, eps=0.0,
+         row_mask=None, col_mask=None):
     """agcf_spmm_csr_f32: t = A X (+addend) (+noise perturbation); Y = t;
     acc_out = (acc_in + t) / acc_div."""
     lib = _lib.load()
@@ -43,10 +44,10 @@ def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_
     for t in (Y, addend, acc_in, acc_out, noise):
         if t is not None and tuple(t.shape) != (g.n_rows, d):
             raise ValueError("operand shape mismatch")
-    _lib.check(lib.agcf_spmm_csr_f32(g.rowptr.data_ptr(), g.col.data_ptr(), g.val.data_ptr(), X.data_ptr(), _p(Y),
+    _lib.check(lib.agcf_spmm_csr_f32(g.p_rowptr.data_ptr(), g.p_col.data_ptr(), g.p_val.data_ptr(), X.data_ptr(), _p(Y),
                                      _p(addend), _p(acc_in), _p(acc_out), float(acc_div), _p(noise), float(eps),
-                                     g.row_order.data_ptr(), g.n_long, g.n_rows, d, _lib.stream_ptr()),
-               "agcf_spmm_csr_f32")
+                                     g.row_order.data_ptr(), g.n_long, _p(row_mask), _p(col_mask), g.n_rows, d,
+                                     _lib.stream_ptr()), "agcf_spmm_csr_f32")
 
 
 def sddmm(g: DeviceGraph, H, E, gval, accumulate=False):
@@ -81,11 +82,12 @@ def bpr_sample_epoch(e_user, e_item, rej_rowptr, rej_items, n_items, seed, epoch
                "agcf_bpr_sample_epoch")
 
 
-def bpr_group_batches(u, i, j, n_triples, batch, n_users, occ, seg_off, seg_node, n_seg):
+def bpr_group_batches(u, i, j, n_triples, batch, n_users, occ, seg_off, seg_node, n_seg, n_nodes=0, node_mask=None):
     lib = _lib.load()
     _lib.check(lib.agcf_bpr_group_batches(u.data_ptr(), i.data_ptr(), j.data_ptr(), int(n_triples), int(batch),
                                           int(n_users), occ.data_ptr(), seg_off.data_ptr(), seg_node.data_ptr(),
-                                          n_seg.data_ptr(), _lib.stream_ptr()), "agcf_bpr_group_batches")
+                                          n_seg.data_ptr(), int(n_nodes), _p(node_mask), _lib.stream_ptr()),
+               "agcf_bpr_group_batches")
 
 
 def bpr_ws_bytes(nb):

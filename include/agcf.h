@@ -62,7 +62,11 @@ int agcf_csr_expand_rows(const int32_t* rowptr, int32_t* row_of, int32_t n_rows,
  *   if acc_out:    acc_out[i,:] = ((acc_in ? acc_in[i,:] : 0) + t[i,:]) / acc_div
  * row_order (nullable) is a permutation of rows giving the processing order
  * (longest rows first); n_long leading entries of it are rows handled by a whole
- * CTA.  Forward AND backward of the encoder: A is symmetric so A^T = A.
+ * CTA.  row_mask / col_mask (nullable bitmaps, bit k of word k/32): only rows whose
+ * bit is set are computed and written; rows of X whose bit is clear are known to be
+ * all-zero and are not gathered (the last forward layer only needs the batch's
+ * rows, the first backward layer only sees the batch's gradient rows).
+ * Forward AND backward of the encoder: A is symmetric so A^T = A.
  * Replaces: torch.sparse.mm + stack + mean in recommender/LightGCN.py:230-240,
  * the noise lines of recommender/SimGCL.py:202-206 / XSimGCL.py:211-215, and the
  * autograd of those (transposed SpMM + mean backward). */
@@ -72,6 +76,7 @@ int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* va
                       const float* acc_in, float* acc_out, float acc_div,
                       const float* noise, float eps,
                       const int32_t* row_order, int32_t n_long,
+                      const uint32_t* row_mask, const uint32_t* col_mask,
                       int32_t n_rows, int32_t d, agcf_stream_t stream);
 
 /* gval[p] (+)= <H[i,:], E[col[p],:]> for p in row i (accumulate != 0 adds).
@@ -107,11 +112,13 @@ int agcf_bpr_sample_epoch(const int32_t* e_user, const int32_t* e_item, int32_t 
  *   seg_off[b*(3B+1)+s] s <= n_seg: start of segment s in occ (one segment = one node)
  *   seg_node[b*3B + s] : the node (users 0..U-1, items U..U+I-1)
  *   n_seg[b]
+ *   node_mask[b*ceil(n_nodes/32) + w] (nullable): bitmap of the batch's nodes -- the
+ *                                 row / column mask of the batch-sparse SpMM layers
  * 3*B must be <= 16384. One CTA per batch; all batches of an epoch in one call. */
 int agcf_bpr_group_batches(const int32_t* u, const int32_t* i, const int32_t* j,
                            int32_t n_triples, int32_t batch, int32_t n_users,
                            int32_t* occ, int32_t* seg_off, int32_t* seg_node, int32_t* n_seg,
-                           agcf_stream_t stream);
+                           int32_t n_nodes, uint32_t* node_mask, agcf_stream_t stream);
 
 /* Fused gather - score - BPR - L2 forward for one batch of nb triples on the
  * propagated table F [N,d]:

@@ -84,7 +84,9 @@ def test_group_batches_is_a_sorted_segmentation(nb, B):
     seg_off = torch.full((nbat * (3 * B + 1),), -1, dtype=torch.int32, device=DEV)
     seg_node = torch.full((nbat * 3 * B,), -1, dtype=torch.int32, device=DEV)
     n_seg = torch.zeros(nbat, dtype=torch.int32, device=DEV)
-    ops.bpr_group_batches(d(u), d(i), d(j), T, B, U, occ, seg_off, seg_node, n_seg)
+    words = (U + I + 31) // 32
+    mask = torch.full((nbat * words,), -1, dtype=torch.int32, device=DEV)
+    ops.bpr_group_batches(d(u), d(i), d(j), T, B, U, occ, seg_off, seg_node, n_seg, U + I, mask)
     for b, (lo, n) in enumerate(((0, B), (B, nb))):
         nodes, order = _group_ref(u[lo:lo + n], i[lo:lo + n], j[lo:lo + n], U)
         got_occ = occ[b * 3 * B: b * 3 * B + 3 * n].cpu().numpy()
@@ -95,6 +97,9 @@ def test_group_batches_is_a_sorted_segmentation(nb, B):
         assert np.array_equal(seg_node[b * 3 * B: b * 3 * B + ns].cpu().numpy(), uniq)
         off = seg_off[b * (3 * B + 1): b * (3 * B + 1) + ns + 1].cpu().numpy()
         assert np.array_equal(off[:-1], first) and off[-1] == 3 * n
+        bits = mask[b * words:(b + 1) * words].cpu().numpy().view(np.uint32)
+        got_nodes = np.flatnonzero(np.unpackbits(bits.view(np.uint8), bitorder="little"))
+        assert np.array_equal(got_nodes, uniq)
 
 
 @pytest.mark.parametrize("d", [32, 64, 128, 256])

@@ -206,3 +206,35 @@ def test_simgcl_xsimgcl_ngcf_encoders_match_oracle():
     _loss(*ref).backward(); _loss(*got).backward()
     torch.testing.assert_close(enc.embedding_dict['item_emb'].grad.cpu(), ie.grad, rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(enc.W['w2_1'].grad.cpu(), w2[1].grad, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_spmm_row_and_column_masks(d):
+    """Batch-sparse layers: row_mask = only those rows are computed/written; col_mask =
+    rows of X outside it are zero and are skipped (same result as the dense product)."""
+    from arlib_b200 import ops
+    from arlib_b200.graph import DeviceGraph
+    U, I = 700, 900
+    u, i = _rand_graph(U, I, 15000, 9, 500)
+    adj = port.bipartite_adjacency(u, i, U, I)
+    g = DeviceGraph.from_dataloader_adj(adj, _dev())
+    n = U + I
+    rng = np.random.default_rng(0)
+    live = rng.random(n) < 0.15
+    live[:2] = True                                       # the two hub rows (long-row path)
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    for k in np.flatnonzero(live):
+        words[k >> 5] |= np.uint32(1) << np.uint32(k & 31)
+    mask = torch.from_numpy(words.view(np.int32)).to(_dev())
+    X = torch.randn(n, d)
+    Xz = X.clone(); Xz[~torch.from_numpy(live)] = 0
+    ref = torch.sparse.mm(port.to_torch_coo(port.normalize_graph_mat(adj)), Xz)
+    Y = torch.empty(n, d, device=_dev())
+    ops.spmm(g, Xz.to(_dev()), Y=Y, col_mask=mask)
+    torch.testing.assert_close(Y.cpu(), ref, rtol=1e-5, atol=1e-6)
+    ref_full = torch.sparse.mm(port.to_torch_coo(port.normalize_graph_mat(adj)), X)
+    out = torch.full((n, d), 7.0, device=_dev())
+    ops.spmm(g, X.to(_dev()), acc_out=out, row_mask=mask)
+    out = out.cpu()
+    torch.testing.assert_close(out[torch.from_numpy(live)], ref_full[torch.from_numpy(live)], rtol=1e-5, atol=1e-6)
+    assert bool((out[~torch.from_numpy(live)] == 7.0).all())
