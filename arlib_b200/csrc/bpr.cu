@@ -339,12 +339,17 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(const int32_t* __restric
 }
 
 // ========================================================================= Adam
+struct AdamPeers {
+  int n;
+  float* p[AGCF_MAX_PEERS];
+};
+
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
                                                    float4* __restrict__ m, float4* __restrict__ v, long long n4,
                                                    float* __restrict__ p_tail, const float* __restrict__ g_tail,
                                                    float* __restrict__ m_tail, float* __restrict__ v_tail, int n_tail,
                                                    float lr, float beta1, float beta2, float eps, int step,
-                                                   const int32_t* __restrict__ step_dev) {
+                                                   const int32_t* __restrict__ step_dev, AdamPeers peers) {
   __shared__ float sh_step_size, sh_bc2_sqrt;
   if (threadIdx.x == 0) {
     const int t = step_dev != nullptr ? (*step_dev + 1) : step;
@@ -371,11 +376,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
     upd(pp.z, gg.z, mm.z, vv.z);
     upd(pp.w, gg.w, mm.w, vv.w);
     p[k] = pp; m[k] = mm; v[k] = vv;
+    for (int q = 0; q < peers.n; ++q) reinterpret_cast<float4*>(peers.p[q])[k] = pp;
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) {
     float pp = p_tail[threadIdx.x], mm = m_tail[threadIdx.x], vv = v_tail[threadIdx.x];
     upd(pp, g_tail[threadIdx.x], mm, vv);
     p_tail[threadIdx.x] = pp; m_tail[threadIdx.x] = mm; v_tail[threadIdx.x] = vv;
+    for (int q = 0; q < peers.n; ++q) peers.p[q][n4 * 4 + threadIdx.x] = pp;
   }
 }
 
@@ -509,8 +516,13 @@ extern "C" int agcf_zero_rows(const int32_t* seg_node, const int32_t* n_seg, int
 
 extern "C" int agcf_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n,
                                   float lr, float beta1, float beta2, float eps,
-                                  int32_t step, const int32_t* step_dev, agcf_stream_t stream) {
+                                  int32_t step, const int32_t* step_dev,
+                                  void* const* peer_p_host, int32_t n_peers, agcf_stream_t stream) {
   if (!p || !g || !m || !v || n < 0) return AGCF_EINVAL;
+  if (n_peers < 0 || n_peers > AGCF_MAX_PEERS || (n_peers > 0 && !peer_p_host)) return AGCF_EINVAL;
+  AdamPeers peers;
+  peers.n = n_peers;
+  for (int q = 0; q < AGCF_MAX_PEERS; ++q) peers.p[q] = q < n_peers ? reinterpret_cast<float*>(peer_p_host[q]) : nullptr;
   if (step_dev == nullptr && step < 1) return AGCF_EINVAL;
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v)) return AGCF_EINVAL;
   if (n == 0) return AGCF_OK;
@@ -522,7 +534,7 @@ extern "C" int agcf_adam_step_f32(float* p, const float* g, float* m, float* v, 
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), n4, p + n4 * 4, g + n4 * 4, m + n4 * 4, v + n4 * 4, n_tail,
-      lr, beta1, beta2, eps, step, step_dev);
+      lr, beta1, beta2, eps, step, step_dev, peers);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
 }

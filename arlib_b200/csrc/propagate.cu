@@ -46,6 +46,11 @@ struct SpmmParams {
   int32_t n_rows;
   const uint32_t* row_mask;   // nullable bitmap over rows: only rows with their bit set are computed / written
   const uint32_t* col_mask;   // nullable bitmap over columns: rows of X outside it are known to be zero (skipped)
+  // fused all-gather: the same rows are also stored into the peer GPUs' copies of Y / acc_out
+  // (NVLink P2P stores straight from the epilogue; peers see them after the next barrier)
+  int n_peers;
+  float4* peer_Y[AGCF_MAX_PEERS];
+  float4* peer_acc[AGCF_MAX_PEERS];
 };
 
 __device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ m, int k) {
@@ -98,6 +103,11 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
   if (p.Y != nullptr) {
 #pragma unroll
     for (int v = 0; v < C::VPL; ++v) p.Y[rbase + v * C::LPR + gl] = t[v];
+    for (int q = 0; q < p.n_peers; ++q) {
+      if (p.peer_Y[q] == nullptr) continue;
+#pragma unroll
+      for (int v = 0; v < C::VPL; ++v) p.peer_Y[q][rbase + v * C::LPR + gl] = t[v];
+    }
   }
   if (p.acc_out != nullptr) {
 #pragma unroll
@@ -110,6 +120,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
         o.z = __fdiv_rn(o.z, p.acc_div); o.w = __fdiv_rn(o.w, p.acc_div);
       }
       p.acc_out[rbase + v * C::LPR + gl] = o;
+      for (int q = 0; q < p.n_peers; ++q)
+        if (p.peer_acc[q] != nullptr) p.peer_acc[q][rbase + v * C::LPR + gl] = o;
     }
   }
 }
@@ -585,7 +597,9 @@ extern "C" int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, cons
                                  const float* noise, float eps,
                                  const int32_t* row_order, int32_t n_long,
                                  const uint32_t* row_mask, const uint32_t* col_mask,
+                                 void* const* peer_Y_host, void* const* peer_acc_host, int32_t n_peers,
                                  int32_t n_rows, int32_t d, agcf_stream_t stream) {
+  if (n_peers < 0 || n_peers > AGCF_MAX_PEERS) return AGCF_EINVAL;
   if (!rowptr || !col || !val || !X || n_rows < 0 || (Y == nullptr && acc_out == nullptr)) return AGCF_EINVAL;
   if (!supported_d(d)) return AGCF_EUNSUPPORTED;
   if (n_long < 0 || n_long > n_rows || (n_long > 0 && row_order == nullptr)) return AGCF_EINVAL;
@@ -605,6 +619,11 @@ extern "C" int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, cons
   p.eps = eps;
   p.row_order = row_order; p.n_long = n_long; p.n_rows = n_rows;
   p.row_mask = row_mask; p.col_mask = col_mask;
+  p.n_peers = n_peers;
+  for (int q = 0; q < AGCF_MAX_PEERS; ++q) {
+    p.peer_Y[q] = (q < n_peers && peer_Y_host) ? reinterpret_cast<float4*>(peer_Y_host[q]) : nullptr;
+    p.peer_acc[q] = (q < n_peers && peer_acc_host) ? reinterpret_cast<float4*>(peer_acc_host[q]) : nullptr;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   switch (d) {
     case 32: return launch_spmm<32>(p, st);

@@ -53,14 +53,14 @@ __device__ __forceinline__ float exact_dot(const float* __restrict__ urow_smem, 
 __global__ void __launch_bounds__(256) mask_bits_kernel(const int32_t* __restrict__ user_rows, int n_u,
                                                         const int32_t* __restrict__ mask_rowptr,
                                                         const int32_t* __restrict__ mask_items, int n_items,
-                                                        int n_groups, uint32_t* __restrict__ bits) {
+                                                        int item_offset, int n_groups, uint32_t* __restrict__ bits) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_u) return;
   const int uid = user_rows != nullptr ? user_rows[r] : r;
   const int s = mask_rowptr[uid], e = mask_rowptr[uid + 1];
   for (int k = s + lane; k < e; k += 32) {
-    const int it = mask_items[k];
+    const int it = mask_items[k] - item_offset;         // item shards: mask ids are global
     if (it >= 0 && it < n_items) atomicOr(bits + (size_t)r * n_groups + (it >> 5), 1u << (it & 31));
   }
 }
@@ -542,7 +542,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   // stage 0
   AGCF_CUDA_OK(cudaMemsetAsync(bits, 0, (size_t)n_u * L.n_groups * 4, st));
   if (mask_rowptr != nullptr) {
-    mask_bits_kernel<<<(unsigned)((n_u + 7) / 8), 256, 0, st>>>(user_rows, n_u, mask_rowptr, mask_items, n_items, L.n_groups, bits);
+    mask_bits_kernel<<<(unsigned)((n_u + 7) / 8), 256, 0, st>>>(user_rows, n_u, mask_rowptr, mask_items, n_items, item_offset, L.n_groups, bits);
     AGCF_LAUNCH_OK();
   }
   // stage 1

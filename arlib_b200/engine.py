@@ -75,22 +75,44 @@ class DeviceTrainSet:
 class LightGCNEngine:
     def __init__(self, graph: DeviceGraph, table: torch.Tensor, n_users: int, n_layers: int,
                  lr: float, reg: float, batch_size: int, max_triples: int,
-                 betas=(0.9, 0.999), adam_eps=1e-8, sparse_layers=True):
+                 betas=(0.9, 0.999), adam_eps=1e-8, sparse_layers=True, comm=None):
         if 3 * batch_size > 16384:
             raise ValueError("batch_size %d too large for the single-CTA batch grouping (max 5461)" % batch_size)
         if n_layers < 1:
             raise ValueError("n_layers must be >= 1")
-        self.g, self.E0 = graph, table
         self.N, self.d = table.shape
         self.U, self.L = int(n_users), int(n_layers)
         self.lr, self.reg, self.B = float(lr), float(reg), int(batch_size)
         self.betas, self.adam_eps = betas, adam_eps
         dev = table.device
+        self.comm = comm
         f = lambda: torch.empty_like(table)
-        self.F = f()
-        self.fw = [f(), f()] if self.L > 1 else []
+        if comm is None or comm.world == 1:
+            self.comm = None
+            self.g, self.E0 = graph, table
+            self.r0, self.r1 = 0, self.N
+            self.F = f()
+            self.fw = [f(), f()] if self.L > 1 else []
+            self.bw = [f(), f()] if self.L > 1 else []
+        else:
+            # row partition: this rank computes rows [r0, r1); layer tables live in one symmetric arena
+            bounds = graph.row_ranges(comm.world)
+            self.bounds = bounds
+            self.r0, self.r1 = bounds[comm.rank], bounds[comm.rank + 1]
+            self.g = graph.partition(self.r0, self.r1)
+            shape = (self.N, self.d)
+            bufs = comm.allocate({k: (shape, torch.float32) for k in ("E0", "F", "fw0", "fw1", "bw0", "bw1")})
+            self.E0 = bufs["E0"]
+            self.E0.copy_(table)
+            self.F = bufs["F"]
+            self.fw = [bufs["fw0"], bufs["fw1"]]
+            self.bw = [bufs["bw0"], bufs["bw1"]]
+            row_off = self.r0 * self.d * 4
+            self._peer = {k: comm.peers(k) for k in ("E0", "F", "fw0", "fw1", "bw0", "bw1")}
+            self._peer_E0_rows = comm.peers("E0", row_off)
+            torch.cuda.synchronize()
+            comm.barrier()
         self.G = torch.zeros_like(table)
-        self.bw = [f(), f()] if self.L > 1 else []
         self.dE0 = f()
         self.m = torch.zeros_like(table)
         self.v = torch.zeros_like(table)
@@ -113,7 +135,16 @@ class LightGCNEngine:
         self.coef = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.ws = torch.zeros(ops.bpr_ws_bytes(self.B), dtype=torch.uint8, device=dev)
         self._graphs = {}
-        self.launches_per_step = 2 * self.L + 5
+        import os as _os
+        self.dist_graphs = _os.environ.get("ARLIB_B200_DIST_GRAPHS", "1") == "1"
+        self.launches_per_step = 2 * self.L + 5 + (2 * self.L if self.comm is not None else 0)
+
+    def _peers(self, name):
+        return None if self.comm is None else self._peer[name]
+
+    def _barrier(self):
+        if self.comm is not None:
+            self.comm.barrier()
 
     # ------------------------------------------------------------ epoch set-up
     @property
@@ -151,14 +182,21 @@ class LightGCNEngine:
     def forward_table(self, out=None, row_mask=None):
         """F = mean_k A^k E0 into self.F (or ``out``): the encoder forward alone
         (recommender/LightGCN.py:230-240), e.g. for the end-of-epoch embeddings.  With
-        ``row_mask`` the LAST layer only computes (and F is only valid on) the masked rows."""
+        ``row_mask`` the LAST layer only computes (and F is only valid on) the masked rows.
+        Multi-GPU: every layer's rows are also stored into the peers' tables by the SpMM
+        epilogue and a barrier closes the layer (``out`` must then be self.F)."""
         F = self.F if out is None else out
+        if self.comm is not None and out is not None:
+            raise ValueError("multi-GPU forward writes the symmetric F table")
         x = self.E0
         for k in range(1, self.L + 1):
             last = k == self.L
+            name = "fw%d" % ((k - 1) % 2)
             y = None if last else self.fw[(k - 1) % 2]
             ops.spmm(self.g, x, Y=y, acc_in=self.E0 if k == 1 else F, acc_out=F,
-                     acc_div=float(self.L + 1) if last else 1.0, row_mask=row_mask if last else None)
+                     acc_div=float(self.L + 1) if last else 1.0, row_mask=row_mask if last else None,
+                     peer_Y=None if last else self._peers(name), peer_acc=self._peers("F") if last else None)
+            self._barrier()
             x = y
         return F
 
@@ -180,15 +218,21 @@ class LightGCNEngine:
         for k in range(L, 0, -1):
             if k > 1:
                 nxt = self.bw[k % 2]
-                ops.spmm(self.g, H, Y=nxt, addend=self.G, col_mask=mask if k == L else None)
+                ops.spmm(self.g, H, Y=nxt, addend=self.G, col_mask=mask if k == L else None,
+                         peer_Y=self._peers("bw%d" % (k % 2)))
+                self._barrier()
                 H = nxt
             else:
                 ops.spmm(self.g, H, acc_in=self.G, acc_out=self.dE0, acc_div=float(L + 1),
                          col_mask=mask if k == L else None)
         ops.zero_rows(seg_node, n_seg, 3 * nb, self.G)
-        ops.adam_step(self.E0, self.dE0, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.adam_eps,
-                      step_dev=self.step_dev)
+        # owner-computes: Adam on this rank's rows; the updated rows are stored into every peer's E0
+        r0, r1 = self.r0, self.r1
+        ops.adam_step(self.E0[r0:r1], self.dE0[r0:r1], self.m[r0:r1], self.v[r0:r1], self.lr, self.betas[0],
+                      self.betas[1], self.adam_eps, step_dev=self.step_dev,
+                      peer_p=None if self.comm is None else self._peer_E0_rows)
         ops.increment(self.step_dev)
+        self._barrier()
 
     # ------------------------------------------------------------------ running
     def run_steps(self, first_batch=0, n_steps=None, use_graph=True):
@@ -201,7 +245,7 @@ class LightGCNEngine:
             raise ValueError("not enough batches")
         if n_steps <= 0:
             return self.out4[0:0]
-        if not use_graph:
+        if not use_graph or (self.comm is not None and not self.dist_graphs):
             for b in range(first_batch, first_batch + n_steps):
                 self._launch_step(b)
         else:

@@ -119,6 +119,25 @@ class FullRankEvaluator:
             idx[lo:hi] = i
         return vals, idx
 
+    def topk_sharded(self, user_emb, item_emb, K, rank, world, impl=None):
+        """Item-sharded scoring: this rank scores every test user against its
+        item block with the fused top-K, the P per-shard lists are all-gathered (NCCL) and
+        merged on device (agcf_topk_merge).  Identical result on every rank."""
+        import torch.distributed as dist
+        impl = DEFAULT_IMPL if impl is None else impl
+        n_items = item_emb.shape[0]
+        i0 = n_items * rank // world
+        i1 = n_items * (rank + 1) // world
+        block = item_emb[i0:i1].detach().contiguous()
+        n = self.user_rows.numel()
+        vals, idx = ops.score_topk(user_emb.detach().contiguous(), block, K, user_rows=self.user_rows,
+                                   mask_rowptr=self.mask_rowptr, mask_items=self.mask_items, item_offset=i0, impl=impl)
+        all_v = torch.empty((world, n, K), dtype=torch.float32, device=self.device)
+        all_i = torch.empty((world, n, K), dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(all_v, vals)
+        dist.all_gather_into_tensor(all_i, idx)
+        return ops.topk_merge(all_v, all_i)
+
     def per_user_metrics(self, idx, cutoffs):
         """[n_users, n_cutoffs, 3] float64 (hits, dcg, idcg) on device."""
         K = idx.shape[1]

@@ -30,14 +30,29 @@ def _plan_rows(indptr: np.ndarray):
     return order, n_long
 
 
+def balanced_row_ranges(indptr, world):
+    """Boundaries b[0..world] with b[0]=0, b[world]=n_rows and ~nnz/world non-zeros per range."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    n = indptr.shape[0] - 1
+    nnz = int(indptr[-1])
+    bounds = [0]
+    for p in range(1, world):
+        target = nnz * p // world
+        b = int(np.searchsorted(indptr, target, side="left"))
+        bounds.append(min(max(b, bounds[-1]), n))
+    bounds.append(n)
+    return bounds
+
+
 class DeviceGraph:
     """CSR (rowptr, col, val) on the device + SpMM plan.  Immutable after build."""
 
     def __init__(self, rowptr, col, val, n_rows, row_order, n_long):
         self.rowptr, self.col, self.val = rowptr, col, val
-        self.n_rows = int(n_rows)
+        self.n_rows = int(n_rows)                    # global row count (= rows of X / Y)
         self.nnz = int(col.numel())
         self.row_order, self.n_long = row_order, int(n_long)
+        self.n_local_rows = int(row_order.numel())   # rows this graph computes (all, or one rank's partition)
         self._coo_idx = None
         self._build_plan()
 
@@ -48,11 +63,13 @@ class DeviceGraph:
         order = self.row_order.long()
         deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
         pdeg = deg[order]
-        prowptr = torch.zeros(self.n_rows + 1, dtype=torch.int64, device=self.device)
+        prowptr = torch.zeros(self.n_local_rows + 1, dtype=torch.int64, device=self.device)
         prowptr[1:] = torch.cumsum(pdeg, 0)
         # source position of every nnz in slot order: start of its row + offset inside the row
         starts = self.rowptr[:-1].long()[order]
-        src = torch.repeat_interleave(starts - prowptr[:-1], pdeg) + torch.arange(self.nnz, device=self.device)
+        local_nnz = int(prowptr[-1])
+        src = torch.repeat_interleave(starts - prowptr[:-1], pdeg) + torch.arange(local_nnz, device=self.device)
+        self.local_nnz = local_nnz
         self.p_rowptr = prowptr.to(torch.int32)
         self.p_src = src
         self.p_col = self.col[src].contiguous()
@@ -65,6 +82,20 @@ class DeviceGraph:
     @property
     def device(self):
         return self.val.device
+
+    # -------------------------------------------------------------- partitioning
+    def row_ranges(self, world):
+        """world+1 boundaries of contiguous row ranges with ~equal nnz (power-law rows:
+        balance by non-zeros, not by rows)."""
+        return balanced_row_ranges(self.rowptr.cpu().numpy(), world)
+
+    def partition(self, r0, r1):
+        """Graph that COMPUTES only rows [r0, r1) (one rank of the row-partitioned
+        multi-GPU path); X / Y keep global row ids, col ids are global."""
+        deg = (self.rowptr[r0 + 1:r1 + 1] - self.rowptr[r0:r1]).cpu().numpy()
+        order = (np.argsort(-deg, kind="stable") + r0).astype(np.int32)
+        n_long = int(np.count_nonzero(deg > LONG_ROW_THRESHOLD))
+        return DeviceGraph(self.rowptr, self.col, self.val, self.n_rows, torch.from_numpy(order).to(self.device), n_long)
 
     # ---------------------------------------------------------------- builders
     @classmethod

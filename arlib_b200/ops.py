@@ -33,21 +33,25 @@ def _p(t):
 
 
 def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_div=1.0, noise=None, eps=0.0,
-         row_mask=None, col_mask=None):
+         row_mask=None, col_mask=None, peer_Y=None, peer_acc=None):
     """agcf_spmm_csr_f32: t = A X (+addend) (+noise perturbation); Y = t;
     acc_out = (acc_in + t) / acc_div."""
     lib = _lib.load()
     _f32(X, "X"); _f32(Y, "Y"); _f32(addend, "addend"); _f32(acc_in, "acc_in"); _f32(acc_out, "acc_out"); _f32(noise, "noise")
     if X.shape[0] != g.n_rows:
         raise ValueError("X has %d rows, graph has %d" % (X.shape[0], g.n_rows))
+    if peer_Y and peer_acc and len(peer_Y) != len(peer_acc):
+        raise ValueError("peer lists must have equal length")
     d = X.shape[1]
     for t in (Y, addend, acc_in, acc_out, noise):
         if t is not None and tuple(t.shape) != (g.n_rows, d):
             raise ValueError("operand shape mismatch")
+    py, n1 = _lib.ptr_array(peer_Y)
+    pa, n2 = _lib.ptr_array(peer_acc)
     _lib.check(lib.agcf_spmm_csr_f32(g.p_rowptr.data_ptr(), g.p_col.data_ptr(), g.p_val.data_ptr(), X.data_ptr(), _p(Y),
                                      _p(addend), _p(acc_in), _p(acc_out), float(acc_div), _p(noise), float(eps),
-                                     g.row_order.data_ptr(), g.n_long, _p(row_mask), _p(col_mask), g.n_rows, d,
-                                     _lib.stream_ptr()), "agcf_spmm_csr_f32")
+                                     g.row_order.data_ptr(), g.n_long, _p(row_mask), _p(col_mask), py, pa, max(n1, n2),
+                                     g.n_local_rows, d, _lib.stream_ptr()), "agcf_spmm_csr_f32")
 
 
 def sddmm(g: DeviceGraph, H, E, gval, accumulate=False):
@@ -55,7 +59,7 @@ def sddmm(g: DeviceGraph, H, E, gval, accumulate=False):
     lib = _lib.load()
     _f32(H, "H"); _f32(E, "E"); _f32(gval, "gval")
     _lib.check(lib.agcf_sddmm_csr_f32(g.rowptr.data_ptr(), g.col.data_ptr(), H.data_ptr(), E.data_ptr(), gval.data_ptr(),
-                                      1 if accumulate else 0, g.row_order.data_ptr(), g.n_rows, H.shape[1],
+                                      1 if accumulate else 0, g.row_order.data_ptr(), g.n_local_rows, H.shape[1],
                                       _lib.stream_ptr()), "agcf_sddmm_csr_f32")
 
 
@@ -115,11 +119,12 @@ def zero_rows(seg_node, n_seg, max_seg, G):
                                   _lib.stream_ptr()), "agcf_zero_rows")
 
 
-def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0, step_dev=None):
+def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0, step_dev=None, peer_p=None):
     lib = _lib.load()
     _f32(p, "p"); _f32(g, "g"); _f32(m, "m"); _f32(v, "v")
+    pp, n = _lib.ptr_array(peer_p)
     _lib.check(lib.agcf_adam_step_f32(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr),
-                                      float(beta1), float(beta2), float(eps), int(step), _p(step_dev),
+                                      float(beta1), float(beta2), float(eps), int(step), _p(step_dev), pp, n,
                                       _lib.stream_ptr()), "agcf_adam_step_f32")
 
 

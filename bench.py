@@ -226,7 +226,11 @@ def run_ours(args):
     ue, ie = xavier_tables(U, I, d)
     table = torch.cat([ue, ie]).to(dev)
     ts = DeviceTrainSet.from_arrays(D["tu"], D["ti"], U, I, dev)
-    eng = LightGCNEngine(g, table, U, L, LR, REG, B, E)
+    comm = None
+    if world > 1:
+        from arlib_b200.dist import DistContext
+        comm = DistContext(dev)
+    eng = LightGCNEngine(g, table, U, L, LR, REG, B, E, comm=comm)
     K, W = args.steps, max(args.warmup, 3)
     nb_epoch = (E + B - 1) // B
     full_batches = E // B
@@ -236,9 +240,14 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    if world > 1:
-        raise SystemExit("multi-GPU row-partitioned path: see arlib_b200/dist.py (bench wiring pending)")
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
 
+    use_graph = world == 1 or eng.dist_graphs
     # ---- device-resident throughput: K steps replayed from CUDA graphs of <= one epoch each
     eng.sample_epoch(ts, 2018, 0)
     chunks = []
@@ -251,22 +260,21 @@ def run_ours(args):
     for k in range(W):
         eng.run_steps(k % full_batches, 1, use_graph=False)
     for c in set(chunks):
-        eng.run_steps(c[0], c[1], use_graph=True)     # capture + one replay (warm)
+        eng.run_steps(c[0], c[1] if use_graph else min(c[1], 5), use_graph=use_graph)     # capture + one replay (warm)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
         e0.record()
         for c in chunks:
-            eng.run_steps(c[0], c[1], use_graph=True)
+            eng.run_steps(c[0], c[1], use_graph=use_graph)
         e1.record()
         barrier()
         # keep the GPU under the same load while NVML gets enough samples (not timed)
-        t_end = time.time() + 0.6
-        while time.time() < t_end:
-            eng.run_steps(chunks[0][0], chunks[0][1], use_graph=True)
+        for _ in range(3 if world > 1 else 8):
+            eng.run_steps(chunks[0][0], min(chunks[0][1], 200), use_graph=use_graph)
             torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     value = K * B / (ms * 1e-3)
     loss_last = float(eng.out4[chunks[-1][0] + chunks[-1][1] - 1, 0])
 
@@ -328,7 +336,7 @@ def run_ours(args):
         loss_host[k].copy_(row, non_blocking=True)
     e1.record()
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e = {"value": K * B / (e2e_ms * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": 3 * B * 4,
            "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / K,
            "api": "LightGCNEngine.step_external (host pinned triples -> H2D -> grouping -> step kernels -> loss D2H)"}
@@ -337,6 +345,8 @@ def run_ours(args):
     ev = FullRankEvaluator.from_arrays(U, I, D["tu"], D["ti"], D["su"], D["si"], dev)
     F = eng.forward_table().clone()
     n_test = ev.user_rows.numel()
+    if world > 1:
+        ev.topk = lambda ue_, ie_, k_, impl=None: ev.topk_sharded(ue_, ie_, k_, rank, world, impl)
     for _ in range(2):
         vals, idx = ev.topk(F[:U], F[U:], TOPK)
     barrier()
@@ -347,7 +357,7 @@ def run_ours(args):
         per = ev.per_user_metrics(idx, [TOPK])
     e1.record()
     barrier()
-    ev_ms = e0.elapsed_time(e1) / reps
+    ev_ms = max_over_ranks(e0.elapsed_time(e1)) / reps
     t0 = time.perf_counter()
     vals, idx = ev.topk(F[:U], F[U:], TOPK)
     measure = ev.measure(idx, [TOPK])
@@ -368,6 +378,8 @@ def run_ours(args):
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config_of(args, D),
         "roofline": roofline, "e2e": e2e, "eval": evald, "clocks": clk.summary(),
+        "parallelism": "single GPU" if world == 1 else
+        "row-partitioned x%d: per-layer all-gather fused into the SpMM epilogue (NVLink P2P stores), item-sharded eval" % world,
         "gpu_launches": K * eng.launches_per_step, "last_loss": loss_last,
     }
     if rank == 0 and not args.no_cpu_baseline:
@@ -380,9 +392,24 @@ def run_ours(args):
                                           "full-rank eval with oracle/port.py (torch CPU, %d threads)" % (B, cores)}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 def main():
+    # everything (NCCL banners, library chatter) goes to stderr; the ONE JSON line goes to the real stdout
+    global print
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    _print = print
+
+    def print(*a, **k):          # noqa: A001 - rank-0 JSON line writer
+        k.pop("flush", None)
+        _print(*a, file=real_stdout, **k)
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

@@ -1,0 +1,21 @@
+"""Multi-GPU parity (needs >= 2 GPUs: `gpurun --gpus 2`): row-partitioned propagation
+with the all-gather fused into the SpMM epilogue + item-sharded evaluation reproduce
+the single-GPU results."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_engine_matches_single_gpu():
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "dist_check.py")]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and "DIST_CHECK_OK" in res.stdout, res.stdout[-3000:]
