@@ -486,14 +486,14 @@ __global__ void __launch_bounds__(128) rank_metrics_kernel(const int32_t* __rest
 
 // provided by score_tc.cu (tcgen05 TF32 group-max GEMM)
 int launch_group_max_tc(const float* Uemb, const int32_t* user_rows, int n_u, const float* Iemb, int n_items, int d,
-                        const uint32_t* bits, int n_groups, float* gmax, cudaStream_t st);
+                        const uint32_t* bits, int n_groups, float* gmax, float* u_dense, cudaStream_t st);
 
 struct WsLayout {
-  size_t bits_off, gmax_off, norm_off, groups_off, cval_off, total;
+  size_t bits_off, gmax_off, norm_off, groups_off, cval_off, udense_off, total;
   int n_groups, grid2;
 };
 
-static WsLayout ws_layout(int n_u, int n_items) {
+static WsLayout ws_layout(int n_u, int n_items, int d) {
   WsLayout L;
   L.n_groups = (n_items + kGroup - 1) / kGroup;
   L.grid2 = n_u < 2 * kSMs ? (n_u > 0 ? n_u : 1) : 2 * kSMs;
@@ -504,6 +504,7 @@ static WsLayout ws_layout(int n_u, int n_items) {
   L.norm_off = off; off = up(off + 256);
   L.groups_off = off; off = up(off + (size_t)L.grid2 * L.n_groups * 4);
   L.cval_off = off; off = up(off + (size_t)L.grid2 * L.n_groups * kGroup * 4);
+  L.udense_off = off; off = up(off + (size_t)n_u * d * 4);          // gathered user rows for the TMA path
   L.total = off;
   return L;
 }
@@ -515,7 +516,7 @@ using namespace agcf;
 extern "C" int64_t agcf_score_topk_ws_bytes(int32_t n_u, int32_t n_items, int32_t d, int32_t K) {
   if (n_u < 0 || n_items <= 0 || K <= 0) return AGCF_EINVAL;
   if (!supported_d(d) || K > 1024) return AGCF_EUNSUPPORTED;
-  return (int64_t)ws_layout(n_u, n_items).total;
+  return (int64_t)ws_layout(n_u, n_items, d).total;
 }
 
 extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int32_t n_u,
@@ -529,7 +530,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   if (!supported_d(d) || K > 1024 || (impl != 0 && impl != 1)) return AGCF_EUNSUPPORTED;
   if (!aligned16(Uemb) || !aligned16(Iemb) || (reinterpret_cast<uintptr_t>(ws) & 255u)) return AGCF_EINVAL;
   if (n_u == 0) return AGCF_OK;
-  const WsLayout L = ws_layout(n_u, n_items);
+  const WsLayout L = ws_layout(n_u, n_items, d);
   if ((int64_t)L.total > ws_bytes) return AGCF_EWORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* base = reinterpret_cast<unsigned char*>(ws);
@@ -553,7 +554,8 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
     switch (d) { case 32: AGCF_NORM(32) break; case 64: AGCF_NORM(64) break; case 128: AGCF_NORM(128) break; case 256: AGCF_NORM(256) break; }
 #undef AGCF_NORM
     AGCF_LAUNCH_OK();
-    const int rc = launch_group_max_tc(Uemb, user_rows, n_u, Iemb, n_items, d, bits, L.n_groups, gmax, st);
+    const int rc = launch_group_max_tc(Uemb, user_rows, n_u, Iemb, n_items, d, bits, L.n_groups, gmax,
+                                       reinterpret_cast<float*>(base + L.udense_off), st);
     if (rc != AGCF_OK) return rc;
     margin_scale = 2.0f * 1.01f * 0.001953125f;      // 2 * delta, delta = 1.01 * 2^-9 * |u| * max|v|
   } else {

@@ -19,7 +19,8 @@ from . import ops
 from .util.metrics import format_measure
 
 USER_CHUNK = int(os.environ.get("ARLIB_B200_EVAL_CHUNK", "16384"))
-DEFAULT_IMPL = int(os.environ.get("ARLIB_B200_SCORE_IMPL", "0"))
+# stage-1 implementation of agcf_score_topk: 1 = TF32 tcgen05 GEMM (d <= 128), 0 = fp32 CUDA-core GEMM
+DEFAULT_IMPL = int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1"))
 
 
 def _csr_from_lists(lists, n_rows_hint=None):
@@ -101,6 +102,8 @@ class FullRankEvaluator:
     def topk(self, user_emb, item_emb, K, impl=None):
         """(values, ids) [n_test_users, K] on device, reference selection rule."""
         impl = DEFAULT_IMPL if impl is None else impl
+        if item_emb.shape[1] > 128:
+            impl = 0                      # the tcgen05 path is compiled for d in {32, 64, 128}
         user_emb = user_emb.detach().contiguous()
         item_emb = item_emb.detach().contiguous()
         n = self.user_rows.numel()
@@ -125,6 +128,8 @@ class FullRankEvaluator:
         merged on device (agcf_topk_merge).  Identical result on every rank."""
         import torch.distributed as dist
         impl = DEFAULT_IMPL if impl is None else impl
+        if item_emb.shape[1] > 128:
+            impl = 0
         n_items = item_emb.shape[0]
         i0 = n_items * rank // world
         i1 = n_items * (rank + 1) // world

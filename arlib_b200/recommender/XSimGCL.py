@@ -1,0 +1,64 @@
+"""XSimGCL -- drop-in for the reference's recommender/XSimGCL.py (class :18-95, encoder
+:179-223).  Hard-coded hyper-parameters like the reference (:32-36: 2 layers, cl_rate
+0.2, eps 0.1, layer_cl 1, tau 0.1).  One noise-perturbed propagation per step on
+agcf_spmm_csr_f32 (noise fused into the epilogue, the layer_cl view kept)."""
+import torch
+
+from ..encoder import TorchGraphInterface, XSimGCL_Encoder  # noqa: F401
+from ..util.loss import InfoNCE, bpr_loss, l2_reg_loss
+from ..util.sampler import next_batch_pairwise
+from ._base import GraphRecommender
+
+
+class XSimGCL(GraphRecommender):
+    model_name = "XSimGCL"
+
+    def _build_model(self):
+        self.n_layers = 2
+        self.cl_rate = 0.2
+        self.eps = 0.1
+        self.layer_cl = 1
+        self.temp = 0.1
+        return XSimGCL_Encoder(self.data, self.args.emb_size, self.eps, self.n_layers, self.layer_cl)
+
+    def cal_cl_loss(self, idx, user_view1, user_view2, item_view1, item_view2):
+        """recommender/XSimGCL.py:39-44 (ids pass through float32 like torch.Tensor(list))"""
+        dev = user_view1.device
+        u_idx = torch.unique(torch.Tensor(idx[0]).type(torch.long)).to(dev)
+        i_idx = torch.unique(torch.Tensor(idx[1]).type(torch.long)).to(dev)
+        return InfoNCE(user_view1[u_idx], user_view2[u_idx], self.temp) + \
+            InfoNCE(item_view1[i_idx], item_view2[i_idx], self.temp)
+
+    def train(self, requires_adjgrad=False, requires_embgrad=False, gradIterationNum=10, Epoch=0, optimizer=None,
+              evalNum=5):
+        self.bestPerformance = []
+        model = self.model.cuda()
+        if optimizer is None:
+            optimizer = torch.optim.Adam(model.parameters(), lr=self.args.lRate)
+        self._grad_buffers(requires_adjgrad, requires_embgrad, model)
+        maxEpoch = Epoch if Epoch else self.args.maxEpoch
+        dev = model.embedding_dict['user_emb'].device
+        for epoch in range(maxEpoch):
+            for n, batch in enumerate(next_batch_pairwise(self.data, self.args.batch_size)):
+                user_idx, pos_idx, neg_idx = batch
+                ut, pt, nt = (torch.tensor(x, dtype=torch.long, device=dev) for x in batch)
+                model.train()
+                rec_user_emb, rec_item_emb, cl_user_emb, cl_item_emb = model(True)
+                user_emb, pos_item_emb, neg_item_emb = rec_user_emb[ut], rec_item_emb[pt], rec_item_emb[nt]
+                rec_loss = bpr_loss(user_emb, pos_item_emb, neg_item_emb)
+                cl_loss = self.cl_rate * self.cal_cl_loss([user_idx, pos_idx], rec_user_emb, cl_user_emb, rec_item_emb,
+                                                          cl_item_emb)
+                batch_loss = rec_loss + l2_reg_loss(self.args.reg, user_emb, pos_item_emb) + cl_loss
+                optimizer.zero_grad()
+                batch_loss.backward()
+                self._accumulate_grads(requires_adjgrad, requires_embgrad, maxEpoch, epoch, gradIterationNum)
+                optimizer.step()
+                if n % 100 == 0:
+                    print('training:', epoch + 1, 'batch', n, 'rec_loss:', rec_loss.item(), 'cl_loss', cl_loss.item())
+            model.eval()
+            with torch.no_grad():
+                self.user_emb, self.item_emb = self.model()
+            if epoch % evalNum == 0:
+                self.evaluate(epoch)
+        self.user_emb, self.item_emb = self.best_user_emb, self.best_item_emb
+        return self._train_returns(requires_adjgrad, requires_embgrad)

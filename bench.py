@@ -367,7 +367,8 @@ def run_ours(args):
     flops = 2.0 * n_test * I * d
     tpeak = peaks.get("bf16_tflops", 1590.0)
     evald = {"users_per_s": n_test / (ev_ms * 1e-3), "unit": "users/s", "n_users": n_test, "ms": ev_ms,
-             "e2e_users_per_s": n_test / ev_e2e_s, "impl": int(os.environ.get("ARLIB_B200_SCORE_IMPL", "0")),
+             "e2e_users_per_s": n_test / ev_e2e_s,
+             "impl": "tcgen05-tf32 + exact fp32 rescore" if int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1")) == 1 else "fp32 cuda-core",
              "roofline": {"bound": "tensor", "achieved": flops / (ev_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                           "frac": flops / (ev_ms * 1e-3) / 1e12 / tpeak, "traffic": None,
                           "note": "whole eval pipeline (mask bits + group-max GEMM + select/rescore + metrics)"},

@@ -162,3 +162,23 @@ def test_rank_metrics_match_ranking_evaluation():
             ndcg += out[r, c, 1] / out[r, c, 2]
         assert want[5 * c + 1] == 'Hit Ratio:' + str(hr) + '\n'
         assert want[5 * c + 4] == 'NDCG:' + str(ndcg / U) + '\n'
+
+
+@pytest.mark.parametrize("U,I,d,K", [(300, 3000, 64, 50), (129, 257, 64, 10), (1000, 5000, 32, 20), (260, 1500, 128, 50),
+                                      (5, 40, 64, 3)])
+def test_tcgen05_stage1_gives_the_same_topk_as_the_fp32_path(U, I, d, K):
+    """impl=1 (TF32 tcgen05 group-max GEMM + margin + exact re-score) must return exactly
+    what impl=0 (fp32 CUDA-core stage 1) returns: the tensor-core rounding never leaks out."""
+    from arlib_b200 import ops
+    rng = np.random.default_rng(U * 7 + I)
+    ue = torch.randn(U, d).to(DEV)
+    ie = (torch.randn(I, d) * torch.rand(I, 1) * 2).to(DEV)          # varied item norms
+    lists = [rng.choice(I, size=int(rng.integers(0, min(I - K, 80))), replace=False) for _ in range(U)]
+    mrp, mit = _mask_csr(U, lists)
+    rows = torch.from_numpy(rng.permutation(U).astype(np.int32)).to(DEV)
+    for user_rows in (None, rows):
+        v0, i0, f0 = ops.score_topk(ue, ie, K, user_rows=user_rows, mask_rowptr=mrp, mask_items=mit, impl=0, return_flags=True)
+        v1, i1, f1 = ops.score_topk(ue, ie, K, user_rows=user_rows, mask_rowptr=mrp, mask_items=mit, impl=1, return_flags=True)
+        assert torch.equal(i0, i1) and torch.equal(v0, v1)
+        # the TF32 margin admits a few more candidate groups, not an explosion
+        assert float(f1.float().mean()) <= 3.0 * float(f0.float().mean()) + 4

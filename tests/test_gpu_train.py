@@ -101,3 +101,23 @@ def test_dropin_general_path_external_optimizer_and_grad_export(golden_rows):
     c.model._init_uiAdj(data.ui_adj)
     fu, fi = c.model()
     assert fu.shape == (data.user_num, 64) and fi.requires_grad
+
+
+@pytest.mark.parametrize("name", ["NGCF", "SimGCL", "XSimGCL"])
+def test_other_graph_recommenders_train_and_eval(name, golden_rows):
+    """The three other drop-in classes run their reference loop on the agcf kernels:
+    loss decreases, metrics improve over random, API shape holds."""
+    import importlib
+    from arlib_b200.util.DataLoader import DataLoader
+    train, test = golden_rows
+    data = DataLoader.from_rows([list(r) for r in train[:20000]], (), test)
+    random.seed(3); torch.manual_seed(3)
+    cls = getattr(importlib.import_module("arlib_b200.recommender." + name), name)
+    rec = cls(_args(model_name=name, maxEpoch=2), data)
+    rec.train(evalNum=1)
+    rec_list, measure = rec.test()
+    assert len(rec_list) == len(data.test_set) and measure[0] == "Top 50\n"
+    recall = float(measure[3].split(":")[1])
+    assert recall > 0.05, measure                      # random top-50 of ~1200 items would give ~0.04 at best
+    out = rec.train(requires_embgrad=True, Epoch=1)
+    assert len(out) == 4
