@@ -20,6 +20,7 @@
 //                           survivors are sorted by (score desc, item asc).
 #include "common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace agcf {
 
@@ -53,7 +54,7 @@ __device__ __forceinline__ float exact_dot(const float* __restrict__ urow_smem, 
 __global__ void __launch_bounds__(256) mask_bits_kernel(const int32_t* __restrict__ user_rows, int n_u,
                                                         const int32_t* __restrict__ mask_rowptr,
                                                         const int32_t* __restrict__ mask_items, int n_items,
-                                                        int item_offset, int n_groups, uint32_t* __restrict__ bits) {
+                                                        int item_offset, int pitch, uint32_t* __restrict__ bits) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_u) return;
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(256) mask_bits_kernel(const int32_t* __restric
   const int s = mask_rowptr[uid], e = mask_rowptr[uid + 1];
   for (int k = s + lane; k < e; k += 32) {
     const int it = mask_items[k] - item_offset;         // item shards: mask ids are global
-    if (it >= 0 && it < n_items) atomicOr(bits + (size_t)r * n_groups + (it >> 5), 1u << (it & 31));
+    if (it >= 0 && it < n_items) atomicOr(bits + (size_t)r * pitch + (it >> 5), 1u << (it & 31));
   }
 }
 
@@ -91,7 +92,7 @@ struct S1Smem { static constexpr int LD = D + 4; static constexpr size_t bytes =
 template <int D>
 __global__ void __launch_bounds__(256) group_max_fp32_kernel(const float4* __restrict__ Uemb, const int32_t* __restrict__ user_rows,
                                                              int n_u, const float4* __restrict__ Iemb, int n_items,
-                                                             const uint32_t* __restrict__ bits, int n_groups,
+                                                             const uint32_t* __restrict__ bits, int n_groups, int pitch,
                                                              int tiles_per_split, float* __restrict__ gmax) {
   constexpr int LD = D + 4;                 // padded row stride in floats (multiple of 4)
   constexpr int V4 = D / 4;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256) group_max_fp32_kernel(const float4* __res
       for (int q = 0; q < 4; ++q) {
         const int g = (i0 >> 5) + q;
         uint32_t w = 0u;
-        if (ur < n_u && g < n_groups) w = __ldg(bits + (size_t)ur * n_groups + g);
+        if (ur < n_u && g < n_groups) w = __ldg(bits + (size_t)ur * pitch + g);
         float m = -FLT_MAX;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(256) group_max_fp32_kernel(const float4* __res
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (tx == 0 && ur < n_u && g < n_groups) gmax[(size_t)ur * n_groups + g] = m;
+        if (tx == 0 && ur < n_u && g < n_groups) gmax[(size_t)ur * pitch + g] = m;
       }
     }
   }
@@ -229,8 +230,9 @@ __device__ uint32_t block_radix_select(SelectSmem& sm, int n, unsigned int R, Ke
   return sm.prefix;
 }
 
-// block-wide exclusive scan of one int per thread (256 threads); returns exclusive prefix, total via ref
-__device__ __forceinline__ int block_excl_scan_256(int v, int* warp_buf /*[9]*/, int& total) {
+// block-wide exclusive scan of one int per thread (256 threads): warp shuffles + one
+// barrier; the 8 warp totals go through a double-buffered smem row (``flip`` alternates)
+__device__ __forceinline__ int block_excl_scan_256(int v, int (*warp_buf)[8], int& flip, int& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int incl = v;
 #pragma unroll
@@ -238,17 +240,19 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int* warp_buf /*[9]*/,
     const int y = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += y;
   }
-  __syncthreads();                       // protect warp_buf reuse across calls
-  if (lane == 31) warp_buf[warp] = incl;
+  int* buf = warp_buf[flip];
+  flip ^= 1;
+  if (lane == 31) buf[warp] = incl;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int run = 0;
-    for (int w = 0; w < 8; ++w) { const int t = warp_buf[w]; warp_buf[w] = run; run += t; }
-    warp_buf[8] = run;
+  int before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const int t = buf[w];
+    all += t;
+    if (w < warp) before += t;
   }
-  __syncthreads();
-  total = warp_buf[8];
-  return warp_buf[warp] + incl - v;
+  total = all;
+  return before + incl - v;
 }
 
 struct Stage2Params {
@@ -260,6 +264,7 @@ struct Stage2Params {
   const uint32_t* bits;
   const float* gmax;
   int n_groups;
+  int pitch;                   // row stride (words) of bits / gmax
   int K;
   int item_offset;
   float margin_scale;          // 0 for impl 0; 2 * 1.01 * 2^-9 for TF32
@@ -275,7 +280,8 @@ struct Stage2Params {
 template <int D>
 __global__ void __launch_bounds__(256) topk_select_kernel(const Stage2Params p) {
   __shared__ SelectSmem sel;
-  __shared__ int warp_buf[9];
+  __shared__ int warp_buf[3][8];      // rotating rows: a row is rewritten only two scans (two barriers) later
+  int flip = 0;
   __shared__ __align__(16) float urow[D];
   __shared__ int sh_p_pos, sh_gp;
   extern __shared__ __align__(16) unsigned char dyn[];   // K-sized sort buffers
@@ -288,8 +294,8 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const Stage2Params p) 
 
   for (int r = blockIdx.x; r < p.n_u; r += gridDim.x) {
     const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
-    const float* grow = p.gmax + (size_t)r * p.n_groups;
-    const uint32_t* brow = p.bits + (size_t)r * p.n_groups;
+    const float* grow = p.gmax + (size_t)r * p.pitch;
+    const uint32_t* brow = p.bits + (size_t)r * p.pitch;
     __syncthreads();
     if (tid < D / 4) reinterpret_cast<float4*>(urow)[tid] = __ldg(p.Uemb + (size_t)uid * (D / 4) + tid);
     __syncthreads();
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const Stage2Params p) 
       const int g = base + tid;
       const int flag = (g < p.n_groups && grow[g] >= thr) ? 1 : 0;
       int total;
-      const int pos = block_excl_scan_256(flag, warp_buf, total);
+      const int pos = block_excl_scan_256(flag, warp_buf, flip, total);
       if (flag) my_groups[n_cg + pos] = g;
       n_cg += total;
     }
@@ -338,48 +344,53 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const Stage2Params p) 
     if (Keff > 0) {
       const uint32_t skey = block_radix_select(sel, nc, (unsigned int)Keff, [&](int k) { return f2key(my_val[k]); });
       const float sstar = key2f(skey);
-      // pass A: m, pos_p, g_p
+      // pass A: m, pos_p, g_p  (one packed scan per chunk: #(>= s*) in the low half, #(> s*) in the high half)
       if (tid == 0) { sh_p_pos = -1; sh_gp = 0; }
-      int m = 0, run_ge = 0, run_gt = 0;
+      int run_ge = 0, run_gt = 0;
       for (int base = 0; base < nc; base += 256) {
         const int k = base + tid;
         const float v = k < nc ? my_val[k] : -FLT_MAX;
-        const bool real = k < nc && (k < n_valid || v > -FLT_MAX);
+        const bool real = k < n_valid;
         const int gt = (real && v > sstar) ? 1 : 0;
         const int ge = (real && v >= sstar) ? 1 : 0;
-        int tot_ge, tot_gt;
-        const int ex_ge = block_excl_scan_256(ge, warp_buf, tot_ge);
-        const int ex_gt = block_excl_scan_256(gt, warp_buf, tot_gt);
+        int tot;
+        const int ex = block_excl_scan_256(ge | (gt << 16), warp_buf, flip, tot);
+        const int ex_ge = ex & 0xffff, ex_gt = ex >> 16;
         if (ge && run_ge + ex_ge + 1 == Keff) { sh_p_pos = k; sh_gp = run_gt + ex_gt + gt; }
-        run_ge += tot_ge;
-        run_gt += tot_gt;
+        run_ge += tot & 0xffff;
+        run_gt += tot >> 16;
       }
-      m = run_gt;
-      __syncthreads();
-      const int gp = sh_gp;
-      const int tie_lo = m - gp, tie_hi = Keff - gp;
+      const int m = run_gt;
       // pass B: select (ordered), pack (score key desc, idx asc) into 64-bit sort keys
       for (int k = tid; k < kpow2; k += 256) sort_keys[k] = ~0ull;
       __syncthreads();
-      int run_eq = 0, run_sel = 0;
+      const int gp = sh_gp;
+      const int tie_lo = m - gp, tie_n = Keff - m;                  // kept ties: tie-rank in [tie_lo, tie_lo + tie_n)
+      int run_eq = 0;
+      run_gt = 0;
       for (int base = 0; base < nc; base += 256) {
         const int k = base + tid;
         const float v = k < nc ? my_val[k] : -FLT_MAX;
-        const bool real = k < nc && (k < n_valid || v > -FLT_MAX);
+        const bool real = k < n_valid;
+        const int gt = (real && v > sstar) ? 1 : 0;
         const int eq = (real && v == sstar) ? 1 : 0;
-        int tot_eq, tot_sel;
-        const int ex_eq = block_excl_scan_256(eq, warp_buf, tot_eq);
-        const int trank = run_eq + ex_eq;
-        const int take = (real && (v > sstar || (eq && trank >= tie_lo && trank < tie_hi))) ? 1 : 0;
-        const int ex_sel = block_excl_scan_256(take, warp_buf, tot_sel);
+        int tot;
+        const int ex = block_excl_scan_256(eq | (gt << 16), warp_buf, flip, tot);
+        const int trank = run_eq + (ex & 0xffff);                    // ties before this one
+        const int gt_before = run_gt + (ex >> 16);
+        const bool take = gt || (eq && trank >= tie_lo && trank < tie_lo + tie_n);
         if (take) {
+          // output slot = selected items before this one = (> s*) before + kept ties before
+          int ties_before = trank - tie_lo;
+          ties_before = ties_before < 0 ? 0 : (ties_before > tie_n ? tie_n : ties_before);
           const int item = my_groups[k >> 5] * kGroup + (k & 31);
           // ascending sort of (~scorekey, item) == score desc, item asc
-          sort_keys[run_sel + ex_sel] = ((unsigned long long)(~f2key(v)) << 32) | (uint32_t)item;
+          sort_keys[gt_before + ties_before] = ((unsigned long long)(~f2key(v)) << 32) | (uint32_t)item;
         }
-        run_eq += tot_eq;
-        run_sel += tot_sel;
+        run_eq += tot & 0xffff;
+        run_gt += tot >> 16;
       }
+      const int run_sel = Keff;
       n_sel = run_sel;
       __syncthreads();
       for (int kk = 2; kk <= kpow2; kk <<= 1)
@@ -486,21 +497,33 @@ __global__ void __launch_bounds__(128) rank_metrics_kernel(const int32_t* __rest
 
 // provided by score_tc.cu (tcgen05 TF32 group-max GEMM)
 int launch_group_max_tc(const float* Uemb, const int32_t* user_rows, int n_u, const float* Iemb, int n_items, int d,
-                        const uint32_t* bits, int n_groups, float* gmax, float* u_dense, cudaStream_t st);
+                        const uint32_t* bits, int n_groups, int pitch, float* gmax, float* u_dense, cudaStream_t st);
 
 struct WsLayout {
   size_t bits_off, gmax_off, norm_off, groups_off, cval_off, udense_off, total;
-  int n_groups, grid2;
+  int n_groups, pitch, grid2;
 };
+
+static int stage2_ctas_per_sm() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("AGCF_STAGE2_CTAS_PER_SM");      // tuning hook
+    v = e ? atoi(e) : 4;
+    if (v < 1) v = 1;
+    if (v > 8) v = 8;
+  }
+  return v;
+}
 
 static WsLayout ws_layout(int n_u, int n_items, int d) {
   WsLayout L;
   L.n_groups = (n_items + kGroup - 1) / kGroup;
-  L.grid2 = n_u < 2 * kSMs ? (n_u > 0 ? n_u : 1) : 2 * kSMs;
+  L.pitch = (L.n_groups + 7) & ~7;                               // 32-byte rows: vector loads / stores in the tcgen05 epilogue
+  L.grid2 = n_u < stage2_ctas_per_sm() * kSMs ? (n_u > 0 ? n_u : 1) : stage2_ctas_per_sm() * kSMs;      // stage 2 is latency-bound per user: 8 CTAs / SM
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t off = 0;
-  L.bits_off = off; off = up(off + (size_t)n_u * L.n_groups * 4);
-  L.gmax_off = off; off = up(off + (size_t)n_u * L.n_groups * 4);
+  L.bits_off = off; off = up(off + (size_t)n_u * L.pitch * 4);
+  L.gmax_off = off; off = up(off + (size_t)n_u * L.pitch * 4);
   L.norm_off = off; off = up(off + 256);
   L.groups_off = off; off = up(off + (size_t)L.grid2 * L.n_groups * 4);
   L.cval_off = off; off = up(off + (size_t)L.grid2 * L.n_groups * kGroup * 4);
@@ -541,9 +564,9 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   const float4* I4 = reinterpret_cast<const float4*>(Iemb);
 
   // stage 0
-  AGCF_CUDA_OK(cudaMemsetAsync(bits, 0, (size_t)n_u * L.n_groups * 4, st));
+  AGCF_CUDA_OK(cudaMemsetAsync(bits, 0, (size_t)n_u * L.pitch * 4, st));
   if (mask_rowptr != nullptr) {
-    mask_bits_kernel<<<(unsigned)((n_u + 7) / 8), 256, 0, st>>>(user_rows, n_u, mask_rowptr, mask_items, n_items, item_offset, L.n_groups, bits);
+    mask_bits_kernel<<<(unsigned)((n_u + 7) / 8), 256, 0, st>>>(user_rows, n_u, mask_rowptr, mask_items, n_items, item_offset, L.pitch, bits);
     AGCF_LAUNCH_OK();
   }
   // stage 1
@@ -554,7 +577,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
     switch (d) { case 32: AGCF_NORM(32) break; case 64: AGCF_NORM(64) break; case 128: AGCF_NORM(128) break; case 256: AGCF_NORM(256) break; }
 #undef AGCF_NORM
     AGCF_LAUNCH_OK();
-    const int rc = launch_group_max_tc(Uemb, user_rows, n_u, Iemb, n_items, d, bits, L.n_groups, gmax,
+    const int rc = launch_group_max_tc(Uemb, user_rows, n_u, Iemb, n_items, d, bits, L.n_groups, L.pitch, gmax,
                                        reinterpret_cast<float*>(base + L.udense_off), st);
     if (rc != AGCF_OK) return rc;
     margin_scale = 2.0f * 1.01f * 0.001953125f;      // 2 * delta, delta = 1.01 * 2^-9 * |u| * max|v|
@@ -573,7 +596,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
     AGCF_CUDA_OK(cudaFuncSetAttribute(group_max_fp32_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)S1Smem<DD>::bytes));                                               \
     group_max_fp32_kernel<DD><<<grid, 256, S1Smem<DD>::bytes, st>>>(U4, user_rows, n_u, I4, n_items, bits,    \
-                                                                    L.n_groups, tps, gmax);                   \
+                                                                    L.n_groups, L.pitch, tps, gmax);          \
   }
     switch (d) { case 32: AGCF_S1(32) break; case 64: AGCF_S1(64) break; case 128: AGCF_S1(128) break; case 256: AGCF_S1(256) break; }
 #undef AGCF_S1
@@ -582,7 +605,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   // stage 2
   Stage2Params p;
   p.Uemb = U4; p.user_rows = user_rows; p.n_u = n_u; p.Iemb = I4; p.n_items = n_items;
-  p.bits = bits; p.gmax = gmax; p.n_groups = L.n_groups; p.K = K; p.item_offset = item_offset;
+  p.bits = bits; p.gmax = gmax; p.n_groups = L.n_groups; p.pitch = L.pitch; p.K = K; p.item_offset = item_offset;
   p.margin_scale = margin_scale; p.max_item_norm = norm;
   p.out_val = out_val; p.out_idx = out_idx; p.out_flags = out_flags;
   p.cand_groups = reinterpret_cast<int32_t*>(base + L.groups_off);

@@ -132,7 +132,7 @@ struct Smem {
 template <int D>
 __global__ void __launch_bounds__(kThreads, 1)
 group_max_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_constant__ CUtensorMap tmap_i,
-                    int n_u, int n_items, int n_groups, int n_item_tiles, int tiles_per_chunk, int n_chunks, int n_units,
+                    int n_u, int n_items, int n_groups, int pitch, int n_item_tiles, int tiles_per_chunk, int n_chunks, int n_units,
                     const uint32_t* __restrict__ bits, float* __restrict__ gmax) {
   using S = Smem<D>;
   constexpr int kTileN = S::kTileN;
@@ -225,36 +225,57 @@ group_max_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_con
       const int t1 = min(n_item_tiles, t0 + tiles_per_chunk);
       const int r = ut * kTileM + row_in_tile;
       const bool row_ok = r < n_u;
-      const uint32_t* brow = bits + (size_t)(row_ok ? r : 0) * n_groups;
-      float* grow = gmax + (size_t)(row_ok ? r : 0) * n_groups;
+      // rows of bits / gmax are `pitch` words apart (multiple of 8 = 32 B), a tile covers GPT consecutive
+      // groups: one aligned 16/32-byte vector per thread per tile for the mask words and for the maxima
+      constexpr int GPT = kTileN / 32;                               // groups per tile: 8 (or 4 for d = 128)
+      const uint32_t* brow = bits + (size_t)(row_ok ? r : 0) * pitch;
+      float* grow = gmax + (size_t)(row_ok ? r : 0) * pitch;
+      uint32_t w[GPT], wn[GPT];
+#pragma unroll
+      for (int q = 0; q < GPT; q += 4) {
+        const uint4 x = row_ok ? __ldg(reinterpret_cast<const uint4*>(brow + t0 * GPT + q)) : make_uint4(0u, 0u, 0u, 0u);
+        w[q] = x.x; w[q + 1] = x.y; w[q + 2] = x.z; w[q + 3] = x.w;
+      }
       for (int t = t0; t < t1; ++t) {
+        if (t + 1 < t1) {                                            // mask words of the next tile: in flight during this one
+#pragma unroll
+          for (int q = 0; q < GPT; q += 4) {
+            const uint4 x = row_ok ? __ldg(reinterpret_cast<const uint4*>(brow + (t + 1) * GPT + q)) : make_uint4(0u, 0u, 0u, 0u);
+            wn[q] = x.x; wn[q + 1] = x.y; wn[q + 2] = x.z; wn[q + 3] = x.w;
+          }
+        }
         mbar_wait(&bars->acc_full[acc], acc_phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kTileN;
-#pragma unroll 1
-        for (int q = 0; q < kTileN / 32; ++q) {
+        float mx[GPT];
+#pragma unroll
+        for (int q = 0; q < GPT; ++q) {
           uint32_t v[32];
           tmem_ld32(taddr + q * 32, v);
-          const int g = t * (kTileN / 32) + q;
-          if (g < n_groups) {
-            const int valid = min(32, n_items - g * 32);           // the table's last group may be partial
-            const uint32_t w = row_ok ? __ldg(brow + g) : 0u;
-            float m = -FLT_MAX;
-            if (w == 0u && valid == 32) {
+          const int g = t * GPT + q;
+          const int valid = n_items - g * 32;                        // < 32 only in the table's last group; <= 0 past it
+          float m = -FLT_MAX;
+          if (w[q] == 0u && valid >= 32) {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(v[c]));
-            } else {
+            for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(v[c]));
+          } else {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                float s = __uint_as_float(v[c]);
-                if ((w >> c) & 1u) s = kMaskedScore;
-                if (c >= valid) s = -FLT_MAX;
-                m = fmaxf(m, s);
-              }
+            for (int c = 0; c < 32; ++c) {
+              float sc = __uint_as_float(v[c]);
+              if ((w[q] >> c) & 1u) sc = kMaskedScore;
+              if (c >= valid) sc = -FLT_MAX;
+              m = fmaxf(m, sc);
             }
-            if (row_ok) grow[g] = m;
           }
+          mx[q] = m;
         }
+        if (row_ok) {
+#pragma unroll
+          for (int q = 0; q < GPT; q += 4)
+            *reinterpret_cast<float4*>(grow + t * GPT + q) = make_float4(mx[q], mx[q + 1], mx[q + 2], mx[q + 3]);
+        }
+#pragma unroll
+        for (int q = 0; q < GPT; ++q) w[q] = wn[q];
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
@@ -311,8 +332,8 @@ static int make_tmap(CUtensorMap* m, const float* base, int rows, int d, int box
 }
 
 template <int D>
-static int launch(const float* U, int n_u, const float* I, int n_items, const uint32_t* bits, int n_groups, float* gmax,
-                  cudaStream_t st) {
+static int launch(const float* U, int n_u, const float* I, int n_items, const uint32_t* bits, int n_groups, int pitch,
+                  float* gmax, cudaStream_t st) {
   CUtensorMap tu, ti;
   int rc = make_tmap(&tu, U, n_u, D, kTileM);
   if (rc != AGCF_OK) return rc;
@@ -330,7 +351,7 @@ static int launch(const float* U, int n_u, const float* I, int n_items, const ui
   const int n_units = n_user_tiles * n_chunks;
   const int grid = n_units < kSMs ? n_units : kSMs;
   AGCF_CUDA_OK(cudaFuncSetAttribute(group_max_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<D>::kTotal));
-  group_max_tc_kernel<D><<<grid, kThreads, Smem<D>::kTotal, st>>>(tu, ti, n_u, n_items, n_groups, n_item_tiles, tiles_per_chunk,
+  group_max_tc_kernel<D><<<grid, kThreads, Smem<D>::kTotal, st>>>(tu, ti, n_u, n_items, n_groups, pitch, n_item_tiles, tiles_per_chunk,
                                                                   n_chunks, n_units, bits, gmax);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
@@ -340,7 +361,7 @@ static int launch(const float* U, int n_u, const float* I, int n_items, const ui
 
 // entry point used by agcf_score_topk (score.cu); `u_dense` is workspace for the gathered user rows
 int launch_group_max_tc(const float* Uemb, const int32_t* user_rows, int n_u, const float* Iemb, int n_items, int d,
-                        const uint32_t* bits, int n_groups, float* gmax, float* u_dense, cudaStream_t st) {
+                        const uint32_t* bits, int n_groups, int pitch, float* gmax, float* u_dense, cudaStream_t st) {
   const float* U = Uemb;
   if (user_rows != nullptr) {
     const long long n4 = (long long)n_u * (d / 4);
@@ -352,9 +373,9 @@ int launch_group_max_tc(const float* Uemb, const int32_t* user_rows, int n_u, co
     U = u_dense;
   }
   switch (d) {
-    case 32: return tc::launch<32>(U, n_u, Iemb, n_items, bits, n_groups, gmax, st);
-    case 64: return tc::launch<64>(U, n_u, Iemb, n_items, bits, n_groups, gmax, st);
-    case 128: return tc::launch<128>(U, n_u, Iemb, n_items, bits, n_groups, gmax, st);
+    case 32: return tc::launch<32>(U, n_u, Iemb, n_items, bits, n_groups, pitch, gmax, st);
+    case 64: return tc::launch<64>(U, n_u, Iemb, n_items, bits, n_groups, pitch, gmax, st);
+    case 128: return tc::launch<128>(U, n_u, Iemb, n_items, bits, n_groups, pitch, gmax, st);
   }
   return AGCF_EUNSUPPORTED;
 }

@@ -364,6 +364,10 @@ def run_ours(args):
     idx_host = idx.cpu()
     torch.cuda.synchronize()
     ev_e2e_s = time.perf_counter() - t0
+    _, _, cg = ops.score_topk(F[:U].contiguous(), F[U:].contiguous(), TOPK, user_rows=ev.user_rows[:4096].contiguous(),
+                              mask_rowptr=ev.mask_rowptr, mask_items=ev.mask_items,
+                              impl=int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1")), return_flags=True)
+    cand_groups = float(cg.float().mean().item())
     flops = 2.0 * n_test * I * d
     tpeak = peaks.get("bf16_tflops", 1590.0)
     evald = {"users_per_s": n_test / (ev_ms * 1e-3), "unit": "users/s", "n_users": n_test, "ms": ev_ms,
@@ -372,7 +376,7 @@ def run_ours(args):
              "roofline": {"bound": "tensor", "achieved": flops / (ev_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                           "frac": flops / (ev_ms * 1e-3) / 1e12 / tpeak, "traffic": None,
                           "note": "whole eval pipeline (mask bits + group-max GEMM + select/rescore + metrics)"},
-             "measure": [m.strip() for m in measure]}
+             "candidate_groups_mean": cand_groups, "measure": [m.strip() for m in measure]}
 
     line = {
         "metric": "LightGCN train triples/s", "value": value, "unit": "triples/s", "n_gpus": world, "steps": K,
