@@ -18,6 +18,17 @@
 //                           largest exact score s* is radix-selected, ties at s* are
 //                           resolved with the reference heap's rule, and the K
 //                           survivors are sorted by (score desc, item asc).
+//
+// Why the result is exact although stage 1 may be approximate (impl 1, TF32):
+//   let e_i be the exact (fp32, fixed-order) masked score of item i, a_i the stage-1 value,
+//   |a_i - e_i| <= delta for all i (TF32 truncates each operand by < 2^-10 relative, so
+//   |a_i - e_i| <= 2^-9 * sum_k |u_k v_ik| (1 + o(1)) <= 1.01 * 2^-9 * |u| * max_i |v_i| =: delta).
+//   tau := K-th largest GROUP maximum of a.  The K groups attaining it contain K distinct items
+//   with a >= tau, hence e >= tau - delta, hence the K-th largest exact score s* >= tau - delta.
+//   Any item of the exact top-K (incl. every item tied at s*) has e_i >= s* >= tau - delta, so
+//   a_i >= tau - 2*delta, so its group's maximum is >= tau - 2*delta: it is in a candidate group.
+//   Candidates are re-scored exactly and the selection / tie rule only look at items with
+//   e >= s*, all of which are candidates.  For impl 0, a == e bit for bit and delta = 0.
 #include "common.cuh"
 #include <float.h>
 #include <stdlib.h>
