@@ -11,7 +11,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libagcf.so")
+# ARLIB_B200_LIB selects another BUILD of the same library (kernel tuning experiments); never a fallback
+LIB_PATH = os.environ.get("ARLIB_B200_LIB") or os.path.join(_HERE, "libagcf.so")
 
 AGCF_OK = 0
 _ERR = {-1: "AGCF_EINVAL", -2: "AGCF_EUNSUPPORTED", -3: "AGCF_ECUDA", -4: "AGCF_EWORKSPACE"}
@@ -24,6 +25,7 @@ SIGNATURES = {
     "agcf_abi_version": (c_int32, []),
     "agcf_strerror": (c_char_p, [c_int32]),
     "agcf_last_cuda_error": (c_int32, []),
+    "agcf_last_cuda_error_where": (c_char_p, []),
     "agcf_device_sm_count": (c_int32, []),
     "agcf_norm_adj_csr": (c_int32, [P, P, P, P, P, P, I32, I64, P]),
     "agcf_csr_expand_rows": (c_int32, [P, P, I32, I64, P]),
@@ -78,7 +80,7 @@ def check(rc, what=""):
     lib = load()
     msg = "%s failed: %s (%s)" % (what or "agcf call", _ERR.get(rc, rc), lib.agcf_strerror(rc).decode())
     if rc == -3:
-        msg += " cudaError=%d" % lib.agcf_last_cuda_error()
+        msg += " cudaError=%d: %s" % (lib.agcf_last_cuda_error(), lib.agcf_last_cuda_error_where().decode())
     raise AgcfError(msg)
 
 

@@ -7,26 +7,32 @@
 namespace agcf {
 
 extern thread_local int g_last_cuda_error;
+extern thread_local const char* g_last_cuda_file;
+extern thread_local int g_last_cuda_line;
 
-inline int cuda_fail(cudaError_t e) {
+inline int cuda_fail(cudaError_t e, const char* file = "", int line = 0) {
   g_last_cuda_error = (int)e;
+  g_last_cuda_file = file;
+  g_last_cuda_line = line;
   return AGCF_ECUDA;
 }
 
-#define AGCF_CUDA_OK(expr)                                   \
-  do {                                                       \
-    cudaError_t _e = (expr);                                 \
-    if (_e != cudaSuccess) return ::agcf::cuda_fail(_e);     \
+#define AGCF_CUDA_OK(expr)                                                       \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) return ::agcf::cuda_fail(_e, __FILE__, __LINE__);     \
   } while (0)
 
-#define AGCF_LAUNCH_OK()                                     \
-  do {                                                       \
-    cudaError_t _e = cudaGetLastError();                     \
-    if (_e != cudaSuccess) return ::agcf::cuda_fail(_e);     \
+#define AGCF_LAUNCH_OK()                                                         \
+  do {                                                                           \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) return ::agcf::cuda_fail(_e, __FILE__, __LINE__);     \
   } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool supported_d(int d) { return d == 32 || d == 64 || d == 128 || d == 256; }
+// row kernels (propagation, loss, optimizer) also take the narrow column slices of the d-sharded multi-GPU tables
+inline bool supported_row_d(int d) { return d == 8 || d == 16 || supported_d(d); }
 
 constexpr int kSMs = 148;  // B200
 

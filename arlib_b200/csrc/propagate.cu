@@ -57,7 +57,7 @@ __device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ m, int k) {
   return (__ldg(m + (k >> 5)) >> (k & 31)) & 1u;
 }
 
-constexpr int default_lpr(int d) { return d / 8 < 8 ? 8 : (d / 8 > 32 ? 32 : d / 8); }   // 8 (d<=64), 16 (128), 32 (256)
+constexpr int default_lpr(int d) { return d / 4 < 32 ? d / 4 : 32; }   // one float4 per lane up to d = 128
 
 template <int D, int LPR_ = default_lpr(D)>
 struct RowCfg {
@@ -65,6 +65,8 @@ struct RowCfg {
   static constexpr int LPR = LPR_;                    // lanes per row
   static constexpr int VPL = V4 / LPR;                // float4 per lane
   static constexpr int RPW = 32 / LPR;                // rows per warp
+  static constexpr int EPL = LPR >= 16 ? 1 : 16 / LPR;  // col/val entries per lane and chunk
+  static constexpr int CH = LPR * EPL;                // entries per chunk: >= 16 gathers in flight per lane group
   static constexpr int THREADS = 256;
   static constexpr int RPB = (THREADS / 32) * RPW;    // rows per block (short path)
   static constexpr int GROUPS = THREADS / LPR;        // lane groups per block (long path)
@@ -79,7 +81,8 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
   const size_t rbase = (size_t)row * C::V4;
   if (p.addend != nullptr && valid) {
 #pragma unroll
-    for (int v = 0; v < C::VPL; ++v) t[v] = add4(t[v], ld_stream_f4(p.addend + rbase + v * C::LPR + gl));
+    for (int v = 0; v < C::VPL; ++v)
+      t[v] = add4(t[v], ld_stream_f4(p.addend + rbase + v * C::LPR + gl));
   }
   if (NOISE) {
     float4 nz[C::VPL];
@@ -128,104 +131,95 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
 
 // accumulate nnz [s + first, s + first + stride*k ...) chunk-wise; `len` = row length,
 // `first`/`stride` = this lane group's starting offset and per-iteration advance,
-// `iters` and `bound_len` are WARP-UNIFORM (shuffles use the full mask): bound_len is
-// an upper bound of (len - first) over the warp's groups.
-//   MODE 0: inner loop fully unrolled over the LPR slots, loads predicated on (t < n)
-//   MODE 1: inner loop runs min(LPR, bound) times (warp-uniform), branch on (ct >= 0)
-//   MODE 2: as 1 but in explicit sub-blocks of 4 slots: all gathers first, then the FMAs
-template <typename C, int MODE>
-__device__ __forceinline__ void spmm_accumulate(const SpmmParams& p, int s, int len, int first, int stride,
-                                                int iters, int bound_len, int gl, float4 (&acc)[C::VPL]) {
-  int c_next = -1;
-  float v_next = 0.f;
-  if (first + gl < len) {
-    c_next = ld_stream_i32(p.col + s + first + gl);
-    v_next = ld_stream_f32(p.val + s + first + gl);
-    if (p.col_mask != nullptr && !bit_set(p.col_mask, c_next)) c_next = -1;
-  }
-  int off = first;
-  int bound = bound_len;
-  for (int it = 0; it < iters; ++it, off += stride, bound -= stride) {
-    const int c = c_next;
-    const float v = v_next;
-    c_next = -1;
-    v_next = 0.f;
-    if (off + stride + gl < len) {                       // prefetch the next chunk's indices
-      c_next = ld_stream_i32(p.col + s + off + stride + gl);
-      v_next = ld_stream_f32(p.val + s + off + stride + gl);
-      if (p.col_mask != nullptr && !bit_set(p.col_mask, c_next)) c_next = -1;
-    }
-    if (MODE == 0 || MODE == 4) {
+// `iters` is WARP-UNIFORM (shuffles use the full mask).  A lane group walks its row in chunks of CH = LPR * EPL entries: lane gl holds
+// entries k * LPR + gl (k < EPL) of the chunk -- consecutive lanes read consecutive col/val words --
+// and every entry is broadcast by shuffle; the CH slots are fully unrolled and predicated, so up to CH
+// independent row gathers are in flight per lane while the next chunk's indices are already loading.
+// For narrow rows (d/4 < 16 lanes, the d-sharded multi-GPU tables) EPL > 1 keeps CH at 16.
+// one chunk held in registers (lane gl owns entries k * LPR + gl): broadcast every entry to the lane group and
+// gather-accumulate its row of X; slots with col < 0 (row end, masked column, padding) are predicated off
+template <typename C, bool PACKED>
+__device__ __forceinline__ void spmm_consume_chunk(const SpmmParams& p, const int (&c)[C::EPL], const float (&v)[C::EPL],
+                                                   int gl, float4 (&acc)[C::VPL]) {
 #pragma unroll
-      for (int t = 0; t < C::LPR; ++t) {
-        const int ct = __shfl_sync(0xffffffffu, c, t, C::LPR);
-        const float vt = __shfl_sync(0xffffffffu, v, t, C::LPR);
-        if (ct >= 0) {
-          const float4* xr = p.X + (size_t)ct * C::V4 + gl;
+  for (int k = 0; k < C::EPL; ++k) {
 #pragma unroll
-          for (int vv = 0; vv < C::VPL; ++vv) {
-            if (MODE == 4) fma4_packed(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
-            else fma4(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
-          }
+    for (int t = 0; t < C::LPR; ++t) {
+      const int ct = __shfl_sync(0xffffffffu, c[k], t, C::LPR);
+      const float vt = __shfl_sync(0xffffffffu, v[k], t, C::LPR);
+      if (ct >= 0) {
+        const float4* xr = p.X + (size_t)ct * C::V4 + gl;
+#pragma unroll
+        for (int vv = 0; vv < C::VPL; ++vv) {
+          if (PACKED) fma4_packed(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
+          else fma4(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
         }
-      }
-    } else if (MODE == 1) {
-      const int nmax = bound < C::LPR ? bound : C::LPR;   // warp-uniform
-#pragma unroll 4
-      for (int t = 0; t < nmax; ++t) {
-        const int ct = __shfl_sync(0xffffffffu, c, t, C::LPR);
-        const float vt = __shfl_sync(0xffffffffu, v, t, C::LPR);
-        if (ct >= 0) {                                     // lanes past their row's end hold c = -1
-          const float4* xr = p.X + (size_t)ct * C::V4 + gl;
-#pragma unroll
-          for (int vv = 0; vv < C::VPL; ++vv) fma4(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
-        }
-      }
-    } else if (MODE == 3) {
-      // quad-blocked: warp-uniform branch per 4 slots (padding <= 3 slots), slots predicated,
-      // packed FFMA2 accumulation
-      const int nmax = bound < C::LPR ? bound : C::LPR;   // warp-uniform
-#pragma unroll
-      for (int q = 0; q < C::LPR / 4; ++q) {
-        if (4 * q < nmax) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int ct = __shfl_sync(0xffffffffu, c, 4 * q + r, C::LPR);
-            const float vt = __shfl_sync(0xffffffffu, v, 4 * q + r, C::LPR);
-            if (ct >= 0) {
-              const float4* xr = p.X + (size_t)ct * C::V4 + gl;
-#pragma unroll
-              for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
-            }
-          }
-        }
-      }
-    } else {
-      const int nmax = bound < C::LPR ? bound : C::LPR;   // warp-uniform
-      for (int t0 = 0; t0 < nmax; t0 += 4) {
-        float4 x[4][C::VPL];
-        float vt[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ct = __shfl_sync(0xffffffffu, c, (t0 + q) & (C::LPR - 1), C::LPR);
-          vt[q] = __shfl_sync(0xffffffffu, v, (t0 + q) & (C::LPR - 1), C::LPR);
-          const bool live = ct >= 0 && (t0 + q) < C::LPR;
-          if (!live) vt[q] = 0.f;
-          const float4* xr = p.X + (size_t)(live ? ct : 0) * C::V4 + gl;
-#pragma unroll
-          for (int vv = 0; vv < C::VPL; ++vv)
-            x[q][vv] = live ? ld_gather_f4(xr + vv * C::LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int vv = 0; vv < C::VPL; ++vv) fma4(acc[vv], vt[q], x[q][vv]);
       }
     }
   }
 }
 
-template <int D, int LPR, int MODE, int MINB, bool NOISE>
+template <typename C, bool PACKED>
+__device__ __forceinline__ void spmm_accumulate_chunks(const SpmmParams& p, int s, int len, int first, int stride,
+                                                       int iters, int gl, float4 (&acc)[C::VPL]) {
+  int c_next[C::EPL];
+  float v_next[C::EPL];
+  auto load_chunk = [&](int off) {
+#pragma unroll
+    for (int k = 0; k < C::EPL; ++k) {
+      c_next[k] = -1;
+      v_next[k] = 0.f;
+      const int e = off + k * C::LPR + gl;
+      if (e < len) {
+        c_next[k] = ld_stream_i32(p.col + s + e);
+        v_next[k] = ld_stream_f32(p.val + s + e);
+        if (p.col_mask != nullptr && !bit_set(p.col_mask, c_next[k])) c_next[k] = -1;
+      }
+    }
+  };
+  load_chunk(first);
+  int off = first;
+  for (int it = 0; it < iters; ++it, off += stride) {
+    int c[C::EPL];
+    float v[C::EPL];
+#pragma unroll
+    for (int k = 0; k < C::EPL; ++k) { c[k] = c_next[k]; v[k] = v_next[k]; }
+    load_chunk(off + stride);                              // prefetch the next chunk's indices
+    spmm_consume_chunk<C, PACKED>(p, c, v, gl, acc);
+  }
+}
+
+// long row: the whole CTA cooperates on one row (slot = blockIdx.x); partial sums of the lane groups are
+// reduced through shared memory in a fixed order (no atomics, run-to-run deterministic)
+template <typename C, bool NOISE>
+__device__ __forceinline__ void spmm_long_row(const SpmmParams& p, float4 (&acc)[C::VPL], int lane, int warp, int gl) {
+  __shared__ float4 part[C::GROUPS][C::V4];
+  const int row = p.row_order != nullptr ? p.row_order[blockIdx.x] : (int)blockIdx.x;
+  if (p.row_mask != nullptr && !bit_set(p.row_mask, row)) return;      // block-uniform
+  const int s = p.rowptr[blockIdx.x];
+  const int len = p.rowptr[blockIdx.x + 1] - s;
+  const int g = threadIdx.x / C::LPR;
+  const int stride = C::GROUPS * C::CH;
+  const int iters = (len + stride - 1) / stride;       // block-uniform
+  spmm_accumulate_chunks<C, true>(p, s, len, g * C::CH, stride, iters, gl, acc);
+#pragma unroll
+  for (int v = 0; v < C::VPL; ++v) part[g][v * C::LPR + gl] = acc[v];
+  __syncthreads();
+  if (warp == 0) {
+    const bool valid = lane < C::LPR;
+    float4 t[C::VPL];
+#pragma unroll
+    for (int v = 0; v < C::VPL; ++v) {
+      t[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        for (int gg = 0; gg < C::GROUPS; ++gg) t[v] = add4(t[v], part[gg][v * C::LPR + gl]);
+      }
+    }
+    spmm_epilogue<C, NOISE>(p, row, valid, t, gl);
+  }
+}
+
+template <int D, int LPR, int MINB, bool NOISE>
 __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
   using C = RowCfg<D, LPR>;
   const int lane = threadIdx.x & 31;
@@ -236,31 +230,7 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
   for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   if ((int)blockIdx.x < p.n_long) {
-    // ---- long row: the whole CTA cooperates on one row --------------------------
-    __shared__ float4 part[C::GROUPS][C::V4];
-    const int row = p.row_order != nullptr ? p.row_order[blockIdx.x] : (int)blockIdx.x;
-    if (p.row_mask != nullptr && !bit_set(p.row_mask, row)) return;      // block-uniform
-    const int s = p.rowptr[blockIdx.x];
-    const int len = p.rowptr[blockIdx.x + 1] - s;
-    const int g = threadIdx.x / C::LPR;
-    const int stride = C::GROUPS * C::LPR;
-    const int iters = (len + stride - 1) / stride;       // block-uniform
-    spmm_accumulate<C, MODE>(p, s, len, g * C::LPR, stride, iters, len, gl, acc);
-#pragma unroll
-    for (int v = 0; v < C::VPL; ++v) part[g][v * C::LPR + gl] = acc[v];
-    __syncthreads();
-    if (warp == 0) {
-      const bool valid = lane < C::LPR;
-      float4 t[C::VPL];
-#pragma unroll
-      for (int v = 0; v < C::VPL; ++v) {
-        t[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-          for (int gg = 0; gg < C::GROUPS; ++gg) t[v] = add4(t[v], part[gg][v * C::LPR + gl]);
-        }
-      }
-      spmm_epilogue<C, NOISE>(p, row, valid, t, gl);
-    }
+    spmm_long_row<C, NOISE>(p, acc, lane, warp, gl);
     return;
   }
 
@@ -270,13 +240,11 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
   bool valid = slot < p.n_rows;
   int row = 0, s = 0, len = 0;
   if (valid) {
-    row = p.row_order != nullptr ? p.row_order[slot] : (int)slot;
-    if (p.row_mask != nullptr && !bit_set(p.row_mask, row)) {
-      valid = false;
-    } else {
-      s = p.rowptr[slot];
-      len = p.rowptr[slot + 1] - s;
-    }
+    // row id and row extent are both addressed by the slot: independent loads
+    row = p.row_order != nullptr ? __ldg(p.row_order + slot) : (int)slot;
+    s = __ldg(p.rowptr + slot);
+    len = __ldg(p.rowptr + slot + 1) - s;
+    if (p.row_mask != nullptr && !bit_set(p.row_mask, row)) { valid = false; len = 0; }
   }
   int maxlen = len;
 #pragma unroll
@@ -284,228 +252,32 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
     const int other = __shfl_xor_sync(0xffffffffu, maxlen, o);
     maxlen = other > maxlen ? other : maxlen;
   }
-  const int iters = (maxlen + C::LPR - 1) / C::LPR;      // warp-uniform
-  spmm_accumulate<C, MODE>(p, s, len, 0, C::LPR, iters, maxlen, gl, acc);
+  const int iters = (maxlen + C::CH - 1) / C::CH;        // warp-uniform
+  spmm_accumulate_chunks<C, true>(p, s, len, 0, C::CH, iters, gl, acc);
   spmm_epilogue<C, NOISE>(p, row, valid, acc, gl);
 }
 
-// ---------------------------------------------------------------- persistent kernel
-// The row-per-group kernel above is latency-bound: per task a warp walks a chain of
-// DEPENDENT global loads (row id -> rowptr -> col/val -> gathers -> epilogue operand)
-// and only the gather phase moves real data.  This version keeps every warp resident
-// and software-pipelines that chain ACROSS tasks: while task t is gathering, the
-// metadata of task t+2 and the first col/val chunk of task t+1 are already in flight.
-struct TaskMeta {
-  int row, s, len;
-  bool valid;
-};
+// resident CTAs per SM the register allocation is held to: 4 (<= 64 registers) measured best at d <= 64
+#ifndef AGCF_SPMM_MINB
+#define AGCF_SPMM_MINB(D) ((D) <= 64 ? 4 : ((D) == 128 ? 3 : 2))
+#endif
 
-template <typename C>
-__device__ __forceinline__ TaskMeta load_task_meta(const SpmmParams& p, long long task, long long n_tasks, int grp) {
-  TaskMeta m;
-  m.row = 0; m.s = 0; m.len = 0; m.valid = false;
-  const long long slot = (long long)p.n_long + task * C::RPW + grp;
-  if (task < n_tasks && slot < p.n_rows) {
-    m.row = p.row_order != nullptr ? __ldg(p.row_order + slot) : (int)slot;
-    m.s = __ldg(p.rowptr + slot);
-    m.len = __ldg(p.rowptr + slot + 1) - m.s;
-    m.valid = true;
-  }
-  return m;
-}
-
-template <typename C>
-__device__ __forceinline__ void load_first_chunk(const SpmmParams& p, TaskMeta& m, int gl, int& c, float& v) {
-  // the row mask is resolved here (one stage after the row id arrived)
-  if (m.valid && p.row_mask != nullptr && !bit_set(p.row_mask, m.row)) { m.valid = false; m.len = 0; }
-  c = -1;
-  v = 0.f;
-  if (gl < m.len) {
-    c = ld_stream_i32(p.col + m.s + gl);
-    v = ld_stream_f32(p.val + m.s + gl);
-    if (p.col_mask != nullptr && !bit_set(p.col_mask, c)) c = -1;
-  }
-}
-
-template <int D, int LPR, int MINB, bool NOISE>
-__global__ void __launch_bounds__(256, MINB) spmm_pipe_kernel(const SpmmParams p) {
-  using C = RowCfg<D, LPR>;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int gl = lane & (C::LPR - 1);
-
-  if ((int)blockIdx.x < p.n_long) {
-    // ---- long row: the whole CTA cooperates on one row (same as the simple kernel) ----
-    __shared__ float4 part[C::GROUPS][C::V4];
-    float4 acc[C::VPL];
-#pragma unroll
-    for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int row = p.row_order != nullptr ? p.row_order[blockIdx.x] : (int)blockIdx.x;
-    if (p.row_mask != nullptr && !bit_set(p.row_mask, row)) return;
-    const int s = p.rowptr[blockIdx.x];
-    const int len = p.rowptr[blockIdx.x + 1] - s;
-    const int g = threadIdx.x / C::LPR;
-    const int stride = C::GROUPS * C::LPR;
-    const int iters = (len + stride - 1) / stride;
-    spmm_accumulate<C, 0>(p, s, len, g * C::LPR, stride, iters, len, gl, acc);
-#pragma unroll
-    for (int v = 0; v < C::VPL; ++v) part[g][v * C::LPR + gl] = acc[v];
-    __syncthreads();
-    if (warp == 0) {
-      const bool valid = lane < C::LPR;
-      float4 t[C::VPL];
-#pragma unroll
-      for (int v = 0; v < C::VPL; ++v) {
-        t[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) {
-          for (int gg = 0; gg < C::GROUPS; ++gg) t[v] = add4(t[v], part[gg][v * C::LPR + gl]);
-        }
-      }
-      spmm_epilogue<C, NOISE>(p, row, valid, t, gl);
-    }
-    return;
-  }
-
-  const int grp = lane / C::LPR;
-  const long long n_short = (long long)p.n_rows - p.n_long;
-  const long long n_tasks = (n_short + C::RPW - 1) / C::RPW;
-  const long long W = (long long)(gridDim.x - p.n_long) * (C::THREADS / 32);
-  long long task = (long long)(blockIdx.x - p.n_long) * (C::THREADS / 32) + warp;
-  if (task >= n_tasks) return;                                  // warp-uniform
-  TaskMeta m0 = load_task_meta<C>(p, task, n_tasks, grp);
-  TaskMeta m1 = load_task_meta<C>(p, task + W, n_tasks, grp);
-  int c0; float v0;
-  load_first_chunk<C>(p, m0, gl, c0, v0);
-  for (; task < n_tasks; task += W) {
-    TaskMeta m2 = load_task_meta<C>(p, task + 2 * W, n_tasks, grp);      // two tasks ahead
-    int c1; float v1;
-    load_first_chunk<C>(p, m1, gl, c1, v1);                                // one task ahead
-    // ---- current task -------------------------------------------------------------
-    float4 acc[C::VPL];
-#pragma unroll
-    for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int maxlen = m0.len;
-#pragma unroll
-    for (int o = C::LPR; o < 32; o <<= 1) {
-      const int other = __shfl_xor_sync(0xffffffffu, maxlen, o);
-      maxlen = other > maxlen ? other : maxlen;
-    }
-    int c = c0;
-    float v = v0;
-    for (int off = 0; off < maxlen; off += C::LPR) {
-      int cn = -1;
-      float vn = 0.f;
-      if (off + C::LPR + gl < m0.len) {                          // next chunk of this row
-        cn = ld_stream_i32(p.col + m0.s + off + C::LPR + gl);
-        vn = ld_stream_f32(p.val + m0.s + off + C::LPR + gl);
-        if (p.col_mask != nullptr && !bit_set(p.col_mask, cn)) cn = -1;
-      }
-#pragma unroll
-      for (int t = 0; t < C::LPR; ++t) {
-        const int ct = __shfl_sync(0xffffffffu, c, t, C::LPR);
-        const float vt = __shfl_sync(0xffffffffu, v, t, C::LPR);
-        if (ct >= 0) {
-          const float4* xr = p.X + (size_t)ct * C::V4 + gl;
-#pragma unroll
-          for (int vv = 0; vv < C::VPL; ++vv) fma4(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
-        }
-      }
-      c = cn;
-      v = vn;
-    }
-    spmm_epilogue<C, NOISE>(p, m0.row, m0.valid, acc, gl);
-    m0 = m1; c0 = c1; v0 = v1; m1 = m2;
-  }
-}
-
-template <int D, int LPR, int MINB>
-static int launch_spmm_pipe(const SpmmParams& p, cudaStream_t st) {
-  using C = RowCfg<D, LPR>;
-  static int ctas_per_sm[2] = {0, 0};
-  const int which = p.noise != nullptr ? 1 : 0;
-  if (ctas_per_sm[which] == 0) {
-    int n = 0;
-    cudaError_t e = which ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmm_pipe_kernel<D, LPR, MINB, true>, 256, 0)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmm_pipe_kernel<D, LPR, MINB, false>, 256, 0);
-    if (e != cudaSuccess) return cuda_fail(e);
-    ctas_per_sm[which] = n > 0 ? n : 1;
-  }
-  const long long n_short = (long long)p.n_rows - p.n_long;
-  const long long n_tasks = (n_short + C::RPW - 1) / C::RPW;
-  long long persistent = (long long)kSMs * ctas_per_sm[which];
-  const long long need = (n_tasks + 7) / 8;
-  if (persistent > need) persistent = need;
-  const long long blocks = p.n_long + persistent;
-  if (blocks <= 0) return AGCF_OK;
-  if (p.noise != nullptr)
-    spmm_pipe_kernel<D, LPR, MINB, true><<<(unsigned)blocks, 256, 0, st>>>(p);
-  else
-    spmm_pipe_kernel<D, LPR, MINB, false><<<(unsigned)blocks, 256, 0, st>>>(p);
-  AGCF_LAUNCH_OK();
-  return AGCF_OK;
-}
-
-template <int D, int LPR, int MODE, int MINB>
-static int launch_spmm_cfg(const SpmmParams& p, cudaStream_t st) {
+template <int D>
+static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
+  // lane mapping measured best on B200 (profiles/): one float4 per lane, d/4 lanes per row (16 at d = 64),
+  // fully unrolled 16-entry chunks, packed FFMA2 accumulation
+  constexpr int LPR = default_lpr(D);
   using C = RowCfg<D, LPR>;
   const long long short_rows = (long long)p.n_rows - p.n_long;
   const long long blocks = p.n_long + (short_rows + C::RPB - 1) / C::RPB;
   if (blocks <= 0) return AGCF_OK;
   if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
   if (p.noise != nullptr)
-    spmm_csr_kernel<D, LPR, MODE, MINB, true><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
   else
-    spmm_csr_kernel<D, LPR, MODE, MINB, false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
-}
-
-// tuning hook (profiling only): AGCF_SPMM_VARIANT selects the lane mapping / inner loop for d = 64
-static int spmm_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("AGCF_SPMM_VARIANT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
-template <int D>
-static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
-  return launch_spmm_cfg<D, (D / 4 < 32 ? D / 4 : 32), 4, 1>(p, st);
-}
-
-template <>
-int launch_spmm<64>(const SpmmParams& p, cudaStream_t st) {
-  switch (spmm_variant()) {
-    case 1: return launch_spmm_cfg<64, 8, 1, 1>(p, st);
-    case 2: return launch_spmm_cfg<64, 8, 2, 1>(p, st);
-    case 3: return launch_spmm_cfg<64, 16, 1, 1>(p, st);
-    case 4: return launch_spmm_cfg<64, 16, 2, 1>(p, st);
-    case 5: return launch_spmm_cfg<64, 8, 0, 1>(p, st);
-    case 6: return launch_spmm_cfg<64, 16, 0, 6>(p, st);
-    case 7: return launch_spmm_cfg<64, 16, 2, 6>(p, st);
-    case 8: return launch_spmm_cfg<64, 8, 2, 5>(p, st);
-    case 9: return launch_spmm_cfg<64, 16, 0, 8>(p, st);
-    case 20: return launch_spmm_pipe<64, 16, 1>(p, st);
-    case 21: return launch_spmm_pipe<64, 16, 4>(p, st);
-    case 22: return launch_spmm_pipe<64, 16, 5>(p, st);
-    case 23: return launch_spmm_pipe<64, 8, 1>(p, st);
-    case 24: return launch_spmm_pipe<64, 8, 4>(p, st);
-    case 30: return launch_spmm_cfg<64, 16, 4, 1>(p, st);
-    case 31: return launch_spmm_cfg<64, 16, 4, 4>(p, st);
-    case 32: return launch_spmm_cfg<64, 16, 4, 5>(p, st);
-    case 33: return launch_spmm_cfg<64, 16, 4, 6>(p, st);
-    case 34: return launch_spmm_cfg<64, 16, 0, 5>(p, st);
-    case 35: return launch_spmm_cfg<64, 16, 0, 4>(p, st);
-    case 10: return launch_spmm_cfg<64, 16, 3, 1>(p, st);
-    case 11: return launch_spmm_cfg<64, 8, 3, 1>(p, st);
-    case 12: return launch_spmm_cfg<64, 16, 3, 6>(p, st);
-    case 13: return launch_spmm_cfg<64, 8, 3, 4>(p, st);
-    case 14: return launch_spmm_cfg<64, 8, 3, 5>(p, st);
-    case 99: return launch_spmm_cfg<64, 16, 0, 1>(p, st);
-    default: return launch_spmm_cfg<64, 16, 4, 1>(p, st);      // 16 lanes/row, full unroll, FFMA2: best measured (profiles/)
-  }
 }
 
 // ------------------------------------------------------------------------ SDDMM
@@ -601,7 +373,7 @@ extern "C" int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, cons
                                  int32_t n_rows, int32_t d, agcf_stream_t stream) {
   if (n_peers < 0 || n_peers > AGCF_MAX_PEERS) return AGCF_EINVAL;
   if (!rowptr || !col || !val || !X || n_rows < 0 || (Y == nullptr && acc_out == nullptr)) return AGCF_EINVAL;
-  if (!supported_d(d)) return AGCF_EUNSUPPORTED;
+  if (!supported_row_d(d)) return AGCF_EUNSUPPORTED;
   if (n_long < 0 || n_long > n_rows || (n_long > 0 && row_order == nullptr)) return AGCF_EINVAL;
   if (!aligned16(X) || !aligned16(Y) || !aligned16(addend) || !aligned16(acc_in) || !aligned16(acc_out) || !aligned16(noise))
     return AGCF_EINVAL;
@@ -626,6 +398,8 @@ extern "C" int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, cons
   }
   cudaStream_t st = (cudaStream_t)stream;
   switch (d) {
+    case 8: return launch_spmm<8>(p, st);
+    case 16: return launch_spmm<16>(p, st);
     case 32: return launch_spmm<32>(p, st);
     case 64: return launch_spmm<64>(p, st);
     case 128: return launch_spmm<128>(p, st);

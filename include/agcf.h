@@ -39,6 +39,7 @@ typedef void* agcf_stream_t;    /* cudaStream_t */
 int         agcf_abi_version(void);
 const char* agcf_strerror(int code);
 int         agcf_last_cuda_error(void);   /* cudaError_t of the last AGCF_ECUDA on this thread */
+const char* agcf_last_cuda_error_where(void);  /* its message and the library source line that saw it */
 int         agcf_device_sm_count(void);
 
 /* ------------------------------------------------------------------ adjacency

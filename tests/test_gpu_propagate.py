@@ -58,7 +58,7 @@ def test_norm_adj_fractional_weights_bit_exact():
     assert np.array_equal(g.val.cpu().numpy().view(np.uint32), ref.values().numpy().view(np.uint32))
 
 
-@pytest.mark.parametrize("d", [32, 64, 128, 256])
+@pytest.mark.parametrize("d", [8, 16, 32, 64, 128, 256])
 @pytest.mark.parametrize("hub", [0, 700])
 def test_spmm_matches_oracle(d, hub):
     from arlib_b200 import ops
