@@ -184,6 +184,51 @@ struct BprWs {                 // layout of the workspace
   float partial[1];            // [3 * n_blocks]: loss, sum u^2, sum i^2
 };
 
+// Block partials -> workspace; the last block to arrive (ticket) reduces all partials in a fixed order with
+// double accumulators and writes out4 = {loss, bpr term, ||F[u_.]||_F, ||F[i_.]||_F}.  Deterministic.
+template <int NRED>
+__device__ __forceinline__ void bpr_finalize(float (&red)[3][NRED], int nb, float reg, float* __restrict__ out4,
+                                             BprWs* __restrict__ ws) {
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 3) {
+    float acc = 0.f;
+    for (int k = 0; k < NRED; ++k) acc += red[threadIdx.x][k];      // fixed order
+    ws->partial[3 * blockIdx.x + threadIdx.x] = acc;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int tk = atomicAdd(&ws->ticket, 1u);
+    is_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || warp != 0) return;
+  __threadfence();
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  const volatile float* part = ws->partial;
+  for (int k = lane; k < (int)gridDim.x; k += 32) {
+    a0 += (double)part[3 * k + 0];
+    a1 += (double)part[3 * k + 1];
+    a2 += (double)part[3 * k + 2];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (lane == 0) {
+    const float bpr = (float)(a0 / (double)nb);
+    const float nu = (float)sqrt(a1), ni = (float)sqrt(a2);
+    out4[0] = bpr + (nu + ni) * reg;                          // emb_loss * reg, util/loss.py:29
+    out4[1] = bpr;
+    out4[2] = nu;
+    out4[3] = ni;
+    ws->ticket = 0u;
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(256) bpr_forward_kernel(const float4* __restrict__ F, const int32_t* __restrict__ u,
                                                           const int32_t* __restrict__ i, const int32_t* __restrict__ j,
@@ -191,7 +236,6 @@ __global__ void __launch_bounds__(256) bpr_forward_kernel(const float4* __restri
                                                           float* __restrict__ coef, BprWs* __restrict__ ws) {
   using C = RowCfg2<D>;
   __shared__ float red[3][C::RPB];
-  __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gl = lane & (C::LPR - 1), grp = lane / C::LPR;
   const int slot = warp * C::RPW + grp;
@@ -226,43 +270,78 @@ __global__ void __launch_bounds__(256) bpr_forward_kernel(const float4* __restri
   }
   if (gl == 0) { red[0][slot] = l; red[1][slot] = su; red[2][slot] = si; }
   __syncthreads();
-  if (threadIdx.x < 3) {
-    float acc = 0.f;
-    for (int k = 0; k < C::RPB; ++k) acc += red[threadIdx.x][k];      // fixed order
-    ws->partial[3 * blockIdx.x + threadIdx.x] = acc;
-    __threadfence();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int tk = atomicAdd(&ws->ticket, 1u);
-    is_last = (tk == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last || warp != 0) return;
-  __threadfence();
-  // last CTA: fixed-order final reduction (lane-strided then butterfly), double accumulators
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  const volatile float* part = ws->partial;
-  for (int k = lane; k < (int)gridDim.x; k += 32) {
-    a0 += (double)part[3 * k + 0];
-    a1 += (double)part[3 * k + 1];
-    a2 += (double)part[3 * k + 2];
-  }
+  bpr_finalize<C::RPB>(red, nb, reg, out4, ws);
+}
+
+// ===================================================== d-sharded forward (multi-GPU)
+// Every rank holds a column slice [N, d/P] of the tables.  bpr_partial computes, per triple, the slice's
+// share of the two dot products and of the two squared norms and stores the float4 into slot `rank` of the
+// exchange buffer on EVERY rank (plain NVLink P2P stores); after a barrier bpr_finish sums the P shares in
+// rank order -- identical bits on all ranks -- and does what bpr_forward does from there on.  The exchange
+// buffer is double-buffered on the parity of the device step counter, so one barrier per step suffices.
+struct XchgPeers {
+  int n;
+  float4* p[AGCF_MAX_PEERS];
+};
+
+template <int D>
+__global__ void __launch_bounds__(256) bpr_partial_kernel(const float4* __restrict__ F, const int32_t* __restrict__ u,
+                                                          const int32_t* __restrict__ i, const int32_t* __restrict__ j,
+                                                          int nb, int n_users, int rank, int cap,
+                                                          const int32_t* __restrict__ step_dev, XchgPeers x) {
+  using C = RowCfg2<D>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane & (C::LPR - 1), grp = lane / C::LPR;
+  const int t = blockIdx.x * C::RPB + warp * C::RPW + grp;
+  const bool valid = t < nb;
+  float dpos = 0.f, dneg = 0.f, su = 0.f, si = 0.f;
+  if (valid) {
+    const float4* fu = F + (size_t)u[t] * C::V4 + gl;
+    const float4* fi = F + ((size_t)n_users + i[t]) * C::V4 + gl;
+    const float4* fj = F + ((size_t)n_users + j[t]) * C::V4 + gl;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    for (int v = 0; v < C::VPL; ++v) {
+      const float4 a = __ldg(fu + v * C::LPR), p = __ldg(fi + v * C::LPR), n = __ldg(fj + v * C::LPR);
+      dpos += dot4(a, p);
+      dneg += dot4(a, n);
+      su += dot4(a, a);
+      si += dot4(p, p);
+    }
   }
-  if (lane == 0) {
-    const float bpr = (float)(a0 / (double)nb);
-    const float nu = (float)sqrt(a1), ni = (float)sqrt(a2);
-    out4[0] = bpr + (nu + ni) * reg;                          // emb_loss * reg, util/loss.py:29
-    out4[1] = bpr;
-    out4[2] = nu;
-    out4[3] = ni;
-    ws->ticket = 0u;
+  dpos = group_sum<C::LPR>(dpos);
+  dneg = group_sum<C::LPR>(dneg);
+  su = group_sum<C::LPR>(su);
+  si = group_sum<C::LPR>(si);
+  if (valid && gl == 0) {
+    const int parity = step_dev != nullptr ? (__ldg(step_dev) & 1) : 0;
+    const size_t off = ((size_t)parity * AGCF_MAX_PEERS + rank) * cap + t;
+    const float4 out = make_float4(dpos, dneg, su, si);
+    for (int q = 0; q < x.n; ++q) x.p[q][off] = out;
   }
+}
+
+__global__ void __launch_bounds__(256) bpr_finish_kernel(const float4* __restrict__ xchg, int world, int cap, int nb,
+                                                         float reg, const int32_t* __restrict__ step_dev,
+                                                         float* __restrict__ out4, float* __restrict__ coef,
+                                                         BprWs* __restrict__ ws) {
+  __shared__ float red[3][256];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int parity = step_dev != nullptr ? (__ldg(step_dev) & 1) : 0;
+  float l = 0.f, su = 0.f, si = 0.f;
+  if (t < nb) {
+    float dpos = 0.f, dneg = 0.f;
+    for (int r = 0; r < world; ++r) {                       // rank order: the same bits on every rank
+      const float4 v = xchg[((size_t)parity * AGCF_MAX_PEERS + r) * cap + t];
+      dpos += v.x; dneg += v.y; su += v.z; si += v.w;
+    }
+    const float x = dpos - dneg;
+    const float s = 1.f / (1.f + expf(-x));
+    l = -logf(1e-7f + s);
+    coef[t] = -(s * (1.f - s)) / ((1e-7f + s) * (float)nb);
+  }
+  red[0][threadIdx.x] = l; red[1][threadIdx.x] = su; red[2][threadIdx.x] = si;
+  __syncthreads();
+  bpr_finalize<256>(red, nb, reg, out4, ws);
 }
 
 // ================================================================= BPR backward
@@ -441,7 +520,7 @@ extern "C" int agcf_bpr_forward(const float* F, const int32_t* u, const int32_t*
                                 int32_t nb, int32_t n_users, int32_t d, float reg,
                                 float* out4, float* coef, void* ws, agcf_stream_t stream) {
   if (!F || !u || !i || !j || !out4 || !coef || !ws || nb <= 0 || n_users < 0) return AGCF_EINVAL;
-  if (!supported_d(d)) return AGCF_EUNSUPPORTED;
+  if (!supported_row_d(d)) return AGCF_EUNSUPPORTED;
   if (!aligned16(F) || !aligned16(ws)) return AGCF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const float4* F4 = reinterpret_cast<const float4*>(F);
@@ -452,6 +531,8 @@ extern "C" int agcf_bpr_forward(const float* F, const int32_t* u, const int32_t*
     bpr_forward_kernel<DD><<<blocks, 256, 0, st>>>(F4, u, i, j, nb, n_users, reg, out4, coef, w); \
   }
   switch (d) {
+    case 8: AGCF_BPRF(8) break;
+    case 16: AGCF_BPRF(16) break;
     case 32: AGCF_BPRF(32) break;
     case 64: AGCF_BPRF(64) break;
     case 128: AGCF_BPRF(128) break;
@@ -462,13 +543,63 @@ extern "C" int agcf_bpr_forward(const float* F, const int32_t* u, const int32_t*
   return AGCF_OK;
 }
 
+extern "C" int64_t agcf_bpr_xchg_bytes(int32_t cap) {
+  if (cap < 0) return AGCF_EINVAL;
+  return 2ll * AGCF_MAX_PEERS * (long long)cap * 16;
+}
+
+extern "C" int agcf_bpr_partial(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
+                                int32_t nb, int32_t n_users, int32_t d, int32_t rank, int32_t cap,
+                                const int32_t* step_dev, void* const* xchg_all_host, int32_t world,
+                                agcf_stream_t stream) {
+  if (!F || !u || !i || !j || nb <= 0 || n_users < 0 || !xchg_all_host) return AGCF_EINVAL;
+  if (world < 1 || world > AGCF_MAX_PEERS || rank < 0 || rank >= world || nb > cap) return AGCF_EINVAL;
+  if (!supported_row_d(d)) return AGCF_EUNSUPPORTED;
+  if (!aligned16(F)) return AGCF_EINVAL;
+  XchgPeers x;
+  x.n = world;
+  for (int q = 0; q < AGCF_MAX_PEERS; ++q) {
+    x.p[q] = q < world ? reinterpret_cast<float4*>(xchg_all_host[q]) : nullptr;
+    if (q < world && (x.p[q] == nullptr || !aligned16(x.p[q]))) return AGCF_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const float4* F4 = reinterpret_cast<const float4*>(F);
+#define AGCF_BPRP(DD)                                                                              \
+  {                                                                                                \
+    const unsigned blocks = (unsigned)((nb + RowCfg2<DD>::RPB - 1) / RowCfg2<DD>::RPB);             \
+    bpr_partial_kernel<DD><<<blocks, 256, 0, st>>>(F4, u, i, j, nb, n_users, rank, cap, step_dev, x); \
+  }
+  switch (d) {
+    case 8: AGCF_BPRP(8) break;
+    case 16: AGCF_BPRP(16) break;
+    case 32: AGCF_BPRP(32) break;
+    case 64: AGCF_BPRP(64) break;
+    case 128: AGCF_BPRP(128) break;
+    case 256: AGCF_BPRP(256) break;
+  }
+#undef AGCF_BPRP
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+extern "C" int agcf_bpr_finish(const void* xchg, int32_t world, int32_t cap, int32_t nb, float reg,
+                               const int32_t* step_dev, float* out4, float* coef, void* ws, agcf_stream_t stream) {
+  if (!xchg || !out4 || !coef || !ws || nb <= 0 || nb > cap || world < 1 || world > AGCF_MAX_PEERS) return AGCF_EINVAL;
+  if (!aligned16(xchg) || !aligned16(ws)) return AGCF_EINVAL;
+  const unsigned blocks = (unsigned)((nb + 255) / 256);
+  bpr_finish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(xchg), world, cap, nb, reg,
+                                                              step_dev, out4, coef, reinterpret_cast<BprWs*>(ws));
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
 extern "C" int agcf_bpr_backward(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
                                  int32_t nb, int32_t n_users, int32_t d, float reg, float scale,
                                  const float* out4, const float* coef,
                                  const int32_t* occ, const int32_t* seg_off, const int32_t* seg_node,
                                  const int32_t* n_seg, float* G, agcf_stream_t stream) {
   if (!F || !u || !i || !j || !out4 || !coef || !occ || !seg_off || !seg_node || !n_seg || !G || nb <= 0) return AGCF_EINVAL;
-  if (!supported_d(d)) return AGCF_EUNSUPPORTED;
+  if (!supported_row_d(d)) return AGCF_EUNSUPPORTED;
   if (!aligned16(F) || !aligned16(G) || F == G) return AGCF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   const float4* F4 = reinterpret_cast<const float4*>(F);
@@ -480,6 +611,8 @@ extern "C" int agcf_bpr_backward(const float* F, const int32_t* u, const int32_t
                                                     occ, seg_off, seg_node, n_seg, G4);            \
   }
   switch (d) {
+    case 8: AGCF_BPRB(8) break;
+    case 16: AGCF_BPRB(16) break;
     case 32: AGCF_BPRB(32) break;
     case 64: AGCF_BPRB(64) break;
     case 128: AGCF_BPRB(128) break;
@@ -493,7 +626,7 @@ extern "C" int agcf_bpr_backward(const float* F, const int32_t* u, const int32_t
 extern "C" int agcf_zero_rows(const int32_t* seg_node, const int32_t* n_seg, int32_t max_seg,
                               float* G, int32_t d, agcf_stream_t stream) {
   if (!seg_node || !n_seg || !G || max_seg < 0) return AGCF_EINVAL;
-  if (!supported_d(d)) return AGCF_EUNSUPPORTED;
+  if (!supported_row_d(d)) return AGCF_EUNSUPPORTED;
   if (!aligned16(G)) return AGCF_EINVAL;
   if (max_seg == 0) return AGCF_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -504,6 +637,8 @@ extern "C" int agcf_zero_rows(const int32_t* seg_node, const int32_t* n_seg, int
     zero_rows_kernel<DD><<<blocks, 256, 0, st>>>(seg_node, n_seg, G4);                       \
   }
   switch (d) {
+    case 8: AGCF_ZR(8) break;
+    case 16: AGCF_ZR(16) break;
     case 32: AGCF_ZR(32) break;
     case 64: AGCF_ZR(64) break;
     case 128: AGCF_ZR(128) break;

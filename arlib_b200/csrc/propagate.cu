@@ -137,7 +137,7 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
 // independent row gathers are in flight per lane while the next chunk's indices are already loading.
 // For narrow rows (d/4 < 16 lanes, the d-sharded multi-GPU tables) EPL > 1 keeps CH at 16.
 // one chunk held in registers (lane gl owns entries k * LPR + gl): broadcast every entry to the lane group and
-// gather-accumulate its row of X; slots with col < 0 (row end, masked column, padding) are predicated off
+// gather-accumulate its row of X; slots with col < 0 (row end, masked column) are predicated off
 template <typename C, bool PACKED>
 __device__ __forceinline__ void spmm_consume_chunk(const SpmmParams& p, const int (&c)[C::EPL], const float (&v)[C::EPL],
                                                    int gl, float4 (&acc)[C::VPL]) {
@@ -219,8 +219,40 @@ __device__ __forceinline__ void spmm_long_row(const SpmmParams& p, float4 (&acc)
   }
 }
 
+#ifdef AGCF_SPMM_TRACE
+// tuning aid (never in the shipped build): per-CTA timeline of the last launch -- start, metadata arrived,
+// gathers accumulated, end (globaltimer ns, warp 0) and the SM id
+__device__ unsigned long long g_spmm_trace[6 * 16384];
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_put(int k, unsigned long long v) {
+  if (threadIdx.x == 0 && blockIdx.x < 16384) g_spmm_trace[6 * blockIdx.x + k] = v;
+}
+struct TraceScope {
+  __device__ TraceScope() { trace_put(0, trace_now()); }
+  __device__ ~TraceScope() {
+    unsigned int sm;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    trace_put(3, trace_now());
+    trace_put(4, sm);
+  }
+};
+extern "C" int agcf_debug_spmm_trace(unsigned long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_spmm_trace, sizeof(g_spmm_trace)) == cudaSuccess ? 0 : -3;
+}
+#define AGCF_TRACE_AFTER(k, dep) trace_put(k, trace_now() + ((dep) == 0x7fffff01 ? 1ull : 0ull))
+#else
+#define AGCF_TRACE_AFTER(k, dep)
+#endif
+
 template <int D, int LPR, int MINB, bool NOISE>
 __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
+#ifdef AGCF_SPMM_TRACE
+  TraceScope trace_scope;
+#endif
   using C = RowCfg<D, LPR>;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -253,7 +285,9 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
     maxlen = other > maxlen ? other : maxlen;
   }
   const int iters = (maxlen + C::CH - 1) / C::CH;        // warp-uniform
+  AGCF_TRACE_AFTER(1, maxlen + row);
   spmm_accumulate_chunks<C, true>(p, s, len, 0, C::CH, iters, gl, acc);
+  AGCF_TRACE_AFTER(2, __float_as_int(acc[0].x));
   spmm_epilogue<C, NOISE>(p, row, valid, acc, gl);
 }
 

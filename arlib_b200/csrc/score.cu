@@ -283,9 +283,18 @@ struct Stage2Params {
   float* out_val;
   int32_t* out_idx;
   int32_t* out_flags;
-  // per-CTA scratch (global, L2-resident)
+  // per-CTA scratch of the block kernel (global, L2-resident)
   int32_t* cand_groups;        // [grid][n_groups]
   float* cand_val;             // [grid][n_groups*32]
+  // block kernel as the overflow path of the warp kernel: users list[0 .. *list_count) instead of 0 .. n_u-1
+  const int32_t* list;
+  const int32_t* list_count;
+  // warp kernel: per-warp scratch for at most cmax candidate groups; users with more go to the overflow list
+  int cmax;
+  int32_t* w_groups;           // [warps][cmax]
+  float* w_val;                // [warps][cmax*32]
+  int32_t* overflow_list;      // [n_u]
+  int32_t* overflow_count;     // zeroed by the caller
 };
 
 template <int D>
@@ -303,7 +312,9 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const Stage2Params p) 
   int32_t* my_groups = p.cand_groups + (size_t)blockIdx.x * p.n_groups;
   float* my_val = p.cand_val + (size_t)blockIdx.x * p.n_groups * kGroup;
 
-  for (int r = blockIdx.x; r < p.n_u; r += gridDim.x) {
+  const int n_list = p.list_count != nullptr ? *p.list_count : p.n_u;
+  for (int q = blockIdx.x; q < n_list; q += gridDim.x) {
+    const int r = p.list != nullptr ? p.list[q] : q;
     const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
     const float* grow = p.gmax + (size_t)r * p.pitch;
     const uint32_t* brow = p.bits + (size_t)r * p.pitch;
@@ -431,6 +442,229 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const Stage2Params p) 
   }
 }
 
+// ------------------------------------------------------- stage 2, one WARP per user
+// Same algorithm as topk_select_kernel, but a warp owns a user: every block barrier becomes a __syncwarp,
+// block scans become ballots, and 8x as many users are in flight per SM -- the block version spends its
+// ~65 barriers per user waiting.  Shared memory per warp: a 256-bin histogram, the user row, K sort keys.
+// Candidate groups beyond p.cmax (never seen at the benchmark shapes) send the user to the overflow list,
+// which the block kernel then processes.
+__device__ __forceinline__ uint32_t warp_radix_select(unsigned int* hist, int n, unsigned int R, int lane,
+                                                      const float* __restrict__ vals) {
+  uint32_t prefix = 0u;
+  unsigned int remaining = R;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0u;
+    __syncwarp();
+    const uint32_t pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int k = lane; k < n; k += 32) {
+      const uint32_t key = f2key(vals[k]);
+      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncwarp();
+    unsigned int mine = 0u;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) mine += hist[lane * 8 + b];
+    unsigned int run = mine;                     // inclusive suffix sum over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int y = __shfl_down_sync(0xffffffffu, run, o);
+      if (lane + o < 32) run += y;
+    }
+    const unsigned int above = run - mine;
+    const bool here = above < remaining && remaining <= above + mine;
+    uint32_t new_prefix = prefix;
+    unsigned int new_remaining = remaining;
+    if (here) {
+      unsigned int acc = above;
+      int digit = lane * 8;
+      for (int b = 7; b >= 0; --b) {
+        const unsigned int c = hist[lane * 8 + b];
+        if (acc + c >= remaining) { digit = lane * 8 + b; break; }
+        acc += c;
+      }
+      new_prefix = prefix | ((uint32_t)digit << shift);
+      new_remaining = remaining - acc;
+    }
+    const unsigned int who = __ballot_sync(0xffffffffu, here);
+    const int src = who != 0u ? (__ffs(who) - 1) : 0;
+    prefix = __shfl_sync(0xffffffffu, new_prefix, src);
+    remaining = __shfl_sync(0xffffffffu, new_remaining, src);
+    __syncwarp();
+  }
+  return prefix;
+}
+
+// warps per CTA of the warp kernel: the per-warp item tile ([32][D+4] floats) bounds how many fit
+template <int D>
+struct S2W {
+  static constexpr int WPC = D <= 64 ? 4 : (D == 128 ? 2 : 1);
+  static constexpr int LD = D + 4;                                   // padded tile row (floats): conflict-free LDS.128
+  static constexpr size_t tile_bytes = (size_t)kGroup * LD * 4;
+  __host__ __device__ static size_t per_warp(int kpow2) { return 1024 + (size_t)D * 4 + (size_t)kpow2 * 8 + tile_bytes; }
+};
+
+template <int D>
+__global__ void __launch_bounds__(32 * S2W<D>::WPC) topk_select_warp_kernel(const Stage2Params p) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  constexpr int WPC = S2W<D>::WPC, LD = S2W<D>::LD, V4 = D / 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int kpow2 = 1;
+  while (kpow2 < p.K) kpow2 <<= 1;
+  const size_t per_warp = S2W<D>::per_warp(kpow2);
+  unsigned char* mine = dyn + (size_t)warp * per_warp;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(mine);
+  float* urow = reinterpret_cast<float*>(mine + 1024);
+  unsigned long long* sort_keys = reinterpret_cast<unsigned long long*>(mine + 1024 + (size_t)D * 4);
+  float* tile = reinterpret_cast<float*>(mine + 1024 + (size_t)D * 4 + (size_t)kpow2 * 8);
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  const int gw = blockIdx.x * WPC + warp, n_warps = gridDim.x * WPC;
+  int32_t* my_groups = p.w_groups + (size_t)gw * p.cmax;
+  float* my_val = p.w_val + (size_t)gw * p.cmax * kGroup;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+
+  for (int r = gw; r < p.n_u; r += n_warps) {
+    const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
+    const float* grow = p.gmax + (size_t)r * p.pitch;
+    const uint32_t* brow = p.bits + (size_t)r * p.pitch;
+    __syncwarp();
+    for (int k = lane; k < D / 4; k += 32) reinterpret_cast<float4*>(urow)[k] = __ldg(p.Uemb + (size_t)uid * (D / 4) + k);
+    __syncwarp();
+    // ---- 1. threshold on the group maxima
+    const unsigned int R = (unsigned int)min(p.K, p.n_groups);
+    float thr = key2f(warp_radix_select(hist, p.n_groups, R, lane, grow));
+    if (p.margin_scale > 0.f) {
+      float ss = 0.f;
+      for (int k = 0; k < D; ++k) ss = fmaf(urow[k], urow[k], ss);
+      thr -= p.margin_scale * sqrtf(ss) * __ldg(p.max_item_norm);
+    }
+    // ---- 2. ordered compaction of candidate groups
+    int n_cg = 0;
+    bool overflow = false;
+    for (int base = 0; base < p.n_groups; base += 32) {
+      const int g = base + lane;
+      const bool flag = g < p.n_groups && grow[g] >= thr;
+      const unsigned int b = __ballot_sync(0xffffffffu, flag);
+      const int pos = n_cg + __popc(b & lt_mask);
+      if (n_cg + __popc(b) > p.cmax) { overflow = true; break; }       // warp-uniform
+      if (flag) my_groups[pos] = g;
+      n_cg += __popc(b);
+    }
+    if (overflow) {
+      if (lane == 0) p.overflow_list[atomicAdd(p.overflow_count, 1)] = r;
+      continue;
+    }
+    __syncwarp();
+    // ---- 3. exact re-scoring of the candidates.  A group's 32 item rows are one contiguous block: it is
+    // copied global -> shared with coalesced cp.async (a lane-per-item read would fetch 16 B out of every
+    // 128 B line per instruction), then lane l walks ITS item's row in shared memory in the reference
+    // order (k ascending, fmaf) -- the same bits as exact_dot.
+    for (int c = 0; c < n_cg; ++c) {
+      const int g = my_groups[c];
+      const int rows_here = min(kGroup, p.n_items - g * kGroup);
+      const float4* src = p.Iemb + (size_t)g * kGroup * V4;
+#pragma unroll
+      for (int i = 0; i < V4; ++i) {
+        const int f = i * 32 + lane, row = f / V4, c4 = f % V4;
+        const bool in = row < rows_here;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tile_s + (uint32_t)(row * LD + 4 * c4) * 4u),
+                     "l"(in ? src + f : p.Iemb), "r"(in ? 16 : 0) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      float sc = 0.f;
+      const float* mine_row = tile + lane * LD;
+#pragma unroll 4
+      for (int k4 = 0; k4 < V4; ++k4) {
+        const float4 v = *reinterpret_cast<const float4*>(mine_row + 4 * k4);
+        const float4 u = *reinterpret_cast<const float4*>(urow + 4 * k4);
+        sc = fmaf(u.x, v.x, sc);
+        sc = fmaf(u.y, v.y, sc);
+        sc = fmaf(u.z, v.z, sc);
+        sc = fmaf(u.w, v.w, sc);
+      }
+      if (lane >= rows_here) sc = -FLT_MAX;
+      else if ((__ldg(brow + g) >> lane) & 1u) sc = kMasked;
+      my_val[c * kGroup + lane] = sc;
+      __syncwarp();                                        // the tile is refilled by the next group
+    }
+    __syncwarp();
+    const int nc = n_cg * kGroup;
+    int n_valid = nc;
+    if (n_cg > 0 && my_groups[n_cg - 1] == p.n_groups - 1) n_valid = nc - (p.n_groups * kGroup - p.n_items);
+    const int Keff = min(p.K, n_valid);
+    // ---- 4. K-th largest exact score s*, then the reference heap's tie rule (see topk_select_kernel)
+    int n_sel = 0;
+    if (Keff > 0) {
+      const float sstar = key2f(warp_radix_select(hist, nc, (unsigned int)Keff, lane, my_val));
+      int run_ge = 0, run_gt = 0, gp_local = 0;
+      bool found = false;
+      for (int base = 0; base < nc; base += 32) {
+        const int k = base + lane;
+        const float v = my_val[k];
+        const bool real = k < n_valid;
+        const bool gt = real && v > sstar, ge = real && v >= sstar;
+        const unsigned int bge = __ballot_sync(0xffffffffu, ge), bgt = __ballot_sync(0xffffffffu, gt);
+        if (ge && run_ge + __popc(bge & lt_mask) + 1 == Keff) { found = true; gp_local = run_gt + __popc(bgt & lt_mask) + (gt ? 1 : 0); }
+        run_ge += __popc(bge);
+        run_gt += __popc(bgt);
+      }
+      const int m = run_gt;
+      const unsigned int fb = __ballot_sync(0xffffffffu, found);
+      const int gp = __shfl_sync(0xffffffffu, gp_local, fb != 0u ? (__ffs(fb) - 1) : 0);
+      for (int k = lane; k < kpow2; k += 32) sort_keys[k] = ~0ull;
+      __syncwarp();
+      const int tie_lo = m - gp, tie_n = Keff - m;
+      int run_eq = 0;
+      run_gt = 0;
+      for (int base = 0; base < nc; base += 32) {
+        const int k = base + lane;
+        const float v = my_val[k];
+        const bool real = k < n_valid;
+        const bool gt = real && v > sstar, eq = real && v == sstar;
+        const unsigned int beq = __ballot_sync(0xffffffffu, eq), bgt = __ballot_sync(0xffffffffu, gt);
+        const int trank = run_eq + __popc(beq & lt_mask);
+        const int gt_before = run_gt + __popc(bgt & lt_mask);
+        if (gt || (eq && trank >= tie_lo && trank < tie_lo + tie_n)) {
+          int ties_before = trank - tie_lo;
+          ties_before = ties_before < 0 ? 0 : (ties_before > tie_n ? tie_n : ties_before);
+          const int item = my_groups[k >> 5] * kGroup + (k & 31);
+          sort_keys[gt_before + ties_before] = ((unsigned long long)(~f2key(v)) << 32) | (uint32_t)item;
+        }
+        run_eq += __popc(beq);
+        run_gt += __popc(bgt);
+      }
+      n_sel = Keff;
+      __syncwarp();
+      for (int kk = 2; kk <= kpow2; kk <<= 1)
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+          for (int idx = lane; idx < (kpow2 >> 1); idx += 32) {
+            const int a = ((idx & ~(jj - 1)) << 1) | (idx & (jj - 1));
+            const int c = a | jj;
+            const bool up = (a & kk) == 0;
+            const unsigned long long ka = sort_keys[a], kc = sort_keys[c];
+            if ((ka > kc) == up) { sort_keys[a] = kc; sort_keys[c] = ka; }
+          }
+          __syncwarp();
+        }
+    }
+    for (int k = lane; k < p.K; k += 32) {
+      float v = -INFINITY;
+      int idx = -1;
+      if (k < n_sel) {
+        const unsigned long long key = sort_keys[k];
+        v = key2f(~(uint32_t)(key >> 32));
+        idx = (int)(uint32_t)key + p.item_offset;
+      }
+      p.out_val[(size_t)r * p.K + k] = v;
+      p.out_idx[(size_t)r * p.K + k] = idx;
+    }
+    if (lane == 0 && p.out_flags != nullptr) p.out_flags[r] = n_cg;
+  }
+}
+
 // --------------------------------------------------------------------- predict
 template <int D>
 __global__ void __launch_bounds__(256) score_rows_kernel(const float4* __restrict__ Uemb, const int32_t* __restrict__ user_rows,
@@ -511,17 +745,20 @@ int launch_group_max_tc(const float* Uemb, const int32_t* user_rows, int n_u, co
                         const uint32_t* bits, int n_groups, int pitch, float* gmax, float* u_dense, cudaStream_t st);
 
 struct WsLayout {
-  size_t bits_off, gmax_off, norm_off, groups_off, cval_off, udense_off, total;
-  int n_groups, pitch, grid2;
+  size_t bits_off, gmax_off, norm_off, groups_off, cval_off, udense_off, wgroups_off, wval_off, ovf_off, total;
+  int n_groups, pitch, grid2, grid_w, cmax, wpc;
 };
+
+constexpr int kStage2OverflowCtas = 32;      // block-kernel CTAs that mop up users with > cmax candidate groups
+constexpr int kStage2CandMax = 160;          // candidate groups a warp can hold (mean 55, max 72 seen at K = 50)
 
 static int stage2_ctas_per_sm() {
   static int v = 0;
   if (v == 0) {
     const char* e = getenv("AGCF_STAGE2_CTAS_PER_SM");      // tuning hook
-    v = e ? atoi(e) : 4;
+    v = e ? atoi(e) : 5;
     if (v < 1) v = 1;
-    if (v > 8) v = 8;
+    if (v > 16) v = 16;
   }
   return v;
 }
@@ -530,7 +767,18 @@ static WsLayout ws_layout(int n_u, int n_items, int d) {
   WsLayout L;
   L.n_groups = (n_items + kGroup - 1) / kGroup;
   L.pitch = (L.n_groups + 7) & ~7;                               // 32-byte rows: vector loads / stores in the tcgen05 epilogue
-  L.grid2 = n_u < stage2_ctas_per_sm() * kSMs ? (n_u > 0 ? n_u : 1) : stage2_ctas_per_sm() * kSMs;      // stage 2 is latency-bound per user: 8 CTAs / SM
+  L.grid2 = kStage2OverflowCtas;
+  int cmax = kStage2CandMax;
+  if (const char* e = getenv("AGCF_STAGE2_CMAX")) {                // test hook: force the overflow path
+    const int v = atoi(e);
+    if (v >= 1 && v < cmax) cmax = v;
+  }
+  L.cmax = L.n_groups < cmax ? L.n_groups : cmax;
+  const int wpc = d <= 64 ? 4 : (d == 128 ? 2 : 1);                // S2W<D>::WPC
+  const int want = (n_u + wpc - 1) / wpc;                          // one warp per user
+  const int resident = stage2_ctas_per_sm() * kSMs;
+  L.grid_w = want < resident ? (want > 0 ? want : 1) : resident;
+  L.wpc = wpc;
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t off = 0;
   L.bits_off = off; off = up(off + (size_t)n_u * L.pitch * 4);
@@ -539,6 +787,9 @@ static WsLayout ws_layout(int n_u, int n_items, int d) {
   L.groups_off = off; off = up(off + (size_t)L.grid2 * L.n_groups * 4);
   L.cval_off = off; off = up(off + (size_t)L.grid2 * L.n_groups * kGroup * 4);
   L.udense_off = off; off = up(off + (size_t)n_u * d * 4);          // gathered user rows for the TMA path
+  L.wgroups_off = off; off = up(off + (size_t)L.grid_w * L.wpc * L.cmax * 4);
+  L.wval_off = off; off = up(off + (size_t)L.grid_w * L.wpc * L.cmax * kGroup * 4);
+  L.ovf_off = off; off = up(off + ((size_t)n_u + 64) * 4);          // [0] = count, [64 ..] = list
   L.total = off;
   return L;
 }
@@ -621,10 +872,26 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   p.out_val = out_val; p.out_idx = out_idx; p.out_flags = out_flags;
   p.cand_groups = reinterpret_cast<int32_t*>(base + L.groups_off);
   p.cand_val = reinterpret_cast<float*>(base + L.cval_off);
+  int32_t* ovf = reinterpret_cast<int32_t*>(base + L.ovf_off);
+  p.list = ovf + 64; p.list_count = ovf;
+  p.cmax = L.cmax;
+  p.w_groups = reinterpret_cast<int32_t*>(base + L.wgroups_off);
+  p.w_val = reinterpret_cast<float*>(base + L.wval_off);
+  p.overflow_list = ovf + 64; p.overflow_count = ovf;
+  AGCF_CUDA_OK(cudaMemsetAsync(ovf, 0, 4, st));
   int kpow2 = 1;
   while (kpow2 < K) kpow2 <<= 1;
   const size_t dyn = (size_t)kpow2 * 8;
-#define AGCF_S2(DD) topk_select_kernel<DD><<<(unsigned)L.grid2, 256, dyn, st>>>(p);
+  // warp per user, then the block kernel on the users the warp kernel could not hold (normally none)
+#define AGCF_S2(DD)                                                                                              \
+  {                                                                                                              \
+    const size_t dyn_w = S2W<DD>::WPC * S2W<DD>::per_warp(kpow2);                                                \
+    if (dyn_w > 200 * 1024) return AGCF_EUNSUPPORTED;                                                            \
+    if (dyn_w > 48 * 1024)                                                                                       \
+      AGCF_CUDA_OK(cudaFuncSetAttribute(topk_select_warp_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_w)); \
+    topk_select_warp_kernel<DD><<<(unsigned)L.grid_w, 32 * S2W<DD>::WPC, dyn_w, st>>>(p);                        \
+    topk_select_kernel<DD><<<(unsigned)L.grid2, 256, dyn, st>>>(p);                                              \
+  }
   switch (d) { case 32: AGCF_S2(32) break; case 64: AGCF_S2(64) break; case 128: AGCF_S2(128) break; case 256: AGCF_S2(256) break; }
 #undef AGCF_S2
   AGCF_LAUNCH_OK();

@@ -58,6 +58,11 @@ class DistContext:
         base = self._off[name] + int(extra_bytes)
         return [int(self.hdl.buffer_ptrs[r]) + base for r in range(self.world) if r != self.rank]
 
+    def all_ptrs(self, name, extra_bytes=0):
+        """device pointers of buffer ``name`` on ALL ranks in rank order (own copy included)"""
+        base = self._off[name] + int(extra_bytes)
+        return [int(self.hdl.buffer_ptrs[r]) + base for r in range(self.world)]
+
     def barrier(self):
         """device-side barrier across ranks on the current stream"""
         self.hdl.barrier(channel=0)

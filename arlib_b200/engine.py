@@ -18,6 +18,17 @@ from . import ops
 from .graph import DeviceGraph
 
 
+def dshard_columns(d, world, rank):
+    """Column range [c0, c1) of rank ``rank`` when d columns are split over ``world`` ranks; the slice
+    width must be one the row kernels are compiled for."""
+    if d % world:
+        raise ValueError("embedding size %d is not divisible by %d ranks" % (d, world))
+    w = d // world
+    if w not in (8, 16, 32, 64, 128, 256):
+        raise ValueError("d/P = %d: the row kernels take slices of 8, 16, 32, 64, 128 or 256 columns" % w)
+    return rank * w, (rank + 1) * w
+
+
 class DeviceTrainSet:
     """Device mirror of what util/sampler.py:4-30 reads from ``data``: the edge list
     (data.training_data through data.user / data.item) and, per user, the sorted item
@@ -73,27 +84,59 @@ class DeviceTrainSet:
 
 
 class LightGCNEngine:
+    """``mode`` (multi-GPU only):
+      "rows"   -- node rows and adjacency rows partitioned; every layer's rows are all-gathered by the SpMM
+                  epilogue (P2P stores) and closed by a barrier: 2L + 1 exchanges per step;
+      "dshard" -- the graph is replicated and every table is COLUMN-sharded (rank r owns columns
+                  [r*d/P, (r+1)*d/P)): propagation, backward and Adam need no communication at all, the
+                  only exchange of a step is 16 bytes per triple per peer (the partial scores) and one
+                  barrier.  Needs d/P in {8, 16, 32, ...} and the graph to fit on one GPU."""
+
     def __init__(self, graph: DeviceGraph, table: torch.Tensor, n_users: int, n_layers: int,
                  lr: float, reg: float, batch_size: int, max_triples: int,
-                 betas=(0.9, 0.999), adam_eps=1e-8, sparse_layers=True, comm=None):
+                 betas=(0.9, 0.999), adam_eps=1e-8, sparse_layers=True, comm=None, mode="rows"):
         if 3 * batch_size > 16384:
             raise ValueError("batch_size %d too large for the single-CTA batch grouping (max 5461)" % batch_size)
         if n_layers < 1:
             raise ValueError("n_layers must be >= 1")
-        self.N, self.d = table.shape
+        if mode not in ("rows", "dshard"):
+            raise ValueError("mode must be 'rows' or 'dshard'")
+        self.N, self.d_full = table.shape
+        self.d = self.d_full
         self.U, self.L = int(n_users), int(n_layers)
         self.lr, self.reg, self.B = float(lr), float(reg), int(batch_size)
         self.betas, self.adam_eps = betas, adam_eps
         dev = table.device
         self.comm = comm
+        self.mode = mode if (comm is not None and comm.world > 1) else "single"
         f = lambda: torch.empty_like(table)
-        if comm is None or comm.world == 1:
+        if self.mode == "single":
             self.comm = None
             self.g, self.E0 = graph, table
             self.r0, self.r1 = 0, self.N
             self.F = f()
             self.fw = [f(), f()] if self.L > 1 else []
             self.bw = [f(), f()] if self.L > 1 else []
+        elif self.mode == "dshard":
+            c0, c1 = dshard_columns(self.d_full, comm.world, comm.rank)
+            self.d = c1 - c0
+            self.col0, self.col1 = c0, c1
+            self.g = graph
+            self.r0, self.r1 = 0, self.N
+            self.E0 = table[:, c0:c1].contiguous()
+            table = self.E0                      # every per-step table below has the slice's shape
+            f = lambda: torch.empty_like(self.E0)
+            self.F = f()
+            self.fw = [f(), f()] if self.L > 1 else []
+            self.bw = [f(), f()] if self.L > 1 else []
+            # exchange buffer of the partial scores: one symmetric allocation, every rank writes its slot everywhere
+            nbytes = ops.bpr_xchg_bytes(self.B)
+            bufs = comm.allocate({"xchg": ((nbytes,), torch.uint8)})
+            self.xchg = bufs["xchg"]
+            self.xchg.zero_()
+            self._xchg_all = comm.all_ptrs("xchg")
+            torch.cuda.synchronize()
+            comm.barrier()
         else:
             # row partition: this rank computes rows [r0, r1); layer tables live in one symmetric arena
             bounds = graph.row_ranges(comm.world)
@@ -135,16 +178,30 @@ class LightGCNEngine:
         self.coef = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.ws = torch.zeros(ops.bpr_ws_bytes(self.B), dtype=torch.uint8, device=dev)
         self._graphs = {}
+        self._ext = None
+        self._loss_eager = None
         import os as _os
         self.dist_graphs = _os.environ.get("ARLIB_B200_DIST_GRAPHS", "1") == "1"
-        self.launches_per_step = 2 * self.L + 5 + (2 * self.L if self.comm is not None else 0)
+        self.launches_per_step = {"single": 2 * self.L + 5, "rows": 4 * self.L + 5, "dshard": 2 * self.L + 7}[self.mode]
 
     def _peers(self, name):
-        return None if self.comm is None else self._peer[name]
+        return self._peer[name] if self.mode == "rows" else None
 
     def _barrier(self):
-        if self.comm is not None:
+        if self.mode == "rows":
             self.comm.barrier()
+
+    def full_table(self, local: torch.Tensor) -> torch.Tensor:
+        """[N, d] table from this rank's copy: identity except in "dshard" mode, where the P column
+        slices are all-gathered (NCCL) and interleaved back -- used once per evaluation / export,
+        never inside a training step."""
+        if self.mode != "dshard":
+            return local
+        import torch.distributed as dist
+        w = self.comm.world
+        parts = torch.empty((w * local.shape[0], local.shape[1]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(parts, local.contiguous(), group=self.comm.group)
+        return parts.view(w, self.N, -1).permute(1, 0, 2).reshape(self.N, self.d_full).contiguous()
 
     # ------------------------------------------------------------ epoch set-up
     @property
@@ -186,8 +243,8 @@ class LightGCNEngine:
         Multi-GPU: every layer's rows are also stored into the peers' tables by the SpMM
         epilogue and a barrier closes the layer (``out`` must then be self.F)."""
         F = self.F if out is None else out
-        if self.comm is not None and out is not None:
-            raise ValueError("multi-GPU forward writes the symmetric F table")
+        if self.mode == "rows" and out is not None:
+            raise ValueError("row-partitioned forward writes the symmetric F table")
         x = self.E0
         for k in range(1, self.L + 1):
             last = k == self.L
@@ -212,7 +269,12 @@ class LightGCNEngine:
         out4 = self.out4[b]
         mask = self.node_mask[b * self.mask_words:] if self.sparse_layers else None
         F = self.forward_table(row_mask=mask)
-        ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)
+        if self.mode == "dshard":
+            ops.bpr_partial(F, u, i, j, nb, self.U, self.comm.rank, self.B, self.step_dev, self._xchg_all)
+            self.comm.barrier()                  # the step's only exchange: 16 B per triple to every peer
+            ops.bpr_finish(self.xchg, self.comm.world, self.B, nb, self.reg, self.step_dev, out4, self.coef, self.ws)
+        else:
+            ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)
         ops.bpr_backward(F, u, i, j, nb, self.U, self.reg, 1.0, out4, self.coef, occ, seg_off, seg_node, n_seg, self.G)
         H = self.G
         for k in range(L, 0, -1):
@@ -230,7 +292,7 @@ class LightGCNEngine:
         r0, r1 = self.r0, self.r1
         ops.adam_step(self.E0[r0:r1], self.dE0[r0:r1], self.m[r0:r1], self.v[r0:r1], self.lr, self.betas[0],
                       self.betas[1], self.adam_eps, step_dev=self.step_dev,
-                      peer_p=None if self.comm is None else self._peer_E0_rows)
+                      peer_p=self._peer_E0_rows if self.mode == "rows" else None)
         ops.increment(self.step_dev)
         self._barrier()
 
@@ -270,13 +332,91 @@ class LightGCNEngine:
             g.replay()
         return self.out4[first_batch:first_batch + n_steps]
 
-    def step_external(self, host_triples: torch.Tensor, nb: int, dev_staging=None):
-        """One step on triples supplied by the HOST (pinned int32 [3, B]): H2D copy,
-        grouping, the step kernels.  The loss row stays on device (self.out4[0])."""
-        self.tu[:nb].copy_(host_triples[0, :nb], non_blocking=True)
-        self.ti[:nb].copy_(host_triples[1, :nb], non_blocking=True)
-        self.tj[:nb].copy_(host_triples[2, :nb], non_blocking=True)
-        self.T = nb
-        self._group(0, nb)
-        self._launch_step(0)
-        return self.out4[0]
+    def step_external(self, host_triples: torch.Tensor, nb: int, use_graph=True):
+        """One step on triples supplied by the HOST (int32 [3, >=nb], ideally pinned): H2D copy of the
+        triples, grouping, the step kernels and the D2H copy of the 4-float loss row.  Returns the
+        pinned host tensor the loss row lands in (valid after a stream synchronize / until the slot is
+        reused ``n_slots`` calls later).
+
+        With ``use_graph`` every staging slot owns two captured graphs: PREP (H2D memcpy nodes + the
+        batch grouping, which depend on the triples only) runs on a side stream, STEP (propagation, loss,
+        backward, Adam, D2H of the loss row) on the caller's stream after PREP's event.  Calls are
+        asynchronous, so PREP of step k+1 overlaps STEP of step k: the single-CTA sort of the grouping
+        and the copies leave the critical path.  CPU cost per step: one 24 KB memcpy into the slot and two
+        graph launches instead of ~20 python -> ctypes kernel launches."""
+        if not use_graph or (self.comm is not None and not self.dist_graphs):
+            self.tu[:nb].copy_(host_triples[0, :nb], non_blocking=True)
+            self.ti[:nb].copy_(host_triples[1, :nb], non_blocking=True)
+            self.tj[:nb].copy_(host_triples[2, :nb], non_blocking=True)
+            self.T = nb
+            self._group(0, nb)
+            self._launch_step(0)
+            if self._loss_eager is None:
+                self._loss_eager = torch.empty(4, dtype=torch.float32).pin_memory()
+            self._loss_eager.copy_(self.out4[0], non_blocking=True)
+            return self._loss_eager
+        if self._ext is None or self._ext["nb"] != nb:
+            self._ext = self._capture_external(nb)
+        ext = self._ext
+        k = ext["next"]
+        ext["next"] = (k + 1) % len(ext["slots"])
+        slot = ext["slots"][k]
+        main = torch.cuda.current_stream()
+        side = ext["side"]
+        slot["prep_done"].synchronize()            # the PREP that last read this slot's host buffer has finished
+        slot["host"][:, :nb].copy_(host_triples[:, :nb])
+        side.wait_event(slot["step_done"])         # the STEP that last used this slot's device buffers has finished
+        with torch.cuda.stream(side):
+            slot["prep"].replay()
+            slot["prep_done"].record(side)
+        main.wait_event(slot["prep_done"])
+        self.T = slot["batch"] * self.B + nb
+        slot["step"].replay()
+        slot["step_done"].record(main)
+        return slot["loss"]
+
+    def _capture_external(self, nb, n_slots=4):
+        """Graphs of one externally fed step per pinned staging slot (a memcpy node's addresses are baked
+        into the graph).  Slot k uses batch position k of the per-epoch triple / grouping arrays, so the
+        PREP of one slot never writes what the STEP of another is reading."""
+        n_slots = max(1, min(n_slots, self.cap // self.B))
+        torch.cuda.synchronize()
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        state = (self.E0.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone())
+        slots = []
+        for k in range(n_slots):
+            slots.append({"batch": k, "host": torch.zeros((3, self.B), dtype=torch.int32).pin_memory(),
+                          "loss": torch.zeros(4, dtype=torch.float32).pin_memory(),
+                          "prep_done": torch.cuda.Event(), "step_done": torch.cuda.Event()})
+
+        def prep(slot):
+            t0 = slot["batch"] * self.B
+            self.tu[t0:t0 + nb].copy_(slot["host"][0, :nb], non_blocking=True)
+            self.ti[t0:t0 + nb].copy_(slot["host"][1, :nb], non_blocking=True)
+            self.tj[t0:t0 + nb].copy_(slot["host"][2, :nb], non_blocking=True)
+            self._group(t0, nb)
+
+        def step(slot):
+            self.T = slot["batch"] * self.B + nb
+            self._launch_step(slot["batch"])
+            slot["loss"].copy_(self.out4[slot["batch"]], non_blocking=True)
+
+        prep(slots[0]); step(slots[0])              # eager warm-up (module loading, func attributes) on zeros
+        torch.cuda.synchronize()
+        for slot in slots:
+            gp, gs = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gp):
+                prep(slot)
+            prep(slot)                               # the grouping arrays of this slot must be valid while STEP is captured
+            torch.cuda.synchronize()
+            with torch.cuda.graph(gs):
+                step(slot)
+            slot["prep"], slot["step"] = gp, gs
+        self.E0.copy_(state[0]); self.m.copy_(state[1]); self.v.copy_(state[2]); self.step_dev.copy_(state[3])
+        torch.cuda.synchronize()
+        for slot in slots:
+            slot["prep_done"].record(main)
+            slot["step_done"].record(main)
+        torch.cuda.synchronize()
+        return {"nb": nb, "slots": slots, "next": 0, "side": side}

@@ -105,6 +105,25 @@ def bpr_forward(F, u, i, j, nb, n_users, reg, out4, coef, ws):
                                     _lib.stream_ptr()), "agcf_bpr_forward")
 
 
+def bpr_xchg_bytes(cap):
+    return int(_lib.load().agcf_bpr_xchg_bytes(int(cap)))
+
+
+def bpr_partial(F, u, i, j, nb, n_users, rank, cap, step_dev, xchg_all):
+    """agcf_bpr_partial: this rank's column-slice share of the scores, stored on every rank."""
+    lib = _lib.load()
+    arr, n = _lib.ptr_array(xchg_all)
+    _lib.check(lib.agcf_bpr_partial(F.data_ptr(), u.data_ptr(), i.data_ptr(), j.data_ptr(), int(nb), int(n_users),
+                                    F.shape[1], int(rank), int(cap), _p(step_dev), arr, n, _lib.stream_ptr()),
+               "agcf_bpr_partial")
+
+
+def bpr_finish(xchg, world, cap, nb, reg, step_dev, out4, coef, ws):
+    lib = _lib.load()
+    _lib.check(lib.agcf_bpr_finish(xchg.data_ptr(), int(world), int(cap), int(nb), float(reg), _p(step_dev),
+                                   out4.data_ptr(), coef.data_ptr(), ws.data_ptr(), _lib.stream_ptr()), "agcf_bpr_finish")
+
+
 def bpr_backward(F, u, i, j, nb, n_users, reg, scale, out4, coef, occ, seg_off, seg_node, n_seg, G):
     lib = _lib.load()
     _lib.check(lib.agcf_bpr_backward(F.data_ptr(), u.data_ptr(), i.data_ptr(), j.data_ptr(), int(nb), int(n_users),

@@ -230,7 +230,13 @@ def run_ours(args):
     if world > 1:
         from arlib_b200.dist import DistContext
         comm = DistContext(dev)
-    eng = LightGCNEngine(g, table, U, L, LR, REG, B, E, comm=comm)
+    # multi-GPU layout: column-sharded tables (one 16 B/triple exchange per step) when d/P is a supported slice
+    # width, else (or with ARLIB_B200_DIST=rows) row-partitioned tables with the per-layer all-gather fused
+    # into the SpMM epilogue
+    mode = os.environ.get("ARLIB_B200_DIST", "dshard")
+    if world > 1 and (d % world or d // world not in (8, 16, 32, 64, 128, 256)):
+        mode = "rows"
+    eng = LightGCNEngine(g, table, U, L, LR, REG, B, E, comm=comm, mode=mode)
     K, W = args.steps, max(args.warmup, 3)
     nb_epoch = (E + B - 1) // B
     full_batches = E // B
@@ -297,6 +303,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     spmm_avg_ms = float(np.mean([a.elapsed_time(b) for a, b in spmm_ms]))
     b_spmm, b_step = algorithmic_bytes(N, g.nnz, d, L, B)
+    if eng.mode == "dshard":        # per-GPU launch: whole graph, a [N, d/P] slice of the tables
+        b_spmm = g.nnz * 8 + (N + 1) * 4 + 2 * N * eng.d * 4
+    elif eng.mode == "rows":        # per-GPU launch: this rank's rows of the graph, all of X read, its rows of Y written
+        b_spmm = eng.g.local_nnz * 8 + (eng.g.n_local_rows + 1) * 4 + N * d * 4 + eng.g.n_local_rows * d * 4
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -310,7 +320,7 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json"))).get(args.workload)
     except Exception:
         pass
-    roofline = {"kernel": "spmm_csr_kernel<64,false>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "spmm_csr_kernel<%d>" % eng.d, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": b_spmm, "avg_launch_ms": spmm_avg_ms,
                 "launches_per_step": 2 * L, "step_algorithmic_bytes": b_step,
@@ -326,24 +336,23 @@ def run_ours(args):
         t[0].copy_(torch.from_numpy(D["tu"][sl:sl + B].astype(np.int32)))
         t[1].copy_(torch.from_numpy(D["ti"][sl:sl + B].astype(np.int32)))
         t[2].copy_(torch.from_numpy(rng.integers(0, I, B).astype(np.int32)))
-    loss_host = torch.empty((max(K, 1), 4), dtype=torch.float32).pin_memory()
     for k in range(W):
         eng.step_external(tu_h[k % 4], B)
     barrier()
     e0.record()
     for k in range(K):
-        row = eng.step_external(tu_h[k % 4], B)
-        loss_host[k].copy_(row, non_blocking=True)
+        loss_row = eng.step_external(tu_h[k % 4], B)      # pinned host row the step's loss is copied into
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e = {"value": K * B / (e2e_ms * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": 3 * B * 4,
-           "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / K,
-           "api": "LightGCNEngine.step_external (host pinned triples -> H2D -> grouping -> step kernels -> loss D2H)"}
+           "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / K, "last_loss": float(loss_row[0]),
+           "api": "LightGCNEngine.step_external: triples in HOST memory -> pinned staging slot -> one CUDA-graph replay "
+                  "per step (H2D memcpy nodes, grouping, step kernels, D2H of the loss row)"}
 
     # ---- full-rank evaluation (users/s)
     ev = FullRankEvaluator.from_arrays(U, I, D["tu"], D["ti"], D["su"], D["si"], dev)
-    F = eng.forward_table().clone()
+    F = eng.full_table(eng.forward_table()).clone()
     n_test = ev.user_rows.numel()
     if world > 1:
         ev.topk = lambda ue_, ie_, k_, impl=None: ev.topk_sharded(ue_, ie_, k_, rank, world, impl)
@@ -383,8 +392,12 @@ def run_ours(args):
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config_of(args, D),
         "roofline": roofline, "e2e": e2e, "eval": evald, "clocks": clk.summary(),
-        "parallelism": "single GPU" if world == 1 else
-        "row-partitioned x%d: per-layer all-gather fused into the SpMM epilogue (NVLink P2P stores), item-sharded eval" % world,
+        "parallelism": {"single": "single GPU",
+                        "rows": "row-partitioned x%d: per-layer all-gather fused into the SpMM epilogue (NVLink P2P "
+                                "stores), item-sharded eval" % world,
+                        "dshard": "column-sharded x%d: every table split [N, d/%d], graph replicated, propagation / "
+                                  "backward / Adam communication-free, one P2P exchange of the partial scores (16 B per "
+                                  "triple per peer) + one barrier per step; item-sharded eval" % (world, world)}[eng.mode],
         "gpu_launches": K * eng.launches_per_step, "last_loss": loss_last,
     }
     if rank == 0 and not args.no_cpu_baseline:

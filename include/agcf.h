@@ -14,7 +14,8 @@
  *     enqueues work on it and is capturable in a CUDA graph;
  *   - return value: 0 = ok, <0 = AGCF_E* below; nothing throws;
  *   - fp32 everywhere, int32 indices; tables are row-major [rows, d], 16-byte
- *     aligned, d in {32, 64, 128, 256};
+ *     aligned, d in {32, 64, 128, 256}; the row kernels (propagation, loss, optimizer) also take
+ *     d in {8, 16}: the column slices of d-sharded multi-GPU tables;
  *   - a "node" id is a row of the stacked table [users; items] (N = U + I); item
  *     ids handed to the loss / sampler / eval calls are item-local (0..I-1).
  */
@@ -141,6 +142,22 @@ int64_t agcf_bpr_ws_bytes(int32_t nb);
 int agcf_bpr_forward(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
                      int32_t nb, int32_t n_users, int32_t d, float reg,
                      float* out4, float* coef, void* ws, agcf_stream_t stream);
+
+/* The same forward when the tables are COLUMN-sharded over `world` GPUs (d here is the local slice
+ * width): agcf_bpr_partial computes each triple's share {<u,i>, <u,j>, |u|^2, |i|^2} on this rank's
+ * slice and stores it into slot `rank` of the exchange buffer of EVERY rank (xchg_all_host: HOST array
+ * of `world` device pointers, own buffer included, peer-mapped over NVLink; agcf_bpr_xchg_bytes(cap)
+ * bytes each, cap >= nb).  After a cross-rank barrier agcf_bpr_finish sums the shares in rank order --
+ * the same bits on every rank -- and produces out4 / coef exactly like agcf_bpr_forward.  The buffer
+ * is double-buffered on the parity of *step_dev (device step counter, nullable), so one barrier per
+ * step is enough.  This is the ONLY exchange of a d-sharded training step: 16*nb bytes per peer. */
+int64_t agcf_bpr_xchg_bytes(int32_t cap);
+int agcf_bpr_partial(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
+                     int32_t nb, int32_t n_users, int32_t d, int32_t rank, int32_t cap,
+                     const int32_t* step_dev, void* const* xchg_all_host, int32_t world,
+                     agcf_stream_t stream);
+int agcf_bpr_finish(const void* xchg, int32_t world, int32_t cap, int32_t nb, float reg,
+                    const int32_t* step_dev, float* out4, float* coef, void* ws, agcf_stream_t stream);
 
 /* Backward of the above into the dense gradient of F, atomic-free: one
  * half-warp per node segment sums that node's contributions in occurrence order

@@ -1,5 +1,5 @@
 """Worker for tests/test_gpu_dist.py (run under torchrun, one rank per GPU): the
-row-partitioned multi-GPU engine must reproduce the single-GPU engine."""
+row-partitioned and the column-sharded multi-GPU engines must reproduce the single-GPU engine."""
 import os
 import sys
 
@@ -52,6 +52,26 @@ def main():
     Fm = multi.forward_table()
     torch.cuda.synchronize(); dist.barrier()
     assert float((Fm - Fs).abs().max()) < 1e-6
+    # column-sharded engine ("dshard"): graph replicated, every table split by columns, one exchange per step
+    comm2 = DistContext(dev)
+    shard = LightGCNEngine(g, table0.clone().to(dev), U, L, 0.005, 1e-4, B, E, comm=comm2, mode="dshard")
+    assert shard.d == d // world
+    shard.sample_epoch(ts, 7, 0)
+    shard.run_steps(0, 3, use_graph=False)
+    shard.run_steps(3, 2, use_graph=True)                  # graph capture incl. the barrier and the parity buffers
+    torch.cuda.synchronize(); dist.barrier()
+    full = shard.full_table(shard.E0)
+    derr = float((full - single.E0).abs().max())
+    dloss = float((shard.out4[:5] - single.out4[:5]).abs().max())
+    assert derr < 2e-6, "rank %d: d-sharded table differs from single-GPU by %g" % (rank, derr)
+    assert dloss < 2e-6, dloss
+    Fd = shard.full_table(shard.forward_table())
+    torch.cuda.synchronize(); dist.barrier()
+    assert float((Fd - Fs).abs().max()) < 2e-6
+    # every rank computed identical loss rows (partials are summed in rank order everywhere)
+    rows = [torch.empty_like(shard.out4[:5]) for _ in range(world)]
+    dist.all_gather(rows, shard.out4[:5].contiguous())
+    assert all(torch.equal(rows[0], r) for r in rows)
     # item-sharded evaluation == unsharded
     ev = FullRankEvaluator.from_arrays(U, I, tu, ti, su, si, dev)
     v1, i1 = ev.topk(Fs[:U], Fs[U:], 50)
@@ -59,7 +79,7 @@ def main():
     assert torch.equal(i1, i2) and torch.equal(v1, v2)
     dist.barrier()
     if rank == 0:
-        print("DIST_CHECK_OK world=%d table_err=%.2e" % (world, err))
+        print("DIST_CHECK_OK world=%d table_err=%.2e dshard_err=%.2e" % (world, err, derr))
     dist.destroy_process_group()
 
 

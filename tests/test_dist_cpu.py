@@ -74,3 +74,52 @@ def test_balanced_row_ranges_edge_cases():
     for w in (1, 2, 3, 8):
         b = balanced_row_ranges(indptr, w)
         assert len(b) == w + 1 and b[0] == 0 and b[-1] == 7 and all(x <= y for x, y in zip(b, b[1:]))
+
+
+def _dshard_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import types
+    from arlib_b200.engine import LightGCNEngine, dshard_columns
+    N, d = 37, 32
+    torch.manual_seed(0)
+    table = torch.randn(N, d)
+    c0, c1 = dshard_columns(d, world, rank)
+    fake = types.SimpleNamespace(mode="dshard", N=N, d_full=d, comm=types.SimpleNamespace(world=world, group=dist.group.WORLD))
+    full = LightGCNEngine.full_table(fake, table[:, c0:c1].contiguous())
+    # the partial scores of the d-sharded loss: per-slice dots summed in rank order == the full dot
+    u, i = torch.arange(10), torch.arange(10, 20)
+    part = (table[u, c0:c1] * table[i, c0:c1]).sum(1)
+    parts = [torch.empty_like(part) for _ in range(world)]
+    dist.all_gather(parts, part)
+    ok_dot = torch.allclose(sum(parts), (table[u] * table[i]).sum(1), atol=1e-5)
+    if rank == 0:
+        out.put((bool(torch.equal(full, table)), bool(ok_dot), (c0, c1)))
+    dist.destroy_process_group()
+
+
+def test_dshard_column_layout_world2():
+    """Column-sharded mode: slices [r*d/P, (r+1)*d/P), reassembly by all-gather + interleave, and
+    additivity of the per-slice partial scores."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dshard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same, ok_dot, cols = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same and ok_dot and cols == (0, 16)
+
+
+def test_dshard_columns_rejects_unsupported_widths():
+    import pytest
+    from arlib_b200.engine import dshard_columns
+    assert dshard_columns(64, 8, 3) == (24, 32)
+    with pytest.raises(ValueError):
+        dshard_columns(64, 3, 0)
+    with pytest.raises(ValueError):
+        dshard_columns(64, 16, 0)          # 4-column slices are below the 16-byte lane granularity x 2

@@ -44,6 +44,25 @@ def test_topk_exact_scores_and_sets(U, I, d, K):
         assert_topk_matches(idx[r], s64, K, 1e-4)
 
 
+def test_topk_warp_kernel_overflow_goes_through_block_kernel(monkeypatch):
+    """Stage 2 runs one warp per user with room for a bounded number of candidate groups; users beyond
+    it are handed to the block-per-user kernel.  Forcing a tiny bound must not change a single bit."""
+    from arlib_b200 import ops
+    rng = np.random.default_rng(3)
+    U, I, d, K = 300, 5000, 64, 50
+    ue, ie = torch.randn(U, d, device=DEV), torch.randn(I, d, device=DEV)
+    lists = [rng.choice(I, size=int(rng.integers(0, 40)), replace=False) for _ in range(U)]
+    mrp, mit = _mask_csr(U, lists)
+    for impl in (0, 1):
+        monkeypatch.delenv("AGCF_STAGE2_CMAX", raising=False)
+        v0, i0, f0 = ops.score_topk(ue, ie, K, mask_rowptr=mrp, mask_items=mit, impl=impl, return_flags=True)
+        monkeypatch.setenv("AGCF_STAGE2_CMAX", "40")      # K = 50 groups are always candidates -> every user overflows
+        v1, i1, f1 = ops.score_topk(ue, ie, K, mask_rowptr=mrp, mask_items=mit, impl=impl, return_flags=True)
+        assert int(f0.min()) >= K and torch.equal(f0, f1)
+        assert torch.equal(i0, i1) and torch.equal(v0, v1)
+    monkeypatch.delenv("AGCF_STAGE2_CMAX", raising=False)
+
+
 def test_topk_tie_rule_kat():
     """Heavy exact ties: integer-valued embeddings make many scores identical; the set
     must follow the reference heap's rule, not lowest/highest-id-first."""

@@ -37,6 +37,37 @@ def test_engine_epoch_matches_reference_golden(golden, use_graph):
     assert int(eng.step_dev) == len(golden["batch_len"])
 
 
+def test_engine_step_external_host_triples_matches_golden(golden):
+    """The end-to-end entry (triples in HOST memory, graph replay per staging slot) consumes the
+    reference's batches identically: same losses, same parameters after the epoch."""
+    from oracle import port
+    from arlib_b200.engine import LightGCNEngine
+    from arlib_b200.graph import DeviceGraph
+    U, I = golden["user_names"].shape[0], golden["item_names"].shape[0]
+    adj = port.bipartite_adjacency(golden["train_u"].astype(np.int64), golden["train_i"].astype(np.int64), U, I)
+    g = DeviceGraph.from_dataloader_adj(adj, DEV)
+    table = torch.cat([torch.from_numpy(golden["init_user_emb"]), torch.from_numpy(golden["init_item_emb"])]).to(DEV)
+    B = 2048
+    eng = LightGCNEngine(g, table, U, 2, 0.005, 1e-4, B, B)
+    bu, bi, bj = golden["batch_u"], golden["batch_i"], golden["batch_j"]
+    lens = golden["batch_len"]
+    losses, t0 = [], 0
+    for nb in lens:
+        nb = int(nb)
+        host = torch.zeros((3, B), dtype=torch.int32)
+        host[0, :nb] = torch.from_numpy(bu[t0:t0 + nb].astype(np.int32))
+        host[1, :nb] = torch.from_numpy(bi[t0:t0 + nb].astype(np.int32))
+        host[2, :nb] = torch.from_numpy(bj[t0:t0 + nb].astype(np.int32))
+        row = eng.step_external(host, nb)
+        torch.cuda.synchronize()
+        losses.append(float(row[0]))
+        t0 += nb
+    np.testing.assert_allclose(np.array(losses), golden["batch_loss"], rtol=2e-5)
+    assert _rel(table[:U].cpu(), torch.from_numpy(golden["param_user_emb"])) < 1e-4
+    assert _rel(table[U:].cpu(), torch.from_numpy(golden["param_item_emb"])) < 1e-4
+    assert int(eng.step_dev) == len(lens)
+
+
 def _args(**kw):
     base = dict(topK="50", emb_size=64, n_layers=2, batch_size=2048, lRate=0.005, reg=1e-4, maxEpoch=1, seed=2018,
                 sampler="host", model_name="LightGCN")

@@ -16,7 +16,9 @@ __device__ __forceinline__ uint32_t mix(uint32_t h) {
   return h;
 }
 
-template <int V4, int UNROLL>
+// SKEW: row r is drawn with probability ~ r^-1/2 (r = N u^2), the column popularity of the synthetic
+// power-law graphs: the hottest rows are requested thousands of times per launch from all SMs
+template <int V4, int UNROLL, bool SKEW = false>
 __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ X, int n_rows, long long gathers_per_group,
                                                      float4* __restrict__ sink) {
   constexpr int LPR = V4;                       // lanes per row, one float4 per lane
@@ -30,7 +32,11 @@ __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ 
 #pragma unroll
     for (int q = 0; q < UNROLL; ++q) {
       h = h * 1664525u + 1013904223u;
-      const uint32_t r = __umulhi(mix(h), (uint32_t)n_rows);
+      uint32_t r = __umulhi(mix(h), (uint32_t)n_rows);
+      if (SKEW) {
+        const float u = (float)(mix(h) >> 8) * (1.0f / 16777216.0f);
+        r = min((uint32_t)((float)n_rows * u * u), (uint32_t)n_rows - 1);
+      }
       x[q] = __ldg(X + (size_t)r * V4 + gl);
     }
 #pragma unroll
@@ -73,16 +79,16 @@ static float time_ms(F f, int reps = 20) {
   return ms / reps;
 }
 
-template <int V4, int UNROLL>
+template <int V4, int UNROLL, bool SKEW = false>
 static void run_gather(const float4* X, int n_rows, float4* sink, int ctas_per_sm) {
   const long long total_gathers = 1ll << 24;                   // 16 M row gathers per launch
   const int blocks = 148 * ctas_per_sm;
   const long long groups = (long long)blocks * 256 / V4;
   long long per = (total_gathers / groups + UNROLL - 1) / UNROLL * UNROLL;
-  const float ms = time_ms([&] { gather_kernel<V4, UNROLL><<<blocks, 256>>>(X, n_rows, per, sink); });
+  const float ms = time_ms([&] { gather_kernel<V4, UNROLL, SKEW><<<blocks, 256>>>(X, n_rows, per, sink); });
   CK(cudaGetLastError());
   const double bytes = (double)per * groups * V4 * 16;
-  printf("gather row=%4d B  unroll=%2d  ctas/sm=%d  table=%.1f MB : %8.1f GB/s  (%.3f ms)\n", V4 * 16, UNROLL, ctas_per_sm,
+  printf("gather %s row=%4d B  unroll=%2d  ctas/sm=%d  table=%.1f MB : %8.1f GB/s  (%.3f ms)\n", SKEW ? "power-law" : "uniform  ", V4 * 16, UNROLL, ctas_per_sm,
          (double)n_rows * V4 * 16 / 1e6, bytes / ms / 1e6, ms);
 }
 
@@ -101,6 +107,9 @@ int main(int argc, char** argv) {
     run_gather<16, 8>(X, n_rows, sink, c);
     run_gather<16, 16>(X, n_rows, sink, c);
   }
+  run_gather<16, 8, true>(X, n_rows, sink, 4);
+  run_gather<16, 8, true>(X, n_rows, sink, 8);
+  run_gather<8, 8, true>(X, n_rows * 2, sink, 8);
   run_gather<8, 16>(X, n_rows * 2, sink, 8);
   run_gather<4, 16>(X, n_rows * 4, sink, 8);
   run_gather<2, 16>(X, n_rows * 8, sink, 8);
