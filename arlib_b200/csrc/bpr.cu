@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(const int32_t* __restric
 struct AdamPeers {
   int n;
   float* p[AGCF_MAX_PEERS];
+  float* mc;        // multicast address of the same range (nullable): one store reaches every copy
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g,
@@ -455,13 +456,15 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
     upd(pp.z, gg.z, mm.z, vv.z);
     upd(pp.w, gg.w, mm.w, vv.w);
     p[k] = pp; m[k] = mm; v[k] = vv;
-    for (int q = 0; q < peers.n; ++q) reinterpret_cast<float4*>(peers.p[q])[k] = pp;
+    if (peers.mc != nullptr) st_multicast_f4(reinterpret_cast<float4*>(peers.mc) + k, pp);
+    else for (int q = 0; q < peers.n; ++q) reinterpret_cast<float4*>(peers.p[q])[k] = pp;
   }
   if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) {
     float pp = p_tail[threadIdx.x], mm = m_tail[threadIdx.x], vv = v_tail[threadIdx.x];
     upd(pp, g_tail[threadIdx.x], mm, vv);
     p_tail[threadIdx.x] = pp; m_tail[threadIdx.x] = mm; v_tail[threadIdx.x] = vv;
-    for (int q = 0; q < peers.n; ++q) peers.p[q][n4 * 4 + threadIdx.x] = pp;
+    if (peers.mc != nullptr) asm volatile("multimem.st.weak.global.f32 [%0], %1;" :: "l"(peers.mc + n4 * 4 + threadIdx.x), "f"(pp) : "memory");
+    else for (int q = 0; q < peers.n; ++q) peers.p[q][n4 * 4 + threadIdx.x] = pp;
   }
 }
 
@@ -652,11 +655,13 @@ extern "C" int agcf_zero_rows(const int32_t* seg_node, const int32_t* n_seg, int
 extern "C" int agcf_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n,
                                   float lr, float beta1, float beta2, float eps,
                                   int32_t step, const int32_t* step_dev,
-                                  void* const* peer_p_host, int32_t n_peers, agcf_stream_t stream) {
+                                  void* const* peer_p_host, int32_t n_peers, void* mc_p, agcf_stream_t stream) {
   if (!p || !g || !m || !v || n < 0) return AGCF_EINVAL;
+  if (!aligned16(mc_p)) return AGCF_EINVAL;
   if (n_peers < 0 || n_peers > AGCF_MAX_PEERS || (n_peers > 0 && !peer_p_host)) return AGCF_EINVAL;
   AdamPeers peers;
   peers.n = n_peers;
+  peers.mc = reinterpret_cast<float*>(mc_p);
   for (int q = 0; q < AGCF_MAX_PEERS; ++q) peers.p[q] = q < n_peers ? reinterpret_cast<float*>(peer_p_host[q]) : nullptr;
   if (step_dev == nullptr && step < 1) return AGCF_EINVAL;
   if (!aligned16(p) || !aligned16(g) || !aligned16(m) || !aligned16(v)) return AGCF_EINVAL;

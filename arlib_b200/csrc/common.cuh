@@ -61,6 +61,12 @@ __device__ __forceinline__ void st_stream_f4(float4* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// store through an NVSwitch multicast mapping: the switch replicates the 16 bytes into every GPU's copy
+__device__ __forceinline__ void st_multicast_f4(float4* mc, const float4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void fma4(float4& acc, float a, const float4& x) {
   acc.x = fmaf(a, x.x, acc.x);
   acc.y = fmaf(a, x.y, acc.y);

@@ -51,6 +51,10 @@ struct SpmmParams {
   int n_peers;
   float4* peer_Y[AGCF_MAX_PEERS];
   float4* peer_acc[AGCF_MAX_PEERS];
+  // NVSwitch multicast addresses of Y / acc_out (nullable): ONE multimem.st reaches every GPU's copy, so a
+  // rank's egress per layer is its own rows once instead of once per peer
+  float4* mc_Y;
+  float4* mc_acc;
 };
 
 __device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ m, int k) {
@@ -106,10 +110,15 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
   if (p.Y != nullptr) {
 #pragma unroll
     for (int v = 0; v < C::VPL; ++v) p.Y[rbase + v * C::LPR + gl] = t[v];
-    for (int q = 0; q < p.n_peers; ++q) {
-      if (p.peer_Y[q] == nullptr) continue;
+    if (p.mc_Y != nullptr) {
 #pragma unroll
-      for (int v = 0; v < C::VPL; ++v) p.peer_Y[q][rbase + v * C::LPR + gl] = t[v];
+      for (int v = 0; v < C::VPL; ++v) st_multicast_f4(p.mc_Y + rbase + v * C::LPR + gl, t[v]);
+    } else {
+      for (int q = 0; q < p.n_peers; ++q) {
+        if (p.peer_Y[q] == nullptr) continue;
+#pragma unroll
+        for (int v = 0; v < C::VPL; ++v) p.peer_Y[q][rbase + v * C::LPR + gl] = t[v];
+      }
     }
   }
   if (p.acc_out != nullptr) {
@@ -123,8 +132,12 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
         o.z = __fdiv_rn(o.z, p.acc_div); o.w = __fdiv_rn(o.w, p.acc_div);
       }
       p.acc_out[rbase + v * C::LPR + gl] = o;
-      for (int q = 0; q < p.n_peers; ++q)
-        if (p.peer_acc[q] != nullptr) p.peer_acc[q][rbase + v * C::LPR + gl] = o;
+      if (p.mc_acc != nullptr) {
+        st_multicast_f4(p.mc_acc + rbase + v * C::LPR + gl, o);
+      } else {
+        for (int q = 0; q < p.n_peers; ++q)
+          if (p.peer_acc[q] != nullptr) p.peer_acc[q][rbase + v * C::LPR + gl] = o;
+      }
     }
   }
 }
@@ -171,8 +184,10 @@ __device__ __forceinline__ void spmm_accumulate_chunks(const SpmmParams& p, int 
       v_next[k] = 0.f;
       const int e = off + k * C::LPR + gl;
       if (e < len) {
-        c_next[k] = ld_stream_i32(p.col + s + e);
-        v_next[k] = ld_stream_f32(p.val + s + e);
+        // narrow rows (EPL > 1): a lane group covers only LPR * 4 bytes per load, so the EPL loads of a chunk
+        // touch the same 32-byte sectors again and again -- let L1 keep them; wide rows stream past L1
+        c_next[k] = C::EPL > 1 ? __ldg(p.col + s + e) : ld_stream_i32(p.col + s + e);
+        v_next[k] = C::EPL > 1 ? __ldg(p.val + s + e) : ld_stream_f32(p.val + s + e);
         if (p.col_mask != nullptr && !bit_set(p.col_mask, c_next[k])) c_next[k] = -1;
       }
     }
@@ -404,6 +419,7 @@ extern "C" int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, cons
                                  const int32_t* row_order, int32_t n_long,
                                  const uint32_t* row_mask, const uint32_t* col_mask,
                                  void* const* peer_Y_host, void* const* peer_acc_host, int32_t n_peers,
+                                 void* mc_Y, void* mc_acc,
                                  int32_t n_rows, int32_t d, agcf_stream_t stream) {
   if (n_peers < 0 || n_peers > AGCF_MAX_PEERS) return AGCF_EINVAL;
   if (!rowptr || !col || !val || !X || n_rows < 0 || (Y == nullptr && acc_out == nullptr)) return AGCF_EINVAL;
@@ -425,6 +441,9 @@ extern "C" int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, cons
   p.eps = eps;
   p.row_order = row_order; p.n_long = n_long; p.n_rows = n_rows;
   p.row_mask = row_mask; p.col_mask = col_mask;
+  if (!aligned16(mc_Y) || !aligned16(mc_acc)) return AGCF_EINVAL;
+  p.mc_Y = Y != nullptr ? reinterpret_cast<float4*>(mc_Y) : nullptr;
+  p.mc_acc = acc_out != nullptr ? reinterpret_cast<float4*>(mc_acc) : nullptr;
   p.n_peers = n_peers;
   for (int q = 0; q < AGCF_MAX_PEERS; ++q) {
     p.peer_Y[q] = (q < n_peers && peer_Y_host) ? reinterpret_cast<float4*>(peer_Y_host[q]) : nullptr;

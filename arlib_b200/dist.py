@@ -33,6 +33,8 @@ class DistContext:
         self.hdl = None
         self._off = {}
         self._chan = 0
+        import os
+        self.use_multicast = os.environ.get("ARLIB_B200_MULTICAST", "1") == "1"    # tuning switch
 
     def allocate(self, specs):
         """specs: {name: (shape, dtype)} -> {name: local tensor}; all in ONE symmetric
@@ -62,6 +64,14 @@ class DistContext:
         """device pointers of buffer ``name`` on ALL ranks in rank order (own copy included)"""
         base = self._off[name] + int(extra_bytes)
         return [int(self.hdl.buffer_ptrs[r]) + base for r in range(self.world)]
+
+    def multicast_ptr(self, name, extra_bytes=0):
+        """NVSwitch multicast address of buffer ``name`` (a store to it lands in every rank's copy), or 0
+        when the platform has no multicast mapping (then the per-peer pointers are used)."""
+        base = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        if base == 0 or not self.use_multicast:
+            return 0
+        return base + self._off[name] + int(extra_bytes)
 
     def barrier(self):
         """device-side barrier across ranks on the current stream"""

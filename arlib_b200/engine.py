@@ -153,6 +153,9 @@ class LightGCNEngine:
             row_off = self.r0 * self.d * 4
             self._peer = {k: comm.peers(k) for k in ("E0", "F", "fw0", "fw1", "bw0", "bw1")}
             self._peer_E0_rows = comm.peers("E0", row_off)
+            # NVSwitch multicast mappings of the same buffers (0 when unavailable): one store reaches all copies
+            self._mc = {k: comm.multicast_ptr(k) for k in ("E0", "F", "fw0", "fw1", "bw0", "bw1")}
+            self._mc_E0_rows = comm.multicast_ptr("E0", row_off)
             torch.cuda.synchronize()
             comm.barrier()
         self.G = torch.zeros_like(table)
@@ -186,6 +189,9 @@ class LightGCNEngine:
 
     def _peers(self, name):
         return self._peer[name] if self.mode == "rows" else None
+
+    def _mcast(self, name):
+        return self._mc[name] if self.mode == "rows" else 0
 
     def _barrier(self):
         if self.mode == "rows":
@@ -252,7 +258,8 @@ class LightGCNEngine:
             y = None if last else self.fw[(k - 1) % 2]
             ops.spmm(self.g, x, Y=y, acc_in=self.E0 if k == 1 else F, acc_out=F,
                      acc_div=float(self.L + 1) if last else 1.0, row_mask=row_mask if last else None,
-                     peer_Y=None if last else self._peers(name), peer_acc=self._peers("F") if last else None)
+                     peer_Y=None if last else self._peers(name), peer_acc=self._peers("F") if last else None,
+                     mc_Y=0 if last else self._mcast(name), mc_acc=self._mcast("F") if last else 0)
             self._barrier()
             x = y
         return F
@@ -281,7 +288,7 @@ class LightGCNEngine:
             if k > 1:
                 nxt = self.bw[k % 2]
                 ops.spmm(self.g, H, Y=nxt, addend=self.G, col_mask=mask if k == L else None,
-                         peer_Y=self._peers("bw%d" % (k % 2)))
+                         peer_Y=self._peers("bw%d" % (k % 2)), mc_Y=self._mcast("bw%d" % (k % 2)))
                 self._barrier()
                 H = nxt
             else:
@@ -292,7 +299,8 @@ class LightGCNEngine:
         r0, r1 = self.r0, self.r1
         ops.adam_step(self.E0[r0:r1], self.dE0[r0:r1], self.m[r0:r1], self.v[r0:r1], self.lr, self.betas[0],
                       self.betas[1], self.adam_eps, step_dev=self.step_dev,
-                      peer_p=self._peer_E0_rows if self.mode == "rows" else None)
+                      peer_p=self._peer_E0_rows if self.mode == "rows" else None,
+                      mc_p=self._mc_E0_rows if self.mode == "rows" else 0)
         ops.increment(self.step_dev)
         self._barrier()
 

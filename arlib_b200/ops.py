@@ -33,7 +33,7 @@ def _p(t):
 
 
 def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_div=1.0, noise=None, eps=0.0,
-         row_mask=None, col_mask=None, peer_Y=None, peer_acc=None):
+         row_mask=None, col_mask=None, peer_Y=None, peer_acc=None, mc_Y=None, mc_acc=None):
     """agcf_spmm_csr_f32: t = A X (+addend) (+noise perturbation); Y = t;
     acc_out = (acc_in + t) / acc_div."""
     lib = _lib.load()
@@ -51,7 +51,7 @@ def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_
     _lib.check(lib.agcf_spmm_csr_f32(g.p_rowptr.data_ptr(), g.p_col.data_ptr(), g.p_val.data_ptr(), X.data_ptr(), _p(Y),
                                      _p(addend), _p(acc_in), _p(acc_out), float(acc_div), _p(noise), float(eps),
                                      g.row_order.data_ptr(), g.n_long, _p(row_mask), _p(col_mask), py, pa, max(n1, n2),
-                                     g.n_local_rows, d, _lib.stream_ptr()), "agcf_spmm_csr_f32")
+                                     mc_Y or None, mc_acc or None, g.n_local_rows, d, _lib.stream_ptr()), "agcf_spmm_csr_f32")
 
 
 def sddmm(g: DeviceGraph, H, E, gval, accumulate=False):
@@ -138,12 +138,12 @@ def zero_rows(seg_node, n_seg, max_seg, G):
                                   _lib.stream_ptr()), "agcf_zero_rows")
 
 
-def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0, step_dev=None, peer_p=None):
+def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0, step_dev=None, peer_p=None, mc_p=None):
     lib = _lib.load()
     _f32(p, "p"); _f32(g, "g"); _f32(m, "m"); _f32(v, "v")
     pp, n = _lib.ptr_array(peer_p)
     _lib.check(lib.agcf_adam_step_f32(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr),
-                                      float(beta1), float(beta2), float(eps), int(step), _p(step_dev), pp, n,
+                                      float(beta1), float(beta2), float(eps), int(step), _p(step_dev), pp, n, mc_p or None,
                                       _lib.stream_ptr()), "agcf_adam_step_f32")
 
 

@@ -74,6 +74,10 @@ int agcf_csr_expand_rows(const int32_t* rowptr, int32_t* row_of, int32_t n_rows,
  * to the other ranks' copies of Y / acc_out (peer-mapped over NVLink): the epilogue
  * stores every computed row there too -- the per-layer all-gather is fused into the
  * SpMM and overlaps it row by row.  Visibility on the peers needs a barrier after.
+ * mc_Y / mc_acc (nullable): NVSwitch MULTICAST addresses of Y / acc_out (a multicast object bound
+ * to every rank's copy): the epilogue then issues ONE multimem.st per 16 bytes and the switch
+ * replicates it to all GPUs -- a rank's NVLink egress per layer is its rows once, not once per peer;
+ * the peer arrays are ignored when these are given.
  * Forward AND backward of the encoder: A is symmetric so A^T = A.
  * Replaces: torch.sparse.mm + stack + mean in recommender/LightGCN.py:230-240,
  * the noise lines of recommender/SimGCL.py:202-206 / XSimGCL.py:211-215, and the
@@ -86,6 +90,7 @@ int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* va
                       const int32_t* row_order, int32_t n_long,
                       const uint32_t* row_mask, const uint32_t* col_mask,
                       void* const* peer_Y_host, void* const* peer_acc_host, int32_t n_peers,
+                      void* mc_Y, void* mc_acc,
                       int32_t n_rows, int32_t d, agcf_stream_t stream);
 
 /* gval[p] (+)= <H[i,:], E[col[p],:]> for p in row i (accumulate != 0 adds).
@@ -184,13 +189,14 @@ int agcf_zero_rows(const int32_t* seg_node, const int32_t* n_seg, int32_t max_se
  *   p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
  * t = *step_dev + 1 if step_dev (device int32, NOT modified) else step (>=1).
  * peer_p_host (nullable): the updated parameters are also stored at the same offsets
- * of n_peers peer-mapped copies (multi-GPU: owner updates its rows everywhere).
+ * of n_peers peer-mapped copies (multi-GPU: owner updates its rows everywhere), or -- when mc_p, the
+ * multicast address of the same range, is given -- with one multimem.st that reaches every copy.
  * Replaces: optimizer.step() of recommender/LightGCN.py:32-35,64 when the caller
  * did not hand in its own optimizer. */
 int agcf_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n,
                        float lr, float beta1, float beta2, float eps,
                        int32_t step, const int32_t* step_dev,
-                       void* const* peer_p_host, int32_t n_peers, agcf_stream_t stream);
+                       void* const* peer_p_host, int32_t n_peers, void* mc_p, agcf_stream_t stream);
 int agcf_increment_i32(int32_t* counter, agcf_stream_t stream);
 
 /* ----------------------------------------------------------------- evaluation

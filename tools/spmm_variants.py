@@ -10,7 +10,7 @@ from arlib_b200.graph import DeviceGraph
 name = sys.argv[1] if len(sys.argv) > 1 else "gowalla"
 alpha = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
 D = make_data(name, alpha)
-U, I, E, d = D["U"], D["I"], D["E"], D["d"]
+U, I, E, d = D["U"], D["I"], D["E"], int(os.environ.get("SPMM_D", D["d"]))
 N = U + I
 dev = torch.device("cuda:0")
 half = sp.csr_matrix((np.ones(E, dtype=np.float32), (D["tu"], D["ti"] + U)), shape=(N, N), dtype=np.float32)
@@ -35,9 +35,19 @@ def timeit(fn, n=200):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n * 1e3
 
+part = os.environ.get("SPMM_PART")            # "world": time each rank's row partition on this one GPU (no peer stores)
+if part:
+    w = int(part)
+    b = g.row_ranges(w)
+    for r in range(w):
+        gp = g.partition(b[r], b[r + 1])
+        tp = timeit(lambda: ops.spmm(gp, X, Y=Y, acc_in=X, acc_out=A))
+        deg = np.diff(gp.p_rowptr.cpu().numpy())
+        print("partition %d/%d rows [%d,%d) nnz %d n_long %d max deg %d: %.1f us" % (r, w, b[r], b[r + 1], gp.local_nnz, gp.n_long, deg.max(), tp))
+    sys.exit(0)
 t_full = timeit(lambda: ops.spmm(g, X, Y=Y, acc_in=X, acc_out=A))
 t_row = timeit(lambda: ops.spmm(g, X, acc_in=A, acc_out=A, row_mask=mask))
 t_col = timeit(lambda: ops.spmm(g, Xs, Y=Y, addend=Xs, col_mask=mask))
 live = np.diff(g.rowptr.cpu().numpy())[nodes].sum() / g.nnz
-print("variant %s %s a=%s: full %.1f us  row-masked %.1f us  col-masked %.1f us  (live nnz %.3f, n_long %d)"
-      % (os.environ.get("AGCF_SPMM_VARIANT", "0"), name, alpha, t_full, t_row, t_col, live, g.n_long))
+print("d=%d variant %s %s a=%s: full %.1f us  row-masked %.1f us  col-masked %.1f us  (live nnz %.3f, n_long %d)"
+      % (d, os.environ.get("AGCF_SPMM_VARIANT", "0"), name, alpha, t_full, t_row, t_col, live, g.n_long))
