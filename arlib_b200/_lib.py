@@ -29,7 +29,7 @@ SIGNATURES = {
     "agcf_device_sm_count": (c_int32, []),
     "agcf_norm_adj_csr": (c_int32, [P, P, P, P, P, P, I32, I64, P]),
     "agcf_csr_expand_rows": (c_int32, [P, P, I32, I64, P]),
-    "agcf_spmm_csr_f32": (c_int32, [P, P, P, P, P, P, P, P, F32, P, F32, P, I32, P, P, P, P, I32, P, P, I32, I32, P]),
+    "agcf_spmm_csr_f32": (c_int32, [P, P, I32, P, P, P, P, P, P, P, P, P, F32, P, F32, P, P, P, P, I32, P, P, I32, P]),
     "agcf_sddmm_csr_f32": (c_int32, [P, P, P, P, P, I32, P, I32, I32, P]),
     "agcf_concat_rows_f32": (c_int32, [P, I64, P, I64, P, I32, P]),
     "agcf_bpr_sample_epoch": (c_int32, [P, P, I32, P, P, I32, U64, U64, P, P, P, P]),

@@ -10,27 +10,34 @@
 // attack/White/PGA.py:97-117 (adjacency gradient), util/DataLoader.py:73-87 and
 // recommender/LightGCN.py:212-215 (normalization).
 //
-// SpMM design (HBM/L2-bound gather, no tensor cores -- see DESIGN.md):
+// SpMM design (L2-gather bound, no tensor cores -- see DESIGN.md):
 //   * a row of X is d fp32 = d/4 float4; LPR = min(d/4, 32) lanes own one row and
 //     each lane loads 16 B, so one warp-level LDG.128 fetches whole 128 B lines of
 //     32/LPR different neighbour rows (fully coalesced sectors);
-//   * rows are processed in `row_order` (degree descending): the two rows sharing a
-//     warp have ~equal length, long rows start first, the tail is 1-nnz rows;
-//   * col/val of a row are read 16/32 at a time, coalesced, streaming (no L1
-//     allocation) and broadcast by shuffle; up to LPR independent row gathers are
-//     in flight per lane before the FMA chain consumes them;
-//   * the first n_long rows (degree > a threshold chosen by the host) get a whole
-//     CTA: 256/LPR lane groups stride over the row, partials are reduced through
-//     shared memory in a fixed order (no atomics, deterministic);
-//   * epilogue fuses: + addend (backward's G/(L+1)), SimGCL noise, Y store, and
-//     the running layer sum / mean (acc_out = (acc_in + t) / acc_div).
+//   * the unit of work is a SEGMENT of a row (at most 64 non-zeros, host plan `vrows`):
+//     one lane group per segment, segments sorted by length so the groups of a warp
+//     walk equally long ones.  A hub row is dozens of independent work items instead
+//     of one long pole (that pole set a ~21 us floor under every launch, however few
+//     rows a rank owned);
+//   * col/val of a segment are read 16 at a time, coalesced, and broadcast by shuffle;
+//     the 16 slots of a chunk are unrolled and predicated;
+//   * rows with several segments: every segment stores its partial sum, the one that
+//     arrives last (a ticket per row) adds the partials in segment order and runs the
+//     epilogue -- no floating-point atomics, run-to-run deterministic;
+//   * epilogue fuses: + addend (backward's G/(L+1)), SimGCL noise, Y store, the
+//     running layer sum / mean (acc_out = (acc_in + t) / acc_div) and the stores to
+//     the other GPUs (P2P or one NVSwitch multicast store).
 #include "common.cuh"
 #include <stdlib.h>
 
 namespace agcf {
 
 struct SpmmParams {
-  const int32_t* rowptr;
+  const int4* vrows;          // work items {start, len, row, k | nseg << 16}
+  const int32_t* vpart;       // first partial slot of the item's row (rows with nseg > 1)
+  int32_t n_v;
+  float4* partial;            // [n_partial][d/4] partial sums of multi-segment rows
+  int32_t* tickets;           // [n_partial], zero between launches
   const int32_t* col;
   const float* val;
   const float4* X;
@@ -41,9 +48,6 @@ struct SpmmParams {
   float acc_div;
   const float4* noise;
   float eps;
-  const int32_t* row_order;
-  int32_t n_long;
-  int32_t n_rows;
   const uint32_t* row_mask;   // nullable bitmap over rows: only rows with their bit set are computed / written
   const uint32_t* col_mask;   // nullable bitmap over columns: rows of X outside it are known to be zero (skipped)
   // fused all-gather: the same rows are also stored into the peer GPUs' copies of Y / acc_out
@@ -204,36 +208,6 @@ __device__ __forceinline__ void spmm_accumulate_chunks(const SpmmParams& p, int 
   }
 }
 
-// long row: the whole CTA cooperates on one row (slot = blockIdx.x); partial sums of the lane groups are
-// reduced through shared memory in a fixed order (no atomics, run-to-run deterministic)
-template <typename C, bool NOISE>
-__device__ __forceinline__ void spmm_long_row(const SpmmParams& p, float4 (&acc)[C::VPL], int lane, int warp, int gl) {
-  __shared__ float4 part[C::GROUPS][C::V4];
-  const int row = p.row_order != nullptr ? p.row_order[blockIdx.x] : (int)blockIdx.x;
-  if (p.row_mask != nullptr && !bit_set(p.row_mask, row)) return;      // block-uniform
-  const int s = p.rowptr[blockIdx.x];
-  const int len = p.rowptr[blockIdx.x + 1] - s;
-  const int g = threadIdx.x / C::LPR;
-  const int stride = C::GROUPS * C::CH;
-  const int iters = (len + stride - 1) / stride;       // block-uniform
-  spmm_accumulate_chunks<C, true>(p, s, len, g * C::CH, stride, iters, gl, acc);
-#pragma unroll
-  for (int v = 0; v < C::VPL; ++v) part[g][v * C::LPR + gl] = acc[v];
-  __syncthreads();
-  if (warp == 0) {
-    const bool valid = lane < C::LPR;
-    float4 t[C::VPL];
-#pragma unroll
-    for (int v = 0; v < C::VPL; ++v) {
-      t[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid) {
-        for (int gg = 0; gg < C::GROUPS; ++gg) t[v] = add4(t[v], part[gg][v * C::LPR + gl]);
-      }
-    }
-    spmm_epilogue<C, NOISE>(p, row, valid, t, gl);
-  }
-}
-
 #ifdef AGCF_SPMM_TRACE
 // tuning aid (never in the shipped build): per-CTA timeline of the last launch -- start, metadata arrived,
 // gathers accumulated, end (globaltimer ns, warp 0) and the SM id
@@ -272,27 +246,17 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int gl = lane & (C::LPR - 1);
+  const int grp = lane / C::LPR;
   float4 acc[C::VPL];
 #pragma unroll
   for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  if ((int)blockIdx.x < p.n_long) {
-    spmm_long_row<C, NOISE>(p, acc, lane, warp, gl);
-    return;
-  }
-
-  // ---- short rows: one lane group per row ----------------------------------------
-  const int grp = lane / C::LPR;
-  const long long slot = (long long)p.n_long + ((long long)(blockIdx.x - p.n_long) * (C::THREADS / 32) + warp) * C::RPW + grp;
-  bool valid = slot < p.n_rows;
-  int row = 0, s = 0, len = 0;
-  if (valid) {
-    // row id and row extent are both addressed by the slot: independent loads
-    row = p.row_order != nullptr ? __ldg(p.row_order + slot) : (int)slot;
-    s = __ldg(p.rowptr + slot);
-    len = __ldg(p.rowptr + slot + 1) - s;
-    if (p.row_mask != nullptr && !bit_set(p.row_mask, row)) { valid = false; len = 0; }
-  }
+  const long long slot = ((long long)blockIdx.x * (C::THREADS / 32) + warp) * C::RPW + grp;
+  bool valid = slot < p.n_v;
+  int4 vr = make_int4(0, 0, 0, 1 << 16);
+  if (valid) vr = __ldg(p.vrows + slot);                  // one 16-byte load: start, len, row, segment id
+  const int s = vr.x, row = vr.z, k = vr.w & 0xffff, nseg = vr.w >> 16;
+  int len = vr.y;
+  if (valid && p.row_mask != nullptr && !bit_set(p.row_mask, row)) { valid = false; len = 0; }
   int maxlen = len;
 #pragma unroll
   for (int o = C::LPR; o < 32; o <<= 1) {
@@ -303,7 +267,38 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
   AGCF_TRACE_AFTER(1, maxlen + row);
   spmm_accumulate_chunks<C, true>(p, s, len, 0, C::CH, iters, gl, acc);
   AGCF_TRACE_AFTER(2, __float_as_int(acc[0].x));
-  spmm_epilogue<C, NOISE>(p, row, valid, acc, gl);
+  // ---- rows cut into several segments: combine through the partial-sum scratch -----------------
+  const bool multi = valid && nseg > 1;
+  bool do_epilogue = valid;
+  if (__any_sync(0xffffffffu, multi)) {
+    int pb = 0;
+    if (multi) {
+      pb = __ldg(p.vpart + slot);
+      float4* mine = p.partial + ((size_t)pb + k) * C::V4;
+#pragma unroll
+      for (int v = 0; v < C::VPL; ++v) mine[v * C::LPR + gl] = acc[v];
+      __threadfence();                                     // partial visible before the ticket is taken
+    }
+    __syncwarp();
+    int old = 0;
+    if (multi && gl == 0) old = atomicAdd(p.tickets + pb, 1);
+    old = __shfl_sync(0xffffffffu, old, 0, C::LPR);
+    if (multi) {
+      do_epilogue = old == nseg - 1;                       // the last segment to arrive finishes the row
+      if (do_epilogue) {
+        __threadfence();
+#pragma unroll
+        for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kk = 0; kk < nseg; ++kk) {                // segment order: deterministic
+          const float4* part = p.partial + ((size_t)pb + kk) * C::V4;
+#pragma unroll
+          for (int v = 0; v < C::VPL; ++v) acc[v] = add4(acc[v], __ldcg(part + v * C::LPR + gl));
+        }
+        if (gl == 0) p.tickets[pb] = 0;                    // ready for the next launch
+      }
+    }
+  }
+  spmm_epilogue<C, NOISE>(p, row, do_epilogue, acc, gl);
 }
 
 // resident CTAs per SM the register allocation is held to: 4 (<= 64 registers) measured best at d <= 64
@@ -317,8 +312,7 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   // fully unrolled 16-entry chunks, packed FFMA2 accumulation
   constexpr int LPR = default_lpr(D);
   using C = RowCfg<D, LPR>;
-  const long long short_rows = (long long)p.n_rows - p.n_long;
-  const long long blocks = p.n_long + (short_rows + C::RPB - 1) / C::RPB;
+  const long long blocks = ((long long)p.n_v + C::RPB - 1) / C::RPB;
   if (blocks <= 0) return AGCF_OK;
   if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
   if (p.noise != nullptr)
@@ -412,25 +406,27 @@ __global__ void __launch_bounds__(256) concat_rows_kernel(const float4* __restri
 
 using namespace agcf;
 
-extern "C" int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val,
+extern "C" int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int32_t n_vrows,
+                                 const int32_t* col, const float* val, float* partial, int32_t* tickets,
                                  const float* X, float* Y, const float* addend,
                                  const float* acc_in, float* acc_out, float acc_div,
                                  const float* noise, float eps,
-                                 const int32_t* row_order, int32_t n_long,
                                  const uint32_t* row_mask, const uint32_t* col_mask,
                                  void* const* peer_Y_host, void* const* peer_acc_host, int32_t n_peers,
                                  void* mc_Y, void* mc_acc,
-                                 int32_t n_rows, int32_t d, agcf_stream_t stream) {
+                                 int32_t d, agcf_stream_t stream) {
   if (n_peers < 0 || n_peers > AGCF_MAX_PEERS) return AGCF_EINVAL;
-  if (!rowptr || !col || !val || !X || n_rows < 0 || (Y == nullptr && acc_out == nullptr)) return AGCF_EINVAL;
+  if (!vrows || !vpart || !col || !val || !partial || !tickets || !X || n_vrows < 0 || (Y == nullptr && acc_out == nullptr)) return AGCF_EINVAL;
   if (!supported_row_d(d)) return AGCF_EUNSUPPORTED;
-  if (n_long < 0 || n_long > n_rows || (n_long > 0 && row_order == nullptr)) return AGCF_EINVAL;
+  if (!aligned16(vrows) || !aligned16(partial)) return AGCF_EINVAL;
   if (!aligned16(X) || !aligned16(Y) || !aligned16(addend) || !aligned16(acc_in) || !aligned16(acc_out) || !aligned16(noise))
     return AGCF_EINVAL;
   if (X == Y || X == acc_out) return AGCF_EINVAL;        // rows of X are read by other CTAs
   if (acc_div == 0.f) return AGCF_EINVAL;
   SpmmParams p;
-  p.rowptr = rowptr; p.col = col; p.val = val;
+  p.vrows = reinterpret_cast<const int4*>(vrows); p.vpart = vpart; p.n_v = n_vrows;
+  p.partial = reinterpret_cast<float4*>(partial); p.tickets = tickets;
+  p.col = col; p.val = val;
   p.X = reinterpret_cast<const float4*>(X);
   p.Y = reinterpret_cast<float4*>(Y);
   p.addend = reinterpret_cast<const float4*>(addend);
@@ -439,7 +435,6 @@ extern "C" int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, cons
   p.acc_div = acc_div;
   p.noise = reinterpret_cast<const float4*>(noise);
   p.eps = eps;
-  p.row_order = row_order; p.n_long = n_long; p.n_rows = n_rows;
   p.row_mask = row_mask; p.col_mask = col_mask;
   if (!aligned16(mc_Y) || !aligned16(mc_acc)) return AGCF_EINVAL;
   p.mc_Y = Y != nullptr ? reinterpret_cast<float4*>(mc_Y) : nullptr;

@@ -112,7 +112,7 @@ class LightGCNEngine:
         f = lambda: torch.empty_like(table)
         if self.mode == "single":
             self.comm = None
-            self.g, self.E0 = graph, table
+            self.g, self.E0 = graph.planned_for(self.d), table
             self.r0, self.r1 = 0, self.N
             self.F = f()
             self.fw = [f(), f()] if self.L > 1 else []
@@ -121,7 +121,7 @@ class LightGCNEngine:
             c0, c1 = dshard_columns(self.d_full, comm.world, comm.rank)
             self.d = c1 - c0
             self.col0, self.col1 = c0, c1
-            self.g = graph
+            self.g = graph.planned_for(self.d)                         # narrow slices want short segments (graph.py)
             self.r0, self.r1 = 0, self.N
             self.E0 = table[:, c0:c1].contiguous()
             table = self.E0                      # every per-step table below has the slice's shape

@@ -18,16 +18,25 @@ import torch
 
 from . import _lib
 
-LONG_ROW_THRESHOLD = int(os.environ.get("ARLIB_B200_LONG_ROW", "256"))
+# Every row is processed as segments of at most `segment` non-zeros (the unit of work of the SpMM kernel), so
+# that no row is a long pole: a hub with thousands of non-zeros becomes dozens of independent work items.
+# A lane group needs ~1.5 us per 16 non-zeros, a short launch cannot hide a long segment, and every extra
+# segment costs a partial-sum round trip: measured on B200 (profiles/), 256 is best when a launch covers
+# >= 1.5 M non-zeros (41 us vs 49 us with 64), 64 when a rank owns a fraction of the graph (16.5 us vs 24.7 us
+# for a quarter) or the rows are narrow column slices.
+SEGMENT_ENV = os.environ.get("ARLIB_B200_SEGMENT")
 
 
-def _plan_rows(indptr: np.ndarray):
-    """row_order = rows by degree descending (stable); n_long = #rows above the
-    long-row threshold (those get a whole CTA in the SpMM kernel)."""
-    deg = np.diff(indptr)
-    order = np.argsort(-deg, kind="stable").astype(np.int32)
-    n_long = int(np.count_nonzero(deg > LONG_ROW_THRESHOLD))
-    return order, n_long
+def default_segment(local_nnz, d=64):
+    if SEGMENT_ENV:
+        return int(SEGMENT_ENV)
+    if d <= 32:
+        return 64
+    if local_nnz >= 1_500_000:
+        return 256
+    if local_nnz >= 600_000:
+        return 128
+    return 64
 
 
 def balanced_row_ranges(indptr, world):
@@ -45,39 +54,71 @@ def balanced_row_ranges(indptr, world):
 
 
 class DeviceGraph:
-    """CSR (rowptr, col, val) on the device + SpMM plan.  Immutable after build."""
+    """CSR (rowptr, col, val) on the device + the work plan of the SpMM kernel.  Immutable after build.
 
-    def __init__(self, rowptr, col, val, n_rows, row_order, n_long):
+    Plan ("virtual rows"): row r with deg(r) non-zeros is cut into nseg = max(1, ceil(deg / segment))
+    segments; every segment is one work item ``vrows[v] = (start, len, row, k | nseg << 16)`` (start indexes
+    col / val), items are sorted by length descending so that the lane groups of a warp walk equally long
+    segments.  Rows with several segments own ``nseg`` consecutive slots of the partial-sum scratch starting
+    at ``vpart[v]``; the segment that finishes last (a ticket per row) adds the partials in segment order and
+    runs the epilogue -- deterministic, no floating-point atomics."""
+
+    def __init__(self, rowptr, col, val, n_rows, r0=0, r1=None, segment=None):
         self.rowptr, self.col, self.val = rowptr, col, val
+        self._segment_arg = segment
         self.n_rows = int(n_rows)                    # global row count (= rows of X / Y)
         self.nnz = int(col.numel())
-        self.row_order, self.n_long = row_order, int(n_long)
-        self.n_local_rows = int(row_order.numel())   # rows this graph computes (all, or one rank's partition)
+        self.r0 = int(r0)
+        self.r1 = self.n_rows if r1 is None else int(r1)
+        self.n_local_rows = self.r1 - self.r0        # rows this graph computes (all, or one rank's partition)
         self._coo_idx = None
+        self._scratch = {}
         self._build_plan()
 
     def _build_plan(self):
-        """Slot-ordered copy of the CSR for the SpMM kernel: rows physically permuted into
-        processing order (degree descending), so a task's rowptr / col / val reads are
-        contiguous and independent of the row-id lookup (no dependent-load chain)."""
-        order = self.row_order.long()
-        deg = (self.rowptr[1:] - self.rowptr[:-1]).long()
-        pdeg = deg[order]
-        prowptr = torch.zeros(self.n_local_rows + 1, dtype=torch.int64, device=self.device)
-        prowptr[1:] = torch.cumsum(pdeg, 0)
-        # source position of every nnz in slot order: start of its row + offset inside the row
-        starts = self.rowptr[:-1].long()[order]
-        local_nnz = int(prowptr[-1])
-        src = torch.repeat_interleave(starts - prowptr[:-1], pdeg) + torch.arange(local_nnz, device=self.device)
-        self.local_nnz = local_nnz
-        self.p_rowptr = prowptr.to(torch.int32)
-        self.p_src = src
-        self.p_col = self.col[src].contiguous()
-        self.p_val = self.val[src].contiguous()
+        dev = self.device
+        rp = self.rowptr.long()
+        rows = torch.arange(self.r0, self.r1, device=dev)
+        deg = rp[rows + 1] - rp[rows]
+        SEGMENT = self.segment = int(self._segment_arg) if self._segment_arg else default_segment(int(deg.sum()))
+        if SEGMENT < 16 or SEGMENT > 4096:
+            raise ValueError("segment length must be in [16, 4096]")
+        nseg = torch.clamp((deg + SEGMENT - 1) // SEGMENT, min=1)
+        if int(nseg.max()) >= 1 << 15 if nseg.numel() else False:
+            raise ValueError("a row has more than %d non-zeros" % (SEGMENT << 15))
+        n_v = int(nseg.sum())
+        v_row = torch.repeat_interleave(rows, nseg)                       # real row of every work item
+        first = torch.cumsum(nseg, 0) - nseg                              # first item of each row
+        v_k = torch.arange(n_v, device=dev) - torch.repeat_interleave(first, nseg)
+        v_nseg = torch.repeat_interleave(nseg, nseg)
+        v_deg = torch.repeat_interleave(deg, nseg)
+        v_start = rp[v_row] + v_k * SEGMENT
+        v_len = torch.clamp(v_deg - v_k * SEGMENT, max=SEGMENT)
+        # partial-sum slots: rows with nseg > 1 get nseg consecutive slots
+        multi = nseg > 1
+        pbase_row = torch.cumsum(torch.where(multi, nseg, torch.zeros_like(nseg)), 0) - torch.where(multi, nseg, torch.zeros_like(nseg))
+        v_part = torch.repeat_interleave(pbase_row, nseg)
+        self.n_partial = int(nseg[multi].sum()) if bool(multi.any()) else 0
+        order = torch.argsort(v_len, descending=True, stable=True)
+        vr = torch.stack([v_start, v_len, v_row, v_k | (v_nseg << 16)], 1)[order]
+        self.vrows = vr.to(torch.int32).contiguous()                      # [n_v, 4]
+        self.vpart = v_part[order].to(torch.int32).contiguous()
+        self.n_vrows = n_v
+        self.local_nnz = int(deg.sum())
+        self.max_segments = int(nseg.max()) if nseg.numel() else 0
+        self.tickets = torch.zeros(max(self.n_partial, 1), dtype=torch.int32, device=dev)
+
+    def partial_scratch(self, d):
+        """[n_partial, d] fp32 scratch for the partial sums of multi-segment rows (one per width, reused by
+        every launch on this graph: launches on one graph must be stream-ordered)."""
+        t = self._scratch.get(d)
+        if t is None:
+            t = torch.empty((max(self.n_partial, 1), d), dtype=torch.float32, device=self.device)
+            self._scratch[d] = t
+        return t
 
     def refresh_plan_values(self):
-        """re-gather the slot-ordered values after ``val`` was modified in place"""
-        self.p_val = self.val[self.p_src].contiguous()
+        """the plan indexes ``val`` in place: nothing to refresh after ``val`` was modified"""
 
     @property
     def device(self):
@@ -89,13 +130,20 @@ class DeviceGraph:
         balance by non-zeros, not by rows)."""
         return balanced_row_ranges(self.rowptr.cpu().numpy(), world)
 
-    def partition(self, r0, r1):
+    def partition(self, r0, r1, segment=None):
         """Graph that COMPUTES only rows [r0, r1) (one rank of the row-partitioned
         multi-GPU path); X / Y keep global row ids, col ids are global."""
-        deg = (self.rowptr[r0 + 1:r1 + 1] - self.rowptr[r0:r1]).cpu().numpy()
-        order = (np.argsort(-deg, kind="stable") + r0).astype(np.int32)
-        n_long = int(np.count_nonzero(deg > LONG_ROW_THRESHOLD))
-        return DeviceGraph(self.rowptr, self.col, self.val, self.n_rows, torch.from_numpy(order).to(self.device), n_long)
+        return DeviceGraph(self.rowptr, self.col, self.val, self.n_rows, r0, r1, segment)
+
+    def replan(self, segment):
+        """The same graph (shared CSR arrays) with another segment length."""
+        if segment == self.segment:
+            return self
+        return DeviceGraph(self.rowptr, self.col, self.val, self.n_rows, self.r0, self.r1, segment)
+
+    def planned_for(self, d):
+        """The plan whose segment length suits tables of width d (narrow column slices want short segments)."""
+        return self.replan(default_segment(self.local_nnz, d))
 
     # ---------------------------------------------------------------- builders
     @classmethod
@@ -104,7 +152,6 @@ class DeviceGraph:
             raise ValueError("adjacency must be square")
         if csr.nnz >= 2 ** 31 or csr.shape[0] >= 2 ** 31:
             raise ValueError("graph exceeds int32 indexing")
-        order, n_long = _plan_rows(csr.indptr)
         dev = torch.device(device)
         rowptr = torch.from_numpy(csr.indptr.astype(np.int32)).to(dev)
         col = torch.from_numpy(csr.indices.astype(np.int32)).to(dev)
@@ -112,7 +159,7 @@ class DeviceGraph:
             val = torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float32)).to(dev)
         else:
             val = values
-        return cls(rowptr, col, val, csr.shape[0], torch.from_numpy(order).to(dev), n_long)
+        return cls(rowptr, col, val, csr.shape[0])
 
     @classmethod
     def from_scipy(cls, mat, device="cuda"):
@@ -168,9 +215,7 @@ class DeviceGraph:
         counts = torch.bincount(idx[0], minlength=n)
         rowptr = torch.zeros(n + 1, dtype=torch.int64, device=t.device)
         rowptr[1:] = torch.cumsum(counts, 0)
-        order, n_long = _plan_rows(rowptr.cpu().numpy())
-        return cls(rowptr.to(torch.int32), idx[1].to(torch.int32).contiguous(), t.values().float().contiguous(),
-                   n, torch.from_numpy(order).to(t.device), n_long)
+        return cls(rowptr.to(torch.int32), idx[1].to(torch.int32).contiguous(), t.values().float().contiguous(), n)
 
     # ------------------------------------------------------------------ views
     def coo_indices(self):

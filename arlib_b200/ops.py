@@ -48,10 +48,11 @@ def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_
             raise ValueError("operand shape mismatch")
     py, n1 = _lib.ptr_array(peer_Y)
     pa, n2 = _lib.ptr_array(peer_acc)
-    _lib.check(lib.agcf_spmm_csr_f32(g.p_rowptr.data_ptr(), g.p_col.data_ptr(), g.p_val.data_ptr(), X.data_ptr(), _p(Y),
+    _lib.check(lib.agcf_spmm_csr_f32(g.vrows.data_ptr(), g.vpart.data_ptr(), g.n_vrows, g.col.data_ptr(), g.val.data_ptr(),
+                                     g.partial_scratch(d).data_ptr(), g.tickets.data_ptr(), X.data_ptr(), _p(Y),
                                      _p(addend), _p(acc_in), _p(acc_out), float(acc_div), _p(noise), float(eps),
-                                     g.row_order.data_ptr(), g.n_long, _p(row_mask), _p(col_mask), py, pa, max(n1, n2),
-                                     mc_Y or None, mc_acc or None, g.n_local_rows, d, _lib.stream_ptr()), "agcf_spmm_csr_f32")
+                                     _p(row_mask), _p(col_mask), py, pa, max(n1, n2),
+                                     mc_Y or None, mc_acc or None, d, _lib.stream_ptr()), "agcf_spmm_csr_f32")
 
 
 def sddmm(g: DeviceGraph, H, E, gval, accumulate=False):
@@ -59,7 +60,7 @@ def sddmm(g: DeviceGraph, H, E, gval, accumulate=False):
     lib = _lib.load()
     _f32(H, "H"); _f32(E, "E"); _f32(gval, "gval")
     _lib.check(lib.agcf_sddmm_csr_f32(g.rowptr.data_ptr(), g.col.data_ptr(), H.data_ptr(), E.data_ptr(), gval.data_ptr(),
-                                      1 if accumulate else 0, g.row_order.data_ptr(), g.n_local_rows, H.shape[1],
+                                      1 if accumulate else 0, None, g.n_rows, H.shape[1],
                                       _lib.stream_ptr()), "agcf_sddmm_csr_f32")
 
 

@@ -63,17 +63,23 @@ int agcf_csr_expand_rows(const int32_t* rowptr, int32_t* row_of, int32_t n_rows,
  *   if noise:      t[i,:] += sign(t[i,:]) * noise[i,:]/max(||noise[i,:]||,1e-12) * eps
  *   if Y:          Y[i,:] = t[i,:]
  *   if acc_out:    acc_out[i,:] = ((acc_in ? acc_in[i,:] : 0) + t[i,:]) / acc_div
- * row_order (nullable) is a permutation of rows giving the processing order
- * (longest rows first); n_long leading entries of it are rows handled by a whole
- * CTA.  row_mask / col_mask (nullable bitmaps, bit k of word k/32): only rows whose
- * bit is set are computed and written; rows of X whose bit is clear are known to be
- * all-zero and are not gathered (the last forward layer only needs the batch's
- * rows, the first backward layer only sees the batch's gradient rows).
- * Multi-GPU (row-partitioned tables): rowptr/col/val/row_order describe only this
- * rank's rows; peer_Y_host / peer_acc_host are HOST arrays of n_peers device pointers
- * to the other ranks' copies of Y / acc_out (peer-mapped over NVLink): the epilogue
- * stores every computed row there too -- the per-layer all-gather is fused into the
- * SpMM and overlaps it row by row.  Visibility on the peers needs a barrier after.
+ * Work plan (built once per graph by the caller; arlib_b200/graph.py is the reference builder): row i
+ * with deg non-zeros is cut into nseg = max(1, ceil(deg / S)) segments, S <= 64 recommended.  Work item
+ * v is four int32 {start, len, row, k | nseg << 16}: entries col/val[start .. start+len) of row `row`,
+ * segment k of nseg; items sorted by len descending; n_vrows items (a row without non-zeros is one
+ * item of len 0).  Rows with nseg > 1 own nseg consecutive slots of `partial` ([slots][d] floats) starting
+ * at vpart[v] (same value for all items of the row); `tickets` ([slots] int32) must be zero on entry
+ * and is zero again on exit.  Partials are added in segment order by the segment that arrives last:
+ * results are deterministic.  Launches that share partial/tickets must be stream-ordered.
+ * Rows absent from the plan are not touched (multi-GPU: a rank's plan holds its own rows only).
+ * row_mask / col_mask (nullable bitmaps, bit k of word k/32): only rows whose bit is set are computed
+ * and written; rows of X whose bit is clear are known to be all-zero and are not gathered (the last
+ * forward layer only needs the batch's rows, the first backward layer only sees the batch's gradient
+ * rows).
+ * Multi-GPU (row-partitioned tables): peer_Y_host / peer_acc_host are HOST arrays of n_peers device
+ * pointers to the other ranks' copies of Y / acc_out (peer-mapped over NVLink): the epilogue stores
+ * every computed row there too -- the per-layer all-gather is fused into the SpMM and overlaps it
+ * row by row.  Visibility on the peers needs a barrier after.
  * mc_Y / mc_acc (nullable): NVSwitch MULTICAST addresses of Y / acc_out (a multicast object bound
  * to every rank's copy): the epilogue then issues ONE multimem.st per 16 bytes and the switch
  * replicates it to all GPUs -- a rank's NVLink egress per layer is its rows once, not once per peer;
@@ -82,16 +88,16 @@ int agcf_csr_expand_rows(const int32_t* rowptr, int32_t* row_of, int32_t n_rows,
  * Replaces: torch.sparse.mm + stack + mean in recommender/LightGCN.py:230-240,
  * the noise lines of recommender/SimGCL.py:202-206 / XSimGCL.py:211-215, and the
  * autograd of those (transposed SpMM + mean backward). */
-int agcf_spmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* val,
+int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int32_t n_vrows,
+                      const int32_t* col, const float* val, float* partial, int32_t* tickets,
                       const float* X, float* Y,
                       const float* addend,
                       const float* acc_in, float* acc_out, float acc_div,
                       const float* noise, float eps,
-                      const int32_t* row_order, int32_t n_long,
                       const uint32_t* row_mask, const uint32_t* col_mask,
                       void* const* peer_Y_host, void* const* peer_acc_host, int32_t n_peers,
                       void* mc_Y, void* mc_acc,
-                      int32_t n_rows, int32_t d, agcf_stream_t stream);
+                      int32_t d, agcf_stream_t stream);
 
 /* gval[p] (+)= <H[i,:], E[col[p],:]> for p in row i (accumulate != 0 adds).
  * Replaces: autograd of torch.sparse.mm w.r.t. the sparse operand, restricted to

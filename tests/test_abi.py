@@ -29,7 +29,7 @@ def test_version_and_error_strings():
     assert lib.agcf_strerror(0) == b"ok"
     assert b"invalid" in lib.agcf_strerror(-1)
     # argument validation happens before any CUDA call, so it is checkable without a GPU
-    assert lib.agcf_spmm_csr_f32(None, None, None, None, None, None, None, None, 1.0, None, 0.0, None, 0, None, None, None, None, 0, None, None, 0, 64, None) == -1
+    assert lib.agcf_spmm_csr_f32(None, None, 0, None, None, None, None, None, None, None, None, None, 1.0, None, 0.0, None, None, None, None, 0, None, None, 64, None) == -1
     assert lib.agcf_bpr_ws_bytes(2048) > 0
     assert lib.agcf_score_topk_ws_bytes(10, 100, 48, 5) == -2      # unsupported d
     assert lib.agcf_score_topk_ws_bytes(10, 100, 64, 5) > 0

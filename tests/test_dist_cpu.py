@@ -1,5 +1,5 @@
 """World-size-2 gloo test (CPU) of the multi-GPU HOST logic: nnz-balanced row
-ranges, per-rank slot-ordered CSR plans, and the gather layout (every rank's rows
+ranges, per-rank segmented work plans, and the gather layout (every rank's rows
 land at their global offsets).  The per-rank arithmetic here is the numpy oracle --
 the CUDA kernels are covered by tests/test_gpu_dist.py on real GPUs."""
 import os
@@ -33,12 +33,18 @@ def _worker(rank, world, port, out):
     gp = g.partition(r0, r1)
     torch.manual_seed(0)
     X = torch.randn(U + I, d)
-    # this rank's rows through its slot-ordered plan
+    # this rank's rows through its work plan (segments of rows; partial sums added per row)
     mine = torch.zeros(U + I, d)
-    for s in range(gp.n_local_rows):
-        r = int(gp.row_order[s]); a, e = int(gp.p_rowptr[s]), int(gp.p_rowptr[s + 1])
-        assert r0 <= r < r1
-        mine[r] = (gp.p_val[a:e, None] * X[gp.p_col[a:e].long()]).sum(0)
+    covered = torch.zeros(U + I, dtype=torch.int64)
+    lens = gp.vrows[:, 1]
+    assert bool((lens[:-1] >= lens[1:]).all()) and int(lens.max()) <= 64          # sorted, bounded work items
+    for v in range(gp.n_vrows):
+        a, n, r, seg = (int(x) for x in gp.vrows[v])
+        assert r0 <= r < r1 and 0 <= (seg & 0xffff) < (seg >> 16)
+        mine[r] += (gp.val[a:a + n, None] * X[gp.col[a:a + n].long()]).sum(0)
+        covered[r] += n
+    deg = (g.rowptr[1:] - g.rowptr[:-1]).long()
+    assert torch.equal(covered[r0:r1], deg[r0:r1]) and int(covered.sum()) == int(deg[r0:r1].sum())
     # "all-gather": every rank contributes its row range at the global offsets
     parts = [torch.zeros(U + I, d) for _ in range(world)]
     dist.all_gather(parts, mine)

@@ -69,7 +69,7 @@ def test_spmm_matches_oracle(d, hub):
     norm = port.normalize_graph_mat(adj)
     g = DeviceGraph.from_dataloader_adj(adj, _dev())
     if hub:
-        assert g.n_long >= 2
+        assert g.max_segments >= 10 and g.n_partial > 20       # hub rows are cut into many segments
     X = torch.randn(U + I, d)
     ref = torch.sparse.mm(port.to_torch_coo(norm), X)
     Xd = X.to(_dev())

@@ -24,25 +24,23 @@ buf = (ctypes.c_ulonglong * (6 * 16384))()
 lib.agcf_debug_spmm_trace.argtypes = [ctypes.c_void_p]
 assert lib.agcf_debug_spmm_trace(buf) == 0
 t = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 6).astype(np.int64)
-deg = np.diff(g.p_rowptr.cpu().numpy())
+lens = g.vrows[:, 1].cpu().numpy()
 rpb = 8 * (32 // min(d // 4, 32))
-n_cta = g.n_long + (N - g.n_long + rpb - 1) // rpb
+n_cta = (g.n_vrows + rpb - 1) // rpb
 t = t[:min(n_cta, 16384)]
 t0 = t[:, 0].min()
 start, end = (t[:, 0] - t0) / 1e3, (t[:, 3] - t0) / 1e3
 meta, accd = (t[:, 1] - t[:, 0]) / 1e3, (t[:, 2] - t[:, 1]) / 1e3
 epi = (t[:, 3] - t[:, 2]) / 1e3
-print("%s a=%s d=%d: %d CTAs (%d long), makespan %.1f us" % (name, alpha, d, n_cta, g.n_long, end.max()))
+print("%s a=%s d=%d: %d CTAs (%d work items, longest row %d segments), makespan %.1f us" % (name, alpha, d, n_cta, g.n_vrows, g.max_segments, end.max()))
 dur = end - start
-print("long-row CTAs: dur mean %.1f max %.1f us, last end %.1f us" % (dur[:g.n_long].mean(), dur[:g.n_long].max(), end[:g.n_long].max()))
-print("short CTAs   : dur mean %.1f max %.1f us" % (dur[g.n_long:].mean(), dur[g.n_long:].max()))
-for lo in range(0, len(t), max(1, len(t) // 24)):
-    hi = min(len(t), lo + max(1, len(t) // 24))
-    s0 = g.n_long + max(0, lo - g.n_long) * rpb
-    sh = slice(max(lo, g.n_long), hi)
-    ph = "  warp0: meta %4.2f gather %4.2f epilogue %4.2f us" % (meta[sh].mean(), accd[sh].mean(), epi[sh].mean()) if hi > g.n_long else ""
-    print("CTA %5d-%5d  first-row deg %5d  start %6.1f-%6.1f  dur mean %5.1f max %5.1f  end max %6.1f%s"
-          % (lo, hi, int(deg[min(lo if lo < g.n_long else s0, len(deg) - 1)]), start[lo:hi].min(), start[lo:hi].max(), dur[lo:hi].mean(), dur[lo:hi].max(), end[lo:hi].max(), ph))
+print("CTAs: dur mean %.1f max %.1f us" % (dur.mean(), dur.max()))
+step = max(1, len(t) // 24)
+for lo in range(0, len(t), step):
+    hi = min(len(t), lo + step)
+    print("CTA %5d-%5d  first item len %3d  start %6.1f-%6.1f  dur mean %5.1f max %5.1f  end max %6.1f  warp0: meta %4.2f gather %4.2f epilogue %4.2f us"
+          % (lo, hi, int(lens[min(lo * rpb, len(lens) - 1)]), start[lo:hi].min(), start[lo:hi].max(), dur[lo:hi].mean(), dur[lo:hi].max(), end[lo:hi].max(),
+             meta[lo:hi].mean(), accd[lo:hi].mean(), epi[lo:hi].mean()))
 # concurrency over time
 ev = np.concatenate([np.stack([start, np.ones_like(start)], 1), np.stack([end, -np.ones_like(end)], 1)])
 ev = ev[np.argsort(ev[:, 0])]

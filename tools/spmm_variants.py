@@ -42,12 +42,11 @@ if part:
     for r in range(w):
         gp = g.partition(b[r], b[r + 1])
         tp = timeit(lambda: ops.spmm(gp, X, Y=Y, acc_in=X, acc_out=A))
-        deg = np.diff(gp.p_rowptr.cpu().numpy())
-        print("partition %d/%d rows [%d,%d) nnz %d n_long %d max deg %d: %.1f us" % (r, w, b[r], b[r + 1], gp.local_nnz, gp.n_long, deg.max(), tp))
+        print("partition %d/%d rows [%d,%d) nnz %d work items %d max segments %d: %.1f us" % (r, w, b[r], b[r + 1], gp.local_nnz, gp.n_vrows, gp.max_segments, tp))
     sys.exit(0)
 t_full = timeit(lambda: ops.spmm(g, X, Y=Y, acc_in=X, acc_out=A))
 t_row = timeit(lambda: ops.spmm(g, X, acc_in=A, acc_out=A, row_mask=mask))
 t_col = timeit(lambda: ops.spmm(g, Xs, Y=Y, addend=Xs, col_mask=mask))
 live = np.diff(g.rowptr.cpu().numpy())[nodes].sum() / g.nnz
-print("d=%d variant %s %s a=%s: full %.1f us  row-masked %.1f us  col-masked %.1f us  (live nnz %.3f, n_long %d)"
-      % (d, os.environ.get("AGCF_SPMM_VARIANT", "0"), name, alpha, t_full, t_row, t_col, live, g.n_long))
+print("d=%d variant %s %s a=%s: full %.1f us  row-masked %.1f us  col-masked %.1f us  (live nnz %.3f, %d work items)"
+      % (d, os.environ.get("AGCF_SPMM_VARIANT", "0"), name, alpha, t_full, t_row, t_col, live, g.n_vrows))
