@@ -18,25 +18,30 @@ import torch
 
 from . import _lib
 
-# Every row is processed as segments of at most `segment` non-zeros (the unit of work of the SpMM kernel), so
-# that no row is a long pole: a hub with thousands of non-zeros becomes dozens of independent work items.
-# A lane group needs ~1.5 us per 16 non-zeros, a short launch cannot hide a long segment, and every extra
-# segment costs a partial-sum round trip: measured on B200 (profiles/), 256 is best when a launch covers
-# >= 1.5 M non-zeros (41 us vs 49 us with 64), 64 when a rank owns a fraction of the graph (16.5 us vs 24.7 us
-# for a quarter) or the rows are narrow column slices.
+# Rows with more than `split_above` non-zeros are processed as segments of at most `segment` non-zeros (the unit
+# of work of the SpMM kernel), so that no row is a long pole: a hub with thousands of non-zeros becomes dozens
+# of independent work items.  A lane group needs ~1.5 us per 16 non-zeros, a short launch cannot hide a long
+# work item, and every segment costs a partial-sum round trip: measured on B200 (profiles/r1_summary.md), when a
+# launch covers >= 1.5 M non-zeros segments of 256 are best (Gowalla shape: 43 us at alpha = 0.5 AND at alpha = 0.8,
+# where an uncut 13 689-nnz row took 91 us); when a rank owns a fraction of the graph, or the rows are narrow column
+# slices, 64 is (quarter partition: 16.5 us vs 24.7 us; d = 8 slices: 27 us vs 55 us).
 SEGMENT_ENV = os.environ.get("ARLIB_B200_SEGMENT")
+SPLIT_ENV = os.environ.get("ARLIB_B200_SPLIT_ABOVE")
 
 
 def default_segment(local_nnz, d=64):
-    if SEGMENT_ENV:
-        return int(SEGMENT_ENV)
+    """(split_above, segment): rows with more than split_above non-zeros are cut into segments of `segment`."""
     if d <= 32:
-        return 64
-    if local_nnz >= 1_500_000:
-        return 256
-    if local_nnz >= 600_000:
-        return 128
-    return 64
+        seg = 64
+    elif local_nnz >= 1_500_000:
+        seg = 256
+    elif local_nnz >= 600_000:
+        seg = 128
+    else:
+        seg = 64
+    if SEGMENT_ENV:
+        seg = int(SEGMENT_ENV)
+    return (int(SPLIT_ENV) if SPLIT_ENV else seg), seg
 
 
 def balanced_row_ranges(indptr, world):
@@ -80,10 +85,11 @@ class DeviceGraph:
         rp = self.rowptr.long()
         rows = torch.arange(self.r0, self.r1, device=dev)
         deg = rp[rows + 1] - rp[rows]
-        SEGMENT = self.segment = int(self._segment_arg) if self._segment_arg else default_segment(int(deg.sum()))
-        if SEGMENT < 16 or SEGMENT > 4096:
-            raise ValueError("segment length must be in [16, 4096]")
-        nseg = torch.clamp((deg + SEGMENT - 1) // SEGMENT, min=1)
+        split, SEGMENT = self._segment_arg if self._segment_arg else default_segment(int(deg.sum()))
+        self.split_above, self.segment = int(split), int(SEGMENT)
+        if SEGMENT < 16 or SEGMENT > 4096 or split < SEGMENT:
+            raise ValueError("segment length must be in [16, 4096] and split_above >= segment")
+        nseg = torch.where(deg > split, (deg + SEGMENT - 1) // SEGMENT, torch.ones_like(deg))
         if int(nseg.max()) >= 1 << 15 if nseg.numel() else False:
             raise ValueError("a row has more than %d non-zeros" % (SEGMENT << 15))
         n_v = int(nseg.sum())
@@ -93,7 +99,7 @@ class DeviceGraph:
         v_nseg = torch.repeat_interleave(nseg, nseg)
         v_deg = torch.repeat_interleave(deg, nseg)
         v_start = rp[v_row] + v_k * SEGMENT
-        v_len = torch.clamp(v_deg - v_k * SEGMENT, max=SEGMENT)
+        v_len = torch.where(v_nseg > 1, torch.clamp(v_deg - v_k * SEGMENT, max=SEGMENT), v_deg)
         # partial-sum slots: rows with nseg > 1 get nseg consecutive slots
         multi = nseg > 1
         pbase_row = torch.cumsum(torch.where(multi, nseg, torch.zeros_like(nseg)), 0) - torch.where(multi, nseg, torch.zeros_like(nseg))
@@ -135,15 +141,15 @@ class DeviceGraph:
         multi-GPU path); X / Y keep global row ids, col ids are global."""
         return DeviceGraph(self.rowptr, self.col, self.val, self.n_rows, r0, r1, segment)
 
-    def replan(self, segment):
-        """The same graph (shared CSR arrays) with another segment length."""
-        if segment == self.segment:
+    def replan(self, split_above, segment):
+        """The same graph (shared CSR arrays) with another split threshold / segment length."""
+        if (split_above, segment) == (self.split_above, self.segment):
             return self
-        return DeviceGraph(self.rowptr, self.col, self.val, self.n_rows, self.r0, self.r1, segment)
+        return DeviceGraph(self.rowptr, self.col, self.val, self.n_rows, self.r0, self.r1, (split_above, segment))
 
     def planned_for(self, d):
-        """The plan whose segment length suits tables of width d (narrow column slices want short segments)."""
-        return self.replan(default_segment(self.local_nnz, d))
+        """The plan that suits tables of width d (narrow column slices want every row in short segments)."""
+        return self.replan(*default_segment(self.local_nnz, d))
 
     # ---------------------------------------------------------------- builders
     @classmethod

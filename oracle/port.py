@@ -438,3 +438,47 @@ class ArrayEvalData:
     def user_rated(self, u):
         d = self.training_set_u[u]
         return list(d.keys()), list(d.values())
+
+
+# ------------------------------------------------------------------ AttackMetric
+def attack_metric(predict_fn, users, target_items, top):
+    """Restatement of AttackMetric.precision / hitRate / recall / NDCG (reference util/metrics.py:135-207):
+    per user ``np.argsort(-score)[:k]`` of the UN-masked scores, then the four accumulations exactly as written
+    there.  ``predict_fn(user) -> np.ndarray[I]``.  Returns {"precision": [...], "hitRate": [...], ...}."""
+    n = len(top)
+    lists = {}
+    for u in users:
+        score = predict_fn(u)
+        order = np.argsort(-score, kind="stable")          # reference: default quicksort; ties unspecified there
+        lists[u] = [order[:k] for k in top]
+    tset = set(target_items)
+    prec_hit, prec_tot = [0] * n, [0] * n
+    hr_hit, hr_tot = [0.0] * n, [0] * n
+    rec_hit, rec_tot = [0] * n, [0] * n
+    nd_hit, nd_tot = [0.0] * n, [0.0] * n
+    for u in users:
+        result = lists[u]
+        for i, k in enumerate(top):
+            prec_tot[i] += k                                                   # :144
+            hr_tot[i] += 1                                                     # :162
+            rec_tot[i] += len(target_items)                                    # :178
+            idcg = 0.0
+            for s in range(k):                                                 # :196-199
+                if s < len(target_items):
+                    idcg += 1 / np.log2(2 + s)
+            nd_tot[i] += idcg
+        for j in target_items:                                                 # :145-148, :179-182
+            for i in range(n):
+                if j in result[i]:
+                    prec_hit[i] += 1
+                    rec_hit[i] += 1
+        for i in range(n):                                                     # :163-164
+            hr_hit[i] += int(len(tset & set(result[i].tolist())) > 0) / len(target_items)
+        for i, r in enumerate(result):                                         # :200-203
+            for rank, j in enumerate(r):
+                if j in tset:
+                    nd_hit[i] += 1 / np.log2(2 + rank)
+    return {"precision": [prec_hit[i] / prec_tot[i] for i in range(n)],
+            "hitRate": [hr_hit[i] / hr_tot[i] for i in range(n)],
+            "recall": [rec_hit[i] / rec_tot[i] for i in range(n)],
+            "NDCG": [nd_hit[i] / nd_tot[i] for i in range(n)]}

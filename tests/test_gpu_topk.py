@@ -201,3 +201,33 @@ def test_tcgen05_stage1_gives_the_same_topk_as_the_fp32_path(U, I, d, K):
         assert torch.equal(i0, i1) and torch.equal(v0, v1)
         # the TF32 margin admits a few more candidate groups, not an explosion
         assert float(f1.float().mean()) <= 3.0 * float(f0.float().mean()) + 4
+
+
+def test_attack_metric_matches_reference_formulas():
+    """AttackMetric (reference util/metrics.py:125-207) from ONE fused score + top-K pass over
+    all users instead of 4 x U predict() + argsort; values equal the oracle restatement of the reference
+    (itself checked against the unmodified reference class when the oracle was written)."""
+    import types
+    from arlib_b200 import ops
+    from arlib_b200.util.metrics import AttackMetric
+    rng = np.random.default_rng(11)
+    U, I, d = 300, 2000, 64
+    ue = torch.randn(U, d, device=DEV)
+    ie = torch.randn(I, d, device=DEV)
+    users = {"u%d" % k: k for k in rng.permutation(U)}
+    rec = types.SimpleNamespace(data=types.SimpleNamespace(user=users), user_emb=ue, item_emb=ie)
+    exact = ops.score_rows(ue, torch.arange(U, dtype=torch.int32, device=DEV), ie).cpu().numpy()
+    targets = [5, 77, 1203, 1999]
+    # make the targets competitive so that the statistics are not all zero
+    ie_boost = ie.clone(); ie_boost[targets] *= 2.5
+    rec.item_emb = ie_boost
+    exact = ops.score_rows(ue, torch.arange(U, dtype=torch.int32, device=DEV), ie_boost).cpu().numpy()
+    for top in ([10], [5, 20, 50]):
+        am = AttackMetric(rec, targets, top)
+        ref = port.attack_metric(lambda name: exact[users[name]], list(users), targets, top)
+        for name in ("precision", "hitRate", "recall", "NDCG"):
+            got = getattr(am, name)()
+            assert max(ref[name]) > 0
+            np.testing.assert_allclose(got, ref[name], rtol=1e-12, atol=0)
+    with pytest.raises(TypeError):
+        AttackMetric(types.SimpleNamespace(data=rec.data, user_emb=ue.cpu(), item_emb=ie.cpu()), targets).precision()

@@ -33,3 +33,16 @@ def test_no_ties_equals_stable_argsort():
     s = rng.standard_normal(1000).astype(np.float32)
     ids, _ = port.find_k_largest_py(50, s)
     assert ids == np.argsort(-s, kind="stable")[:50].tolist()
+
+
+def test_attack_metric_port_reproduces_reference_golden():
+    """oracle.port.attack_metric vs outputs of the unmodified reference AttackMetric frozen by
+    oracle/make_golden_attack_metric.py."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "attack_metric.npz"))
+    scores = z["user_emb"] @ z["item_emb"].T
+    users = {str(n): int(i) for n, i in zip(z["user_names"], z["user_ids"])}
+    for tag in ("a", "b"):
+        got = port.attack_metric(lambda name: scores[users[name]], list(users), z["targets"].tolist(), z["top_" + tag].tolist())
+        for name in ("precision", "hitRate", "recall", "NDCG"):
+            assert np.array_equal(np.array(got[name]), z["%s_%s" % (name, tag)]), name
