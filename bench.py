@@ -33,6 +33,7 @@ WORKLOADS = {
     "amazon-book": (52643, 91599, 2984108, 3, 128, 2048),
 }
 LR, REG, TOPK = 0.005, 1e-4, 50
+L2_GATHER_PEAK_GBS = 18400.0      # measured on B200 this round (profiles/r1_l2_gather_peak.txt)
 
 
 def log(*a):
@@ -291,7 +292,8 @@ def run_ours(args):
     def timed_spmm(*a, **k):
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(); orig(*a, **k); a1.record()
-        spmm_ms.append((a0, a1))
+        kind = "row_masked" if k.get("row_mask") is not None else ("col_masked" if k.get("col_mask") is not None else "full")
+        spmm_ms.append((kind, a0, a1))
 
     import arlib_b200.engine as engmod
     engmod.ops.spmm = timed_spmm
@@ -301,7 +303,12 @@ def run_ours(args):
     finally:
         engmod.ops.spmm = orig
     torch.cuda.synchronize()
-    spmm_avg_ms = float(np.mean([a.elapsed_time(b) for a, b in spmm_ms]))
+    by_kind = {}
+    for kind, a, b_ in spmm_ms:
+        by_kind.setdefault(kind, []).append(a.elapsed_time(b_))
+    # the roofline figure is for the FULL launches (the contract bytes B_spmm are those of a full propagation);
+    # the two batch-sparse launches of a step move fewer bytes and are reported beside it
+    spmm_avg_ms = float(np.mean(by_kind["full"]))
     b_spmm, b_step = algorithmic_bytes(N, g.nnz, d, L, B)
     if eng.mode == "dshard":        # per-GPU launch: whole graph, a [N, d/P] slice of the tables
         b_spmm = g.nnz * 8 + (N + 1) * 4 + 2 * N * eng.d * 4
@@ -323,10 +330,19 @@ def run_ours(args):
     roofline = {"kernel": "spmm_csr_kernel<%d>" % eng.d, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": b_spmm, "avg_launch_ms": spmm_avg_ms,
-                "launches_per_step": 2 * L, "step_algorithmic_bytes": b_step,
+                "launches_per_step": 2 * L, "full_launches_per_step": len(by_kind["full"]) // max(1, min(K, 50)),
+                "batch_sparse_launch_ms": {k: float(np.mean(v)) for k, v in by_kind.items() if k != "full"},
+                "step_algorithmic_bytes": b_step,
                 "step_frac_of_hbm_roofline": (b_step / (ms / K * 1e-3) / 1e9) / peak,
-                "note": "table (%.1f MB) is L2-resident: the binding resource is L2->SM gather bandwidth "
-                        "(nnz*(8+4d) = %.0f MB per launch), see DESIGN.md" % (N * d * 4 / 1e6, g.nnz * (8 + 4 * d) / 1e6)}
+                "l2_gather": {"bytes_per_launch": int(eng.g.local_nnz * (8 + 4 * eng.d)),
+                              "achieved": eng.g.local_nnz * (8 + 4 * eng.d) / (spmm_avg_ms * 1e-3) / 1e9,
+                              "peak": L2_GATHER_PEAK_GBS, "unit": "GB/s",
+                              "frac": eng.g.local_nnz * (8 + 4 * eng.d) / (spmm_avg_ms * 1e-3) / 1e9 / L2_GATHER_PEAK_GBS,
+                              "peak_kind": "measured: tools/l2_gather_peak.cu, power-law 256-byte row gathers from an "
+                                           "L2-resident table (profiles/r1_l2_gather_peak.txt)"},
+                "note": "table (%.1f MB) is L2-resident and no on-chip store holds it: the binding resource is the L2->SM "
+                        "gather path (nnz*(8+4d) = %.0f MB per launch), not DRAM; see DESIGN.md 4.1"
+                        % (N * d * 4 / 1e6, g.nnz * (8 + 4 * d) / 1e6)}
 
     # ---- end to end through the public step API with HOST triples (pinned), loss read back
     tu_h = [torch.empty((3, B), dtype=torch.int32).pin_memory() for _ in range(4)]
