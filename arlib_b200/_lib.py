@@ -20,6 +20,29 @@ _ERR = {-1: "AGCF_EINVAL", -2: "AGCF_EUNSUPPORTED", -3: "AGCF_ECUDA", -4: "AGCF_
 P = c_void_p        # every device pointer / stream
 I32, I64, U64, F32 = c_int32, c_int64, c_uint64, c_float
 
+
+
+class SpmmArgs(ctypes.Structure):
+    """struct agcf_spmm_args (include/agcf.h), field for field"""
+    _fields_ = [
+        ("vrows", P), ("vpart", P), ("n_vrows", I32), ("n_vrows_dev", P),
+        ("col", P), ("val", P), ("partial", P), ("tickets", P),
+        ("X", P), ("Y", P), ("addend", P),
+        ("acc_in", P), ("acc_out", P), ("acc_div", F32),
+        ("noise", P), ("eps", F32),
+        ("row_mask", P), ("col_mask", P),
+        ("peer_Y_host", P), ("peer_acc_host", P), ("n_peers", I32),
+        ("mc_Y", P), ("mc_acc", P),
+        ("adam_p", P), ("adam_m", P), ("adam_v", P), ("adam_coefs", P),
+        ("adam_beta1", F32), ("adam_beta2", F32), ("adam_eps", F32),
+        ("zero_acc_in", I32),
+        ("d", I32),
+        ("flags", I32),
+    ]
+
+
+SPMM_PDL = 1
+
 # name -> (restype, argtypes); mirrors include/agcf.h one to one
 SIGNATURES = {
     "agcf_abi_version": (c_int32, []),
@@ -30,6 +53,9 @@ SIGNATURES = {
     "agcf_norm_adj_csr": (c_int32, [P, P, P, P, P, P, I32, I64, P]),
     "agcf_csr_expand_rows": (c_int32, [P, P, I32, I64, P]),
     "agcf_spmm_csr_f32": (c_int32, [P, P, I32, P, P, P, P, P, P, P, P, P, F32, P, F32, P, P, P, P, I32, P, P, I32, P]),
+    "agcf_spmm_csr_f32_ex": (c_int32, [ctypes.POINTER(SpmmArgs), P]),
+    "agcf_spmm_batch_worklists": (c_int32, [P, P, I32, I32, P, I32, I32, I32, I32, P, P, P, I32, P]),
+    "agcf_adam_coefs": (c_int32, [P, I32, F32, F32, F32, P, P]),
     "agcf_sddmm_csr_f32": (c_int32, [P, P, P, P, P, I32, P, I32, I32, P]),
     "agcf_concat_rows_f32": (c_int32, [P, I64, P, I64, P, I32, P]),
     "agcf_bpr_sample_epoch": (c_int32, [P, P, I32, P, P, I32, U64, U64, P, P, P, P]),

@@ -470,6 +470,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
 
 __global__ void increment_kernel(int32_t* c) { *c += 1; }
 
+// same double-precision expressions as adam_kernel's thread 0
+__global__ void adam_coefs_kernel(int32_t* step_dev, int increment, float lr, float beta1, float beta2, float* coefs) {
+  int t = *step_dev;
+  if (increment) { t += 1; *step_dev = t; }
+  t += 1;
+  const double bc1 = 1.0 - pow((double)beta1, (double)t);
+  const double bc2 = 1.0 - pow((double)beta2, (double)t);
+  coefs[0] = (float)((double)lr / bc1);
+  coefs[1] = (float)sqrt(bc2);
+}
+
 }  // namespace agcf
 
 using namespace agcf;
@@ -675,6 +686,14 @@ extern "C" int agcf_adam_step_f32(float* p, const float* g, float* m, float* v, 
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), n4, p + n4 * 4, g + n4 * 4, m + n4 * 4, v + n4 * 4, n_tail,
       lr, beta1, beta2, eps, step, step_dev, peers);
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+extern "C" int agcf_adam_coefs(int32_t* step_dev, int32_t increment, float lr, float beta1, float beta2, float* coefs,
+                               agcf_stream_t stream) {
+  if (!step_dev || !coefs) return AGCF_EINVAL;
+  adam_coefs_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, increment, lr, beta1, beta2, coefs);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
 }

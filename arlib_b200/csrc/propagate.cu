@@ -36,6 +36,7 @@ struct SpmmParams {
   const int4* vrows;          // work items {start, len, row, k | nseg << 16}
   const int32_t* vpart;       // first partial slot of the item's row (rows with nseg > 1)
   int32_t n_v;
+  const int32_t* n_v_dev;     // nullable: device-side item count (per-batch work lists), clamps n_v
   float4* partial;            // [n_partial][d/4] partial sums of multi-segment rows
   int32_t* tickets;           // [n_partial], zero between launches
   const int32_t* col;
@@ -59,6 +60,14 @@ struct SpmmParams {
   // rank's egress per layer is its own rows once instead of once per peer
   float4* mc_Y;
   float4* mc_acc;
+  // fused optimizer (last backward layer): the row's gradient o = (acc_in + t) / acc_div goes straight into
+  // torch.optim.Adam's update of p / m / v; coefs = {lr / (1 - b1^t), sqrt(1 - b2^t)} (agcf_adam_coefs)
+  float4* adam_p;
+  float4* adam_m;
+  float4* adam_v;
+  const float* adam_coefs;
+  float beta1, beta2, adam_eps;
+  float4* zero_rows;          // nullable (== acc_in): rows of acc_in that were non-zero are zeroed after the read
 };
 
 __device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ m, int k) {
@@ -83,14 +92,23 @@ struct RowCfg {
 
 __device__ __forceinline__ float sgnf(float x) { return (float)((x > 0.f) - (x < 0.f)); }
 
+// one Adam update (torch.optim.Adam defaults), same operation order as adam_kernel in bpr.cu
+__device__ __forceinline__ void adam_update(float& pp, float gg, float& mm, float& vv, float w1, float w2, float beta2,
+                                            float step_size, float bc2_sqrt, float eps) {
+  mm = mm + w1 * (gg - mm);
+  vv = fmaf(w2 * gg, gg, vv * beta2);
+  const float denom = __fdiv_rn(sqrtf(vv), bc2_sqrt) + eps;
+  pp = pp - step_size * __fdiv_rn(mm, denom);
+}
+
 template <typename C, bool NOISE>
 __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool valid,
-                                              float4 (&t)[C::VPL], int gl) {
+                                              float4 (&t)[C::VPL], int gl, const float4* pre_add = nullptr) {
   const size_t rbase = (size_t)row * C::V4;
   if (p.addend != nullptr && valid) {
 #pragma unroll
     for (int v = 0; v < C::VPL; ++v)
-      t[v] = add4(t[v], ld_stream_f4(p.addend + rbase + v * C::LPR + gl));
+      t[v] = add4(t[v], pre_add != nullptr ? pre_add[v] : ld_stream_f4(p.addend + rbase + v * C::LPR + gl));
   }
   if (NOISE) {
     float4 nz[C::VPL];
@@ -125,22 +143,42 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
       }
     }
   }
-  if (p.acc_out != nullptr) {
+  if (p.acc_out != nullptr || p.adam_p != nullptr) {
+    float step_size = 0.f, bc2_sqrt = 1.f;
+    if (p.adam_p != nullptr) { step_size = __ldg(p.adam_coefs); bc2_sqrt = __ldg(p.adam_coefs + 1); }
 #pragma unroll
     for (int v = 0; v < C::VPL; ++v) {
+      const size_t at = rbase + v * C::LPR + gl;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.acc_in != nullptr) a = ld_stream_f4(p.acc_in + rbase + v * C::LPR + gl);
+      if (p.acc_in != nullptr) {
+        // (a table this kernel also writes must not go through the non-coherent path)
+        a = p.zero_rows != nullptr ? __ldcg(p.acc_in + at) : ld_stream_f4(p.acc_in + at);
+        // the batch's gradient rows are the only non-zero rows of G: put them back to zero for the next step
+        if (p.zero_rows != nullptr && (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f))
+          p.zero_rows[at] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       float4 o = add4(a, t[v]);
       if (p.acc_div != 1.0f) {
         o.x = __fdiv_rn(o.x, p.acc_div); o.y = __fdiv_rn(o.y, p.acc_div);
         o.z = __fdiv_rn(o.z, p.acc_div); o.w = __fdiv_rn(o.w, p.acc_div);
       }
-      p.acc_out[rbase + v * C::LPR + gl] = o;
-      if (p.mc_acc != nullptr) {
-        st_multicast_f4(p.mc_acc + rbase + v * C::LPR + gl, o);
-      } else {
-        for (int q = 0; q < p.n_peers; ++q)
-          if (p.peer_acc[q] != nullptr) p.peer_acc[q][rbase + v * C::LPR + gl] = o;
+      if (p.acc_out != nullptr) {
+        p.acc_out[at] = o;
+        if (p.mc_acc != nullptr) {
+          st_multicast_f4(p.mc_acc + at, o);
+        } else {
+          for (int q = 0; q < p.n_peers; ++q)
+            if (p.peer_acc[q] != nullptr) p.peer_acc[q][at] = o;
+        }
+      }
+      if (p.adam_p != nullptr) {
+        float4 pp = p.adam_p[at], mm = p.adam_m[at], vv = p.adam_v[at];
+        const float w1 = 1.f - p.beta1, w2 = 1.f - p.beta2;
+        adam_update(pp.x, o.x, mm.x, vv.x, w1, w2, p.beta2, step_size, bc2_sqrt, p.adam_eps);
+        adam_update(pp.y, o.y, mm.y, vv.y, w1, w2, p.beta2, step_size, bc2_sqrt, p.adam_eps);
+        adam_update(pp.z, o.z, mm.z, vv.z, w1, w2, p.beta2, step_size, bc2_sqrt, p.adam_eps);
+        adam_update(pp.w, o.w, mm.w, vv.w, w1, w2, p.beta2, step_size, bc2_sqrt, p.adam_eps);
+        p.adam_p[at] = pp; p.adam_m[at] = mm; p.adam_v[at] = vv;
       }
     }
   }
@@ -237,12 +275,77 @@ extern "C" int agcf_debug_spmm_trace(unsigned long long* host_out) {
 #define AGCF_TRACE_AFTER(k, dep)
 #endif
 
-template <int D, int LPR, int MINB, bool NOISE>
-__global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
+// Column-masked accumulation (first backward layer: only the <= 3B gradient rows of the batch are non-zero, ~13 % of
+// the non-zeros at the benchmark shape).  A chunk is LPR entries, one per lane; the lanes whose column is in the
+// mask are found with a ballot and ONLY those are broadcast, gathered and accumulated, in entry order -- the same
+// order as the dense loop, hence the same bits.  Few registers: the launch holds 2x the warps of the dense kernel,
+// which is what a latency-bound chain (descriptor -> indices -> bitmap -> row) needs.
+template <typename C>
+__device__ __forceinline__ void spmm_accumulate_masked(const SpmmParams& p, int s, int len, int iters, int gl, int grp,
+                                                       float4 (&acc)[C::VPL]) {
+  static_assert(C::EPL == 1, "masked path: one entry per lane and chunk");
+  int c_next = -1;
+  float v_next = 0.f;
+  auto load_chunk = [&](int off) {
+    c_next = -1;
+    v_next = 0.f;
+    const int e = off + gl;
+    if (e < len) {
+      c_next = ld_stream_i32(p.col + s + e);
+      v_next = ld_stream_f32(p.val + s + e);
+    }
+  };
+  load_chunk(0);
+  for (int it = 0, off = 0; it < iters; ++it, off += C::LPR) {
+    const int c = c_next;
+    const float v = v_next;
+    load_chunk(off + C::LPR);
+    const bool live = c >= 0 && bit_set(p.col_mask, c);
+    unsigned bits = __ballot_sync(0xffffffffu, live);
+    if constexpr (C::LPR < 32) bits = (bits >> (grp * C::LPR)) & ((1u << C::LPR) - 1u);
+    while (__any_sync(0xffffffffu, bits != 0u)) {
+      // two live entries per trip: both gathers are in flight together
+      const bool on0 = bits != 0u;
+      const int t0 = on0 ? __ffs(bits) - 1 : 0;
+      bits &= bits - 1u;
+      const bool on1 = bits != 0u;
+      const int t1 = on1 ? __ffs(bits) - 1 : 0;
+      bits &= bits - 1u;
+      const int c0 = __shfl_sync(0xffffffffu, c, t0, C::LPR);
+      const float v0 = __shfl_sync(0xffffffffu, v, t0, C::LPR);
+      const int c1 = __shfl_sync(0xffffffffu, c, t1, C::LPR);
+      const float v1 = __shfl_sync(0xffffffffu, v, t1, C::LPR);
+      float4 x0[C::VPL], x1[C::VPL];
+#pragma unroll
+      for (int vv = 0; vv < C::VPL; ++vv) {
+        x0[vv] = on0 ? ld_gather_f4(p.X + (size_t)c0 * C::V4 + vv * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x1[vv] = on1 ? ld_gather_f4(p.X + (size_t)c1 * C::V4 + vv * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (on0) {
+#pragma unroll
+        for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], v0, x0[vv]);
+      }
+      if (on1) {
+#pragma unroll
+        for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], v1, x1[vv]);
+      }
+    }
+  }
+}
+
+// programmatic dependent launch (sm_90+): a grid launched with the attribute may start while its predecessor in the
+// stream is still draining; everything the predecessor wrote is visible only after pdl_wait().  Both instructions are
+// no-ops in a grid launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <int D, int LPR, bool NOISE, bool CMASK>
+__device__ __forceinline__ void spmm_body(const SpmmParams& p) {
 #ifdef AGCF_SPMM_TRACE
   TraceScope trace_scope;
 #endif
   using C = RowCfg<D, LPR>;
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int gl = lane & (C::LPR - 1);
@@ -251,7 +354,14 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
 #pragma unroll
   for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   const long long slot = ((long long)blockIdx.x * (C::THREADS / 32) + warp) * C::RPW + grp;
-  bool valid = slot < p.n_v;
+  // everything read before pdl_wait() is static for the step (plan, per-batch work lists and bitmaps of the PREP
+  // phase): it overlaps the tail of the previous kernel
+  int n_v = p.n_v;
+  if (p.n_v_dev != nullptr) {
+    const int n_dev = __ldg(p.n_v_dev);
+    n_v = n_dev < n_v ? n_dev : n_v;
+  }
+  bool valid = slot < n_v;
   int4 vr = make_int4(0, 0, 0, 1 << 16);
   if (valid) vr = __ldg(p.vrows + slot);                  // one 16-byte load: start, len, row, segment id
   const int s = vr.x, row = vr.z, k = vr.w & 0xffff, nseg = vr.w >> 16;
@@ -263,9 +373,20 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
     const int other = __shfl_xor_sync(0xffffffffu, maxlen, o);
     maxlen = other > maxlen ? other : maxlen;
   }
-  const int iters = (maxlen + C::CH - 1) / C::CH;        // warp-uniform
   AGCF_TRACE_AFTER(1, maxlen + row);
-  spmm_accumulate_chunks<C, true>(p, s, len, 0, C::CH, iters, gl, acc);
+  pdl_wait();
+  float4 pre[C::VPL];                                      // CMASK: the epilogue's addend row, fetched before the gathers
+  if constexpr (CMASK) {
+    const int iters = (maxlen + C::LPR - 1) / C::LPR;      // warp-uniform
+    const bool has_add = p.addend != nullptr && valid;
+#pragma unroll
+    for (int v = 0; v < C::VPL; ++v)
+      pre[v] = has_add ? ld_stream_f4(p.addend + (size_t)row * C::V4 + v * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+    spmm_accumulate_masked<C>(p, s, len, iters, gl, grp, acc);
+  } else {
+    const int iters = (maxlen + C::CH - 1) / C::CH;        // warp-uniform
+    spmm_accumulate_chunks<C, true>(p, s, len, 0, C::CH, iters, gl, acc);
+  }
   AGCF_TRACE_AFTER(2, __float_as_int(acc[0].x));
   // ---- rows cut into several segments: combine through the partial-sum scratch -----------------
   const bool multi = valid && nseg > 1;
@@ -298,16 +419,46 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
       }
     }
   }
-  spmm_epilogue<C, NOISE>(p, row, do_epilogue, acc, gl);
+  spmm_epilogue<C, NOISE>(p, row, do_epilogue, acc, gl, (CMASK && p.addend != nullptr) ? pre : nullptr);
+}
+
+template <int D, int LPR, int MINB, bool NOISE>
+__global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
+  spmm_body<D, LPR, NOISE, false>(p);
+}
+
+// first backward layer: gathers only the rows in col_mask (spmm_accumulate_masked); twice the resident warps
+template <int D, int LPR, int MINB>
+__global__ void __launch_bounds__(256, MINB) spmm_colmask_kernel(const SpmmParams p) {
+  spmm_body<D, LPR, false, true>(p);
 }
 
 // resident CTAs per SM the register allocation is held to: 4 (<= 64 registers) measured best at d <= 64
 #ifndef AGCF_SPMM_MINB
 #define AGCF_SPMM_MINB(D) ((D) <= 64 ? 4 : ((D) == 128 ? 3 : 2))
 #endif
+#ifndef AGCF_SPMM_CM_MINB
+#define AGCF_SPMM_CM_MINB(D) ((D) <= 64 ? 6 : ((D) == 128 ? 5 : 4))
+#endif
+
+template <typename K>
+static int launch_kernel_pdl(K kernel, unsigned blocks, unsigned threads, cudaStream_t st, bool pdl, const SpmmParams& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  AGCF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
+  return AGCF_OK;
+}
 
 template <int D>
-static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
+static int launch_spmm(const SpmmParams& p, bool pdl, cudaStream_t st) {
   // lane mapping measured best on B200 (profiles/): one float4 per lane, d/4 lanes per row (16 at d = 64),
   // fully unrolled 16-entry chunks, packed FFMA2 accumulation
   constexpr int LPR = default_lpr(D);
@@ -315,12 +466,13 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   const long long blocks = ((long long)p.n_v + C::RPB - 1) / C::RPB;
   if (blocks <= 0) return AGCF_OK;
   if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
+  if constexpr (C::EPL == 1) {
+    if (p.col_mask != nullptr && p.noise == nullptr)
+      return launch_kernel_pdl(spmm_colmask_kernel<D, LPR, AGCF_SPMM_CM_MINB(D)>, (unsigned)blocks, C::THREADS, st, pdl, p);
+  }
   if (p.noise != nullptr)
-    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
-  else
-    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
-  AGCF_LAUNCH_OK();
-  return AGCF_OK;
+    return launch_kernel_pdl(spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true>, (unsigned)blocks, C::THREADS, st, pdl, p);
+  return launch_kernel_pdl(spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), false>, (unsigned)blocks, C::THREADS, st, pdl, p);
 }
 
 // ------------------------------------------------------------------------ SDDMM
@@ -402,9 +554,143 @@ __global__ void __launch_bounds__(256) concat_rows_kernel(const float4* __restri
     out[k] = k < na4 ? ld_stream_f4(a + k) : ld_stream_f4(b + (k - na4));
 }
 
+// ------------------------------------------------- per-batch work lists (last forward layer)
+// The loss reads F only at the <= 3B nodes of a batch, so the last forward layer is computed for those rows only.
+// Instead of testing every work item of the static plan against the batch bitmap (4 448 CTAs that mostly exit),
+// the PREP phase writes the batch's OWN plan: one CTA per batch walks the batch's sorted distinct nodes
+// (agcf_bpr_group_batches), cuts each row into segments of `segment` entries and emits the same
+// {start, len, row, k | nseg << 16} descriptors the SpMM kernel consumes, with partial-sum slots numbered per batch.
+__global__ void __launch_bounds__(1024) batch_worklist_kernel(const int32_t* __restrict__ seg_node,
+                                                              const int32_t* __restrict__ n_seg, int seg_stride,
+                                                              const int32_t* __restrict__ rowptr, int row0, int row1,
+                                                              int split_above, int segment, int4* __restrict__ wl_vrows,
+                                                              int32_t* __restrict__ wl_vpart, int32_t* __restrict__ wl_count,
+                                                              int cap) {
+  __shared__ int warp_items[32], warp_slots[32];
+  __shared__ int total_items;
+  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int32_t* nodes = seg_node + (size_t)b * seg_stride;
+  const int n = n_seg[b];
+  const int per = (n + nthr - 1) / nthr;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  auto segments_of = [&](int node, int& start, int& deg) {
+    if (node < row0 || node >= row1) { start = 0; deg = 0; return 0; }   // another rank's row
+    start = __ldg(rowptr + node);
+    deg = __ldg(rowptr + node + 1) - start;
+    return deg > split_above ? (deg + segment - 1) / segment : 1;
+  };
+  int items = 0, slots = 0;
+  for (int q = lo; q < hi; ++q) {
+    int start, deg;
+    const int ns = segments_of(nodes[q], start, deg);
+    items += ns;
+    slots += ns > 1 ? ns : 0;
+  }
+  int inc_i = items, inc_s = slots;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int yi = __shfl_up_sync(0xffffffffu, inc_i, o);
+    const int ys = __shfl_up_sync(0xffffffffu, inc_s, o);
+    if (lane >= o) { inc_i += yi; inc_s += ys; }
+  }
+  if (lane == 31) { warp_items[warp] = inc_i; warp_slots[warp] = inc_s; }
+  __syncthreads();
+  if (warp == 0) {
+    const int wi = lane < (nthr >> 5) ? warp_items[lane] : 0;
+    const int ws = lane < (nthr >> 5) ? warp_slots[lane] : 0;
+    int ci = wi, cs = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int yi = __shfl_up_sync(0xffffffffu, ci, o);
+      const int ys = __shfl_up_sync(0xffffffffu, cs, o);
+      if (lane >= o) { ci += yi; cs += ys; }
+    }
+    warp_items[lane] = ci - wi;
+    warp_slots[lane] = cs - ws;
+    if (lane == 31) total_items = ci;
+  }
+  __syncthreads();
+  int w = warp_items[warp] + inc_i - items;          // first item of this thread
+  int ps = warp_slots[warp] + inc_s - slots;         // first partial slot of this thread
+  int4* out_v = wl_vrows + (size_t)b * cap;
+  int32_t* out_p = wl_vpart + (size_t)b * cap;
+  for (int q = lo; q < hi; ++q) {
+    int start, deg;
+    const int node = nodes[q];
+    const int ns = segments_of(node, start, deg);
+    for (int k = 0; k < ns; ++k, ++w) {
+      if (w >= cap) break;
+      int len = deg;
+      if (ns > 1) { len = deg - k * segment; len = len > segment ? segment : len; }
+      out_v[w] = make_int4(start + k * segment, len, node, k | (ns << 16));
+      out_p[w] = ps;
+    }
+    if (ns > 1) ps += ns;
+  }
+  if (tid == 0) wl_count[b] = total_items < cap ? total_items : cap;
+}
+
 }  // namespace agcf
 
 using namespace agcf;
+
+extern "C" int agcf_spmm_csr_f32_ex(const agcf_spmm_args* a, agcf_stream_t stream) {
+  if (a == nullptr) return AGCF_EINVAL;
+  if (a->n_peers < 0 || a->n_peers > AGCF_MAX_PEERS) return AGCF_EINVAL;
+  if (!a->vrows || !a->vpart || !a->col || !a->val || !a->partial || !a->tickets || !a->X || a->n_vrows < 0) return AGCF_EINVAL;
+  if (a->Y == nullptr && a->acc_out == nullptr && a->adam_p == nullptr) return AGCF_EINVAL;
+  if (!supported_row_d(a->d)) return AGCF_EUNSUPPORTED;
+  if (!aligned16(a->vrows) || !aligned16(a->partial)) return AGCF_EINVAL;
+  if (!aligned16(a->X) || !aligned16(a->Y) || !aligned16(a->addend) || !aligned16(a->acc_in) || !aligned16(a->acc_out) ||
+      !aligned16(a->noise) || !aligned16(a->mc_Y) || !aligned16(a->mc_acc))
+    return AGCF_EINVAL;
+  if (a->X == a->Y || a->X == a->acc_out) return AGCF_EINVAL;   // rows of X are read by other CTAs
+  if (a->acc_div == 0.f) return AGCF_EINVAL;
+  if (a->adam_p != nullptr) {
+    if (!a->adam_m || !a->adam_v || !a->adam_coefs) return AGCF_EINVAL;
+    if (!aligned16(a->adam_p) || !aligned16(a->adam_m) || !aligned16(a->adam_v)) return AGCF_EINVAL;
+    if (a->adam_p == a->X) return AGCF_EINVAL;
+  }
+  if (a->zero_acc_in && (a->acc_in == nullptr || a->acc_in == a->X)) return AGCF_EINVAL;
+  SpmmParams p;
+  p.vrows = reinterpret_cast<const int4*>(a->vrows); p.vpart = a->vpart; p.n_v = a->n_vrows; p.n_v_dev = a->n_vrows_dev;
+  p.partial = reinterpret_cast<float4*>(a->partial); p.tickets = a->tickets;
+  p.col = a->col; p.val = a->val;
+  p.X = reinterpret_cast<const float4*>(a->X);
+  p.Y = reinterpret_cast<float4*>(a->Y);
+  p.addend = reinterpret_cast<const float4*>(a->addend);
+  p.acc_in = reinterpret_cast<const float4*>(a->acc_in);
+  p.acc_out = reinterpret_cast<float4*>(a->acc_out);
+  p.acc_div = a->acc_div;
+  p.noise = reinterpret_cast<const float4*>(a->noise);
+  p.eps = a->eps;
+  p.row_mask = a->row_mask; p.col_mask = a->col_mask;
+  p.mc_Y = a->Y != nullptr ? reinterpret_cast<float4*>(a->mc_Y) : nullptr;
+  p.mc_acc = a->acc_out != nullptr ? reinterpret_cast<float4*>(a->mc_acc) : nullptr;
+  p.n_peers = a->n_peers;
+  for (int q = 0; q < AGCF_MAX_PEERS; ++q) {
+    p.peer_Y[q] = (q < a->n_peers && a->peer_Y_host) ? reinterpret_cast<float4*>(a->peer_Y_host[q]) : nullptr;
+    p.peer_acc[q] = (q < a->n_peers && a->peer_acc_host) ? reinterpret_cast<float4*>(a->peer_acc_host[q]) : nullptr;
+  }
+  p.adam_p = reinterpret_cast<float4*>(a->adam_p);
+  p.adam_m = reinterpret_cast<float4*>(a->adam_m);
+  p.adam_v = reinterpret_cast<float4*>(a->adam_v);
+  p.adam_coefs = a->adam_coefs;
+  p.beta1 = a->adam_beta1; p.beta2 = a->adam_beta2; p.adam_eps = a->adam_eps;
+  p.zero_rows = a->zero_acc_in ? reinterpret_cast<float4*>(const_cast<float*>(a->acc_in)) : nullptr;
+  const bool pdl = (a->flags & AGCF_SPMM_PDL) != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->d) {
+    case 8: return launch_spmm<8>(p, pdl, st);
+    case 16: return launch_spmm<16>(p, pdl, st);
+    case 32: return launch_spmm<32>(p, pdl, st);
+    case 64: return launch_spmm<64>(p, pdl, st);
+    case 128: return launch_spmm<128>(p, pdl, st);
+    case 256: return launch_spmm<256>(p, pdl, st);
+  }
+  return AGCF_EUNSUPPORTED;
+}
 
 extern "C" int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int32_t n_vrows,
                                  const int32_t* col, const float* val, float* partial, int32_t* tickets,
@@ -415,45 +701,29 @@ extern "C" int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int
                                  void* const* peer_Y_host, void* const* peer_acc_host, int32_t n_peers,
                                  void* mc_Y, void* mc_acc,
                                  int32_t d, agcf_stream_t stream) {
-  if (n_peers < 0 || n_peers > AGCF_MAX_PEERS) return AGCF_EINVAL;
-  if (!vrows || !vpart || !col || !val || !partial || !tickets || !X || n_vrows < 0 || (Y == nullptr && acc_out == nullptr)) return AGCF_EINVAL;
-  if (!supported_row_d(d)) return AGCF_EUNSUPPORTED;
-  if (!aligned16(vrows) || !aligned16(partial)) return AGCF_EINVAL;
-  if (!aligned16(X) || !aligned16(Y) || !aligned16(addend) || !aligned16(acc_in) || !aligned16(acc_out) || !aligned16(noise))
-    return AGCF_EINVAL;
-  if (X == Y || X == acc_out) return AGCF_EINVAL;        // rows of X are read by other CTAs
-  if (acc_div == 0.f) return AGCF_EINVAL;
-  SpmmParams p;
-  p.vrows = reinterpret_cast<const int4*>(vrows); p.vpart = vpart; p.n_v = n_vrows;
-  p.partial = reinterpret_cast<float4*>(partial); p.tickets = tickets;
-  p.col = col; p.val = val;
-  p.X = reinterpret_cast<const float4*>(X);
-  p.Y = reinterpret_cast<float4*>(Y);
-  p.addend = reinterpret_cast<const float4*>(addend);
-  p.acc_in = reinterpret_cast<const float4*>(acc_in);
-  p.acc_out = reinterpret_cast<float4*>(acc_out);
-  p.acc_div = acc_div;
-  p.noise = reinterpret_cast<const float4*>(noise);
-  p.eps = eps;
-  p.row_mask = row_mask; p.col_mask = col_mask;
-  if (!aligned16(mc_Y) || !aligned16(mc_acc)) return AGCF_EINVAL;
-  p.mc_Y = Y != nullptr ? reinterpret_cast<float4*>(mc_Y) : nullptr;
-  p.mc_acc = acc_out != nullptr ? reinterpret_cast<float4*>(mc_acc) : nullptr;
-  p.n_peers = n_peers;
-  for (int q = 0; q < AGCF_MAX_PEERS; ++q) {
-    p.peer_Y[q] = (q < n_peers && peer_Y_host) ? reinterpret_cast<float4*>(peer_Y_host[q]) : nullptr;
-    p.peer_acc[q] = (q < n_peers && peer_acc_host) ? reinterpret_cast<float4*>(peer_acc_host[q]) : nullptr;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (d) {
-    case 8: return launch_spmm<8>(p, st);
-    case 16: return launch_spmm<16>(p, st);
-    case 32: return launch_spmm<32>(p, st);
-    case 64: return launch_spmm<64>(p, st);
-    case 128: return launch_spmm<128>(p, st);
-    case 256: return launch_spmm<256>(p, st);
-  }
-  return AGCF_EUNSUPPORTED;
+  agcf_spmm_args a = {};
+  a.vrows = vrows; a.vpart = vpart; a.n_vrows = n_vrows;
+  a.col = col; a.val = val; a.partial = partial; a.tickets = tickets;
+  a.X = X; a.Y = Y; a.addend = addend; a.acc_in = acc_in; a.acc_out = acc_out; a.acc_div = acc_div;
+  a.noise = noise; a.eps = eps; a.row_mask = row_mask; a.col_mask = col_mask;
+  a.peer_Y_host = peer_Y_host; a.peer_acc_host = peer_acc_host; a.n_peers = n_peers;
+  a.mc_Y = mc_Y; a.mc_acc = mc_acc; a.d = d;
+  return agcf_spmm_csr_f32_ex(&a, stream);
+}
+
+extern "C" int agcf_spmm_batch_worklists(const int32_t* seg_node, const int32_t* n_seg, int32_t n_batches,
+                                         int32_t seg_stride, const int32_t* rowptr, int32_t row0, int32_t row1,
+                                         int32_t split_above, int32_t segment, int32_t* wl_vrows, int32_t* wl_vpart,
+                                         int32_t* wl_count, int32_t cap, agcf_stream_t stream) {
+  if (!seg_node || !n_seg || !rowptr || !wl_vrows || !wl_vpart || !wl_count) return AGCF_EINVAL;
+  if (n_batches < 0 || seg_stride <= 0 || seg_stride > 16384 || cap <= 0 || row0 < 0 || row1 < row0) return AGCF_EINVAL;
+  if (segment < 16 || segment > 4096 || split_above < segment || !aligned16(wl_vrows)) return AGCF_EINVAL;
+  if (n_batches == 0) return AGCF_OK;
+  batch_worklist_kernel<<<(unsigned)n_batches, 1024, 0, (cudaStream_t)stream>>>(
+      seg_node, n_seg, seg_stride, rowptr, row0, row1, split_above, segment, reinterpret_cast<int4*>(wl_vrows), wl_vpart,
+      wl_count, cap);
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
 }
 
 extern "C" int agcf_sddmm_csr_f32(const int32_t* rowptr, const int32_t* col, const float* H, const float* E,

@@ -177,15 +177,58 @@ class LightGCNEngine:
         self.mask_words = (self.N + 31) // 32
         self.sparse_layers = bool(sparse_layers) and nbmax * self.mask_words * 4 <= (1 << 29)
         self.node_mask = i32(nbmax * self.mask_words) if self.sparse_layers else None
+        import os as _os
+        flag = lambda name, default="1": _os.environ.get(name, default) == "1"
+        # per-batch work lists: the last forward layer runs the batch's own plan (its <= 3B rows cut into short
+        # segments) instead of testing every item of the static plan against the bitmap
+        self.wl = None
+        if self.sparse_layers and flag("ARLIB_B200_WORKLISTS"):
+            self._init_worklists(nbmax, dev)
+        # Adam fused into the epilogue of the last backward SpMM (own rows == all rows: not in "rows" mode,
+        # where the updated rows also go to the peers)
+        self.fuse_adam = self.mode != "rows" and flag("ARLIB_B200_FUSE_ADAM")
+        self.adam_coefs = torch.zeros(2, dtype=torch.float32, device=dev)
+        # programmatic dependent launch of the SpMM chain (the next launch's descriptor / index fetch overlaps
+        # the previous kernel's tail)
+        self.pdl = flag("ARLIB_B200_PDL", "0")
         self.out4 = torch.zeros((nbmax, 4), dtype=torch.float32, device=dev)
         self.coef = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.ws = torch.zeros(ops.bpr_ws_bytes(self.B), dtype=torch.uint8, device=dev)
         self._graphs = {}
         self._ext = None
         self._loss_eager = None
-        import os as _os
         self.dist_graphs = _os.environ.get("ARLIB_B200_DIST_GRAPHS", "1") == "1"
         self.launches_per_step = {"single": 2 * self.L + 5, "rows": 4 * self.L + 5, "dshard": 2 * self.L + 7}[self.mode]
+        if self.fuse_adam:       # no adam kernel; no zero_rows kernel either when the last backward layer re-zeroes G
+            self.launches_per_step -= 2 if self.L > 1 else 1
+        self._refresh_adam_coefs()
+
+    WL_SEGMENT = 64
+
+    def _init_worklists(self, nbmax, dev):
+        """Capacity of a batch's work list = the 3B rows with the most segments (an upper bound for any batch)."""
+        g = self.g
+        rp = g.rowptr.long()
+        deg = rp[g.r0 + 1:g.r1 + 1] - rp[g.r0:g.r1]
+        seg = self.WL_SEGMENT
+        nseg = torch.where(deg > seg, (deg + seg - 1) // seg, torch.ones_like(deg))
+        if nseg.numel() == 0 or int(nseg.max()) >= (1 << 15):
+            return
+        top = torch.topk(nseg, min(3 * self.B, nseg.numel())).values
+        cap = (int(top.sum()) + 63) // 64 * 64
+        if nbmax * cap * 20 > (1 << 30):
+            return
+        i32 = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=dev)
+        self.wl = {"vrows": i32(nbmax, cap, 4), "vpart": i32(nbmax, cap), "count": i32(nbmax), "cap": cap,
+                   "partial": torch.empty((cap, self.d), dtype=torch.float32, device=dev), "tickets": i32(cap)}
+
+    def _worklist(self, b):
+        w = self.wl
+        return None if w is None else (w["vrows"][b], w["vpart"][b], w["count"][b:b + 1], w["partial"], w["tickets"])
+
+    def _refresh_adam_coefs(self):
+        """coefs of the NEXT step from the device step counter (after construction / a restore of step_dev)"""
+        ops.adam_coefs(self.step_dev, self.adam_coefs, self.lr, self.betas[0], self.betas[1], increment=False)
 
     def _peers(self, name):
         return self._peer[name] if self.mode == "rows" else None
@@ -240,9 +283,15 @@ class LightGCNEngine:
                               self.occ[b0 * 3 * self.B:], self.seg_off[b0 * (3 * self.B + 1):],
                               self.seg_node[b0 * 3 * self.B:], self.n_seg[b0:], self.N,
                               None if self.node_mask is None else self.node_mask[b0 * self.mask_words:])
+        if self.wl is not None and n > 0:
+            nb = (n + self.B - 1) // self.B
+            w = self.wl
+            ops.spmm_batch_worklists(self.seg_node[b0 * 3 * self.B:], self.n_seg[b0:], nb, 3 * self.B, self.g.rowptr,
+                                     self.g.r0, self.g.r1, self.WL_SEGMENT, self.WL_SEGMENT,
+                                     w["vrows"][b0:], w["vpart"][b0:], w["count"][b0:])
 
     # --------------------------------------------------------------- one step
-    def forward_table(self, out=None, row_mask=None):
+    def forward_table(self, out=None, row_mask=None, worklist=None):
         """F = mean_k A^k E0 into self.F (or ``out``): the encoder forward alone
         (recommender/LightGCN.py:230-240), e.g. for the end-of-epoch embeddings.  With
         ``row_mask`` the LAST layer only computes (and F is only valid on) the masked rows.
@@ -256,10 +305,12 @@ class LightGCNEngine:
             last = k == self.L
             name = "fw%d" % ((k - 1) % 2)
             y = None if last else self.fw[(k - 1) % 2]
+            wl = worklist if last else None
             ops.spmm(self.g, x, Y=y, acc_in=self.E0 if k == 1 else F, acc_out=F,
-                     acc_div=float(self.L + 1) if last else 1.0, row_mask=row_mask if last else None,
+                     acc_div=float(self.L + 1) if last else 1.0, row_mask=row_mask if (last and wl is None) else None,
                      peer_Y=None if last else self._peers(name), peer_acc=self._peers("F") if last else None,
-                     mc_Y=0 if last else self._mcast(name), mc_acc=self._mcast("F") if last else 0)
+                     mc_Y=0 if last else self._mcast(name), mc_acc=self._mcast("F") if last else 0,
+                     worklist=wl, pdl=self.pdl and k > 1)
             self._barrier()
             x = y
         return F
@@ -275,7 +326,7 @@ class LightGCNEngine:
         n_seg = self.n_seg[b:]
         out4 = self.out4[b]
         mask = self.node_mask[b * self.mask_words:] if self.sparse_layers else None
-        F = self.forward_table(row_mask=mask)
+        F = self.forward_table(row_mask=mask, worklist=self._worklist(b) if mask is not None else None)
         if self.mode == "dshard":
             ops.bpr_partial(F, u, i, j, nb, self.U, self.comm.rank, self.B, self.step_dev, self._xchg_all)
             self.comm.barrier()                  # the step's only exchange: 16 B per triple to every peer
@@ -288,12 +339,23 @@ class LightGCNEngine:
             if k > 1:
                 nxt = self.bw[k % 2]
                 ops.spmm(self.g, H, Y=nxt, addend=self.G, col_mask=mask if k == L else None,
-                         peer_Y=self._peers("bw%d" % (k % 2)), mc_Y=self._mcast("bw%d" % (k % 2)))
+                         peer_Y=self._peers("bw%d" % (k % 2)), mc_Y=self._mcast("bw%d" % (k % 2)), pdl=self.pdl)
                 self._barrier()
                 H = nxt
+            elif self.fuse_adam:
+                # dE0 = (G + A H) / (L + 1) never reaches memory: the epilogue applies Adam to the row and puts the
+                # batch's rows of G back to zero (not when L == 1: G is then also the gathered operand)
+                ops.spmm(self.g, H, acc_in=self.G, acc_div=float(L + 1), col_mask=mask if k == L else None,
+                         adam=(self.E0, self.m, self.v, self.adam_coefs, self.betas[0], self.betas[1], self.adam_eps),
+                         zero_acc_in=L > 1, pdl=self.pdl)
             else:
                 ops.spmm(self.g, H, acc_in=self.G, acc_out=self.dE0, acc_div=float(L + 1),
-                         col_mask=mask if k == L else None)
+                         col_mask=mask if k == L else None, pdl=self.pdl)
+        if self.fuse_adam:
+            if L == 1:
+                ops.zero_rows(seg_node, n_seg, 3 * nb, self.G)
+            ops.adam_coefs(self.step_dev, self.adam_coefs, self.lr, self.betas[0], self.betas[1], increment=True)
+            return
         ops.zero_rows(seg_node, n_seg, 3 * nb, self.G)
         # owner-computes: Adam on this rank's rows; the updated rows are stored into every peer's E0
         r0, r1 = self.r0, self.r1
@@ -331,6 +393,7 @@ class LightGCNEngine:
                 state = (self.E0.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone())
                 self._launch_step(first_batch)        # eager warm-up of every kernel in the step
                 self.E0.copy_(state[0]); self.m.copy_(state[1]); self.v.copy_(state[2]); self.step_dev.copy_(state[3])
+                self._refresh_adam_coefs()
                 torch.cuda.synchronize()
                 with torch.cuda.graph(g):
                     for b in range(first_batch, first_batch + n_steps):
@@ -422,6 +485,7 @@ class LightGCNEngine:
                 step(slot)
             slot["prep"], slot["step"] = gp, gs
         self.E0.copy_(state[0]); self.m.copy_(state[1]); self.v.copy_(state[2]); self.step_dev.copy_(state[3])
+        self._refresh_adam_coefs()
         torch.cuda.synchronize()
         for slot in slots:
             slot["prep_done"].record(main)

@@ -6,6 +6,8 @@ to torch's CURRENT stream, so they compose with torch ops and are capturable in
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -33,9 +35,14 @@ def _p(t):
 
 
 def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_div=1.0, noise=None, eps=0.0,
-         row_mask=None, col_mask=None, peer_Y=None, peer_acc=None, mc_Y=None, mc_acc=None):
-    """agcf_spmm_csr_f32: t = A X (+addend) (+noise perturbation); Y = t;
-    acc_out = (acc_in + t) / acc_div."""
+         row_mask=None, col_mask=None, peer_Y=None, peer_acc=None, mc_Y=None, mc_acc=None,
+         worklist=None, adam=None, zero_acc_in=False, pdl=False):
+    """agcf_spmm_csr_f32_ex: t = A X (+addend) (+noise perturbation); Y = t;
+    acc_out = (acc_in + t) / acc_div.
+
+    worklist = (vrows [cap,4], vpart [cap], count [1], partial [cap,d], tickets [cap]): a per-batch plan
+    (spmm_batch_worklists) instead of the graph's; adam = (p, m, v, coefs, beta1, beta2, eps): the optimizer
+    fused into the epilogue; zero_acc_in: re-zero the non-zero rows of acc_in; pdl: programmatic dependent launch."""
     lib = _lib.load()
     _f32(X, "X"); _f32(Y, "Y"); _f32(addend, "addend"); _f32(acc_in, "acc_in"); _f32(acc_out, "acc_out"); _f32(noise, "noise")
     if X.shape[0] != g.n_rows:
@@ -48,11 +55,57 @@ def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_
             raise ValueError("operand shape mismatch")
     py, n1 = _lib.ptr_array(peer_Y)
     pa, n2 = _lib.ptr_array(peer_acc)
-    _lib.check(lib.agcf_spmm_csr_f32(g.vrows.data_ptr(), g.vpart.data_ptr(), g.n_vrows, g.col.data_ptr(), g.val.data_ptr(),
-                                     g.partial_scratch(d).data_ptr(), g.tickets.data_ptr(), X.data_ptr(), _p(Y),
-                                     _p(addend), _p(acc_in), _p(acc_out), float(acc_div), _p(noise), float(eps),
-                                     _p(row_mask), _p(col_mask), py, pa, max(n1, n2),
-                                     mc_Y or None, mc_acc or None, d, _lib.stream_ptr()), "agcf_spmm_csr_f32")
+    a = _lib.SpmmArgs()
+    if worklist is None:
+        a.vrows, a.vpart, a.n_vrows = g.vrows.data_ptr(), g.vpart.data_ptr(), g.n_vrows
+        a.partial, a.tickets = g.partial_scratch(d).data_ptr(), g.tickets.data_ptr()
+    else:
+        wv, wp, wc, wpart, wtick = worklist
+        if wpart.shape[1] != d or wpart.shape[0] < wv.shape[0] or wtick.numel() < wv.shape[0]:
+            raise ValueError("work-list scratch too small")
+        a.vrows, a.vpart, a.n_vrows, a.n_vrows_dev = wv.data_ptr(), wp.data_ptr(), wv.shape[0], wc.data_ptr()
+        a.partial, a.tickets = wpart.data_ptr(), wtick.data_ptr()
+    a.col, a.val = g.col.data_ptr(), g.val.data_ptr()
+    a.X, a.Y, a.addend = X.data_ptr(), _p(Y), _p(addend)
+    a.acc_in, a.acc_out, a.acc_div = _p(acc_in), _p(acc_out), float(acc_div)
+    a.noise, a.eps = _p(noise), float(eps)
+    a.row_mask, a.col_mask = _p(row_mask), _p(col_mask)
+    a.peer_Y_host = ctypes.cast(py, ctypes.c_void_p) if py is not None else None
+    a.peer_acc_host = ctypes.cast(pa, ctypes.c_void_p) if pa is not None else None
+    a.n_peers = max(n1, n2)
+    a.mc_Y, a.mc_acc = mc_Y or None, mc_acc or None
+    if adam is not None:
+        p_, m_, v_, coefs, b1, b2, aeps = adam
+        for t in (p_, m_, v_):
+            _f32(t, "adam table")
+            if tuple(t.shape) != (g.n_rows, d):
+                raise ValueError("adam table shape mismatch")
+        a.adam_p, a.adam_m, a.adam_v, a.adam_coefs = p_.data_ptr(), m_.data_ptr(), v_.data_ptr(), coefs.data_ptr()
+        a.adam_beta1, a.adam_beta2, a.adam_eps = float(b1), float(b2), float(aeps)
+    a.zero_acc_in = 1 if zero_acc_in else 0
+    a.d = d
+    a.flags = _lib.SPMM_PDL if pdl else 0
+    _lib.check(lib.agcf_spmm_csr_f32_ex(ctypes.byref(a), _lib.stream_ptr()), "agcf_spmm_csr_f32_ex")
+
+
+def spmm_batch_worklists(seg_node, n_seg, n_batches, seg_stride, rowptr, row0, row1, split_above, segment,
+                         wl_vrows, wl_vpart, wl_count):
+    """agcf_spmm_batch_worklists: wl_vrows [n_batches, cap, 4], wl_vpart [n_batches, cap], wl_count [n_batches]."""
+    lib = _lib.load()
+    for t, n in ((seg_node, "seg_node"), (n_seg, "n_seg"), (rowptr, "rowptr"), (wl_vrows, "wl_vrows"),
+                 (wl_vpart, "wl_vpart"), (wl_count, "wl_count")):
+        _i32(t, n)
+    cap = wl_vrows.shape[-2]
+    _lib.check(lib.agcf_spmm_batch_worklists(seg_node.data_ptr(), n_seg.data_ptr(), int(n_batches), int(seg_stride),
+                                             rowptr.data_ptr(), int(row0), int(row1), int(split_above), int(segment),
+                                             wl_vrows.data_ptr(), wl_vpart.data_ptr(), wl_count.data_ptr(), int(cap),
+                                             _lib.stream_ptr()), "agcf_spmm_batch_worklists")
+
+
+def adam_coefs(step_dev, coefs, lr, beta1=0.9, beta2=0.999, increment=False):
+    """agcf_adam_coefs: (optionally) advance the device step counter and write {lr/(1-b1^t), sqrt(1-b2^t)}, t = step + 1."""
+    _lib.check(_lib.load().agcf_adam_coefs(step_dev.data_ptr(), 1 if increment else 0, float(lr), float(beta1),
+                                           float(beta2), coefs.data_ptr(), _lib.stream_ptr()), "agcf_adam_coefs")
 
 
 def sddmm(g: DeviceGraph, H, E, gval, accumulate=False):

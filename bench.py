@@ -292,7 +292,14 @@ def run_ours(args):
     def timed_spmm(*a, **k):
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(); orig(*a, **k); a1.record()
-        kind = "row_masked" if k.get("row_mask") is not None else ("col_masked" if k.get("col_mask") is not None else "full")
+        if k.get("row_mask") is not None or k.get("worklist") is not None:
+            kind = "row_masked"                   # last forward layer: the batch's rows only
+        elif k.get("col_mask") is not None:
+            kind = "col_masked"                   # first backward layer: the batch's gradient rows only
+        elif k.get("adam") is not None:
+            kind = "full_with_adam"               # last backward layer: + 6 table passes of the fused optimizer
+        else:
+            kind = "full"
         spmm_ms.append((kind, a0, a1))
 
     import arlib_b200.engine as engmod

@@ -99,6 +99,51 @@ int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int32_t n_vrow
                       void* mc_Y, void* mc_acc,
                       int32_t d, agcf_stream_t stream);
 
+/* The same launch with every argument in one plain-C struct (zero-initialise, then fill), plus what the fused
+ * training step adds:
+ *   n_vrows_dev   nullable device int32: the item count of a per-batch work list (agcf_spmm_batch_worklists);
+ *                 the grid is sized for n_vrows (the list's capacity) and items >= *n_vrows_dev are skipped, so the
+ *                 launch is capturable in a CUDA graph although the count changes from batch to batch;
+ *   adam_*        fused optimizer: the row's o = (acc_in + t) / acc_div is the gradient of torch.optim.Adam's update
+ *                 of adam_p / adam_m / adam_v ([rows, d] tables like Y), coefficients from agcf_adam_coefs;
+ *                 acc_out may then be null (the gradient table is never written).  Same bits as agcf_adam_step_f32;
+ *   zero_acc_in   != 0: rows of acc_in that were non-zero are set to zero after they were read (acc_in is the batch
+ *                 gradient G, non-zero on <= 3B rows: replaces agcf_zero_rows); acc_in must not be X;
+ *   flags         AGCF_SPMM_PDL: launch with programmatic stream serialization -- the grid may start while the
+ *                 previous kernel in the stream drains; it reads only the plan / work list / bitmaps before its
+ *                 griddepcontrol.wait, so those must not be written by the immediately preceding kernel.
+ * A launch with col_mask (and no noise) at d >= 64 runs the sparse variant (ballot over the live entries of a
+ * chunk, twice the resident warps): identical results. */
+#define AGCF_SPMM_PDL 1
+typedef struct agcf_spmm_args {
+  const int32_t* vrows; const int32_t* vpart; int32_t n_vrows; const int32_t* n_vrows_dev;
+  const int32_t* col; const float* val; float* partial; int32_t* tickets;
+  const float* X; float* Y; const float* addend;
+  const float* acc_in; float* acc_out; float acc_div;
+  const float* noise; float eps;
+  const uint32_t* row_mask; const uint32_t* col_mask;
+  void* const* peer_Y_host; void* const* peer_acc_host; int32_t n_peers;
+  void* mc_Y; void* mc_acc;
+  float* adam_p; float* adam_m; float* adam_v; const float* adam_coefs;
+  float adam_beta1; float adam_beta2; float adam_eps;
+  int32_t zero_acc_in;
+  int32_t d;
+  int32_t flags;
+} agcf_spmm_args;
+int agcf_spmm_csr_f32_ex(const agcf_spmm_args* args, agcf_stream_t stream);
+
+/* Per-batch work lists for the LAST forward layer (the loss reads F only at the batch's <= 3B nodes): for every
+ * batch b < n_batches, from its sorted distinct nodes seg_node[b*seg_stride ..][0 .. n_seg[b]) (agcf_bpr_group_batches),
+ * write the batch's own SpMM plan: wl_vrows[b][w] = {start, len, row, k | nseg << 16} (rows with more than split_above
+ * non-zeros cut into segments of `segment`), wl_vpart[b][w] = the row's first partial slot (numbered per batch),
+ * wl_count[b] = number of items (<= cap, the per-batch capacity of both arrays).  Nodes outside [row0, row1) are
+ * skipped (multi-GPU: another rank's rows).  Pass wl_vrows + b*cap*4 / wl_vpart + b*cap / wl_count + b to
+ * agcf_spmm_csr_f32_ex with n_vrows = cap; partial / tickets need cap slots. */
+int agcf_spmm_batch_worklists(const int32_t* seg_node, const int32_t* n_seg, int32_t n_batches, int32_t seg_stride,
+                              const int32_t* rowptr, int32_t row0, int32_t row1, int32_t split_above, int32_t segment,
+                              int32_t* wl_vrows, int32_t* wl_vpart, int32_t* wl_count, int32_t cap,
+                              agcf_stream_t stream);
+
 /* gval[p] (+)= <H[i,:], E[col[p],:]> for p in row i (accumulate != 0 adds).
  * Replaces: autograd of torch.sparse.mm w.r.t. the sparse operand, restricted to
  * the stored pattern -- attack/White/PGA.py:97-117, recommender/LightGCN.py:40-43,58-59. */
@@ -204,6 +249,10 @@ int agcf_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n,
                        int32_t step, const int32_t* step_dev,
                        void* const* peer_p_host, int32_t n_peers, void* mc_p, agcf_stream_t stream);
 int agcf_increment_i32(int32_t* counter, agcf_stream_t stream);
+/* if (increment) *step_dev += 1;  t = *step_dev + 1;  coefs = {lr / (1 - b1^t), sqrt(1 - b2^t)} -- the two
+ * step-dependent scalars of the Adam update, for the optimizer fused into the last backward SpMM. */
+int agcf_adam_coefs(int32_t* step_dev, int32_t increment, float lr, float beta1, float beta2, float* coefs,
+                    agcf_stream_t stream);
 
 /* ----------------------------------------------------------------- evaluation
  * Full-rank scoring + masked top-K for n_u users (rows user_rows[0..n_u) of Uemb,
