@@ -36,12 +36,11 @@ class SpmmArgs(ctypes.Structure):
         ("adam_p", P), ("adam_m", P), ("adam_v", P), ("adam_coefs", P),
         ("adam_beta1", F32), ("adam_beta2", F32), ("adam_eps", F32),
         ("zero_acc_in", I32),
+        ("sched", P),
         ("d", I32),
         ("flags", I32),
     ]
 
-
-SPMM_PDL = 1
 
 # name -> (restype, argtypes); mirrors include/agcf.h one to one
 SIGNATURES = {

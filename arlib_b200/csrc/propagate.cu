@@ -37,6 +37,8 @@ struct SpmmParams {
   const int32_t* vpart;       // first partial slot of the item's row (rows with nseg > 1)
   int32_t n_v;
   const int32_t* n_v_dev;     // nullable: device-side item count (per-batch work lists), clamps n_v
+  int32_t* sched;             // nullable: {next block, CTAs done}, zero between launches -> persistent CTAs that take
+                              // blocks of RPB items dynamically (no CTA turnover gaps, no tail of idle SMs)
   float4* partial;            // [n_partial][d/4] partial sums of multi-segment rows
   int32_t* tickets;           // [n_partial], zero between launches
   const int32_t* col;
@@ -255,22 +257,23 @@ __device__ __forceinline__ unsigned long long trace_now() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void trace_put(int k, unsigned long long v) {
-  if (threadIdx.x == 0 && blockIdx.x < 16384) g_spmm_trace[6 * blockIdx.x + k] = v;
+__device__ __forceinline__ void trace_put(int blk, int k, unsigned long long v) {
+  if (threadIdx.x == 0 && blk < 16384) g_spmm_trace[6 * blk + k] = v;
 }
 struct TraceScope {
-  __device__ TraceScope() { trace_put(0, trace_now()); }
+  int blk;
+  __device__ explicit TraceScope(int b) : blk(b) { trace_put(blk, 0, trace_now()); }
   __device__ ~TraceScope() {
     unsigned int sm;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
-    trace_put(3, trace_now());
-    trace_put(4, sm);
+    trace_put(blk, 3, trace_now());
+    trace_put(blk, 4, sm);
   }
 };
 extern "C" int agcf_debug_spmm_trace(unsigned long long* host_out) {
   return cudaMemcpyFromSymbol(host_out, g_spmm_trace, sizeof(g_spmm_trace)) == cudaSuccess ? 0 : -3;
 }
-#define AGCF_TRACE_AFTER(k, dep) trace_put(k, trace_now() + ((dep) == 0x7fffff01 ? 1ull : 0ull))
+#define AGCF_TRACE_AFTER(k, dep) trace_put(blk, k, trace_now() + ((dep) == 0x7fffff01 ? 1ull : 0ull))
 #else
 #define AGCF_TRACE_AFTER(k, dep)
 #endif
@@ -333,19 +336,13 @@ __device__ __forceinline__ void spmm_accumulate_masked(const SpmmParams& p, int 
   }
 }
 
-// programmatic dependent launch (sm_90+): a grid launched with the attribute may start while its predecessor in the
-// stream is still draining; everything the predecessor wrote is visible only after pdl_wait().  Both instructions are
-// no-ops in a grid launched without the attribute.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
+// one block of RPB work items (one lane group each)
 template <int D, int LPR, bool NOISE, bool CMASK>
-__device__ __forceinline__ void spmm_body(const SpmmParams& p) {
+__device__ __forceinline__ void spmm_block(const SpmmParams& p, const int n_v, const int blk) {
 #ifdef AGCF_SPMM_TRACE
-  TraceScope trace_scope;
+  TraceScope trace_scope(blk);
 #endif
   using C = RowCfg<D, LPR>;
-  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int gl = lane & (C::LPR - 1);
@@ -353,14 +350,7 @@ __device__ __forceinline__ void spmm_body(const SpmmParams& p) {
   float4 acc[C::VPL];
 #pragma unroll
   for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long slot = ((long long)blockIdx.x * (C::THREADS / 32) + warp) * C::RPW + grp;
-  // everything read before pdl_wait() is static for the step (plan, per-batch work lists and bitmaps of the PREP
-  // phase): it overlaps the tail of the previous kernel
-  int n_v = p.n_v;
-  if (p.n_v_dev != nullptr) {
-    const int n_dev = __ldg(p.n_v_dev);
-    n_v = n_dev < n_v ? n_dev : n_v;
-  }
+  const long long slot = ((long long)blk * (C::THREADS / 32) + warp) * C::RPW + grp;
   bool valid = slot < n_v;
   int4 vr = make_int4(0, 0, 0, 1 << 16);
   if (valid) vr = __ldg(p.vrows + slot);                  // one 16-byte load: start, len, row, segment id
@@ -374,7 +364,6 @@ __device__ __forceinline__ void spmm_body(const SpmmParams& p) {
     maxlen = other > maxlen ? other : maxlen;
   }
   AGCF_TRACE_AFTER(1, maxlen + row);
-  pdl_wait();
   float4 pre[C::VPL];                                      // CMASK: the epilogue's addend row, fetched before the gathers
   if constexpr (CMASK) {
     const int iters = (maxlen + C::LPR - 1) / C::LPR;      // warp-uniform
@@ -422,15 +411,48 @@ __device__ __forceinline__ void spmm_body(const SpmmParams& p) {
   spmm_epilogue<C, NOISE>(p, row, do_epilogue, acc, gl, (CMASK && p.addend != nullptr) ? pre : nullptr);
 }
 
+// Grid: one CTA per block of RPB items (sched == nullptr), or PERSISTENT CTAs (148 x MINB of them) that take their
+// first block by CTA id and every further one from a device counter, in plan order (long items first).  The ticket for
+// the next block is taken before the current block is processed, so its latency is hidden; the last CTA to finish
+// puts both counters back to zero for the next launch.
+template <int D, int LPR, bool NOISE, bool CMASK>
+__device__ __forceinline__ void spmm_grid(const SpmmParams& p) {
+  using C = RowCfg<D, LPR>;
+  int n_v = p.n_v;
+  if (p.n_v_dev != nullptr) {
+    const int n_dev = __ldg(p.n_v_dev);
+    n_v = n_dev < n_v ? n_dev : n_v;
+  }
+  if (p.sched == nullptr) {
+    spmm_block<D, LPR, NOISE, CMASK>(p, n_v, (int)blockIdx.x);
+    return;
+  }
+  __shared__ int s_next[2];
+  const int n_blocks = (n_v + C::RPB - 1) / C::RPB;
+  int blk = (int)blockIdx.x;
+  for (int it = 0; blk < n_blocks; ++it) {
+    int nxt = 0;
+    if (threadIdx.x == 0) nxt = atomicAdd(p.sched, 1) + (int)gridDim.x;
+    spmm_block<D, LPR, NOISE, CMASK>(p, n_v, blk);
+    if (threadIdx.x == 0) s_next[it & 1] = nxt;
+    __syncthreads();
+    blk = s_next[it & 1];
+  }
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(p.sched + 1, 1);
+    if (done == (int)gridDim.x - 1) { p.sched[0] = 0; p.sched[1] = 0; }
+  }
+}
+
 template <int D, int LPR, int MINB, bool NOISE>
 __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p) {
-  spmm_body<D, LPR, NOISE, false>(p);
+  spmm_grid<D, LPR, NOISE, false>(p);
 }
 
 // first backward layer: gathers only the rows in col_mask (spmm_accumulate_masked); twice the resident warps
 template <int D, int LPR, int MINB>
 __global__ void __launch_bounds__(256, MINB) spmm_colmask_kernel(const SpmmParams p) {
-  spmm_body<D, LPR, false, true>(p);
+  spmm_grid<D, LPR, false, true>(p);
 }
 
 // resident CTAs per SM the register allocation is held to: 4 (<= 64 registers) measured best at d <= 64
@@ -438,41 +460,37 @@ __global__ void __launch_bounds__(256, MINB) spmm_colmask_kernel(const SpmmParam
 #define AGCF_SPMM_MINB(D) ((D) <= 64 ? 4 : ((D) == 128 ? 3 : 2))
 #endif
 #ifndef AGCF_SPMM_CM_MINB
-#define AGCF_SPMM_CM_MINB(D) ((D) <= 64 ? 6 : ((D) == 128 ? 5 : 4))
+#define AGCF_SPMM_CM_MINB(D) ((D) <= 64 ? 5 : ((D) == 128 ? 4 : 3))
 #endif
 
-template <typename K>
-static int launch_kernel_pdl(K kernel, unsigned blocks, unsigned threads, cudaStream_t st, bool pdl, const SpmmParams& p) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(blocks, 1, 1);
-  cfg.blockDim = dim3(threads, 1, 1);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  AGCF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
-  return AGCF_OK;
-}
-
 template <int D>
-static int launch_spmm(const SpmmParams& p, bool pdl, cudaStream_t st) {
+static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   // lane mapping measured best on B200 (profiles/): one float4 per lane, d/4 lanes per row (16 at d = 64),
   // fully unrolled 16-entry chunks, packed FFMA2 accumulation
   constexpr int LPR = default_lpr(D);
   using C = RowCfg<D, LPR>;
-  const long long blocks = ((long long)p.n_v + C::RPB - 1) / C::RPB;
+  long long blocks = ((long long)p.n_v + C::RPB - 1) / C::RPB;
   if (blocks <= 0) return AGCF_OK;
   if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
+  bool cmask = false;
+  if constexpr (C::EPL == 1) cmask = p.col_mask != nullptr && p.noise == nullptr;
+  if (p.sched != nullptr) {                                  // persistent: every CTA resident at once
+    const long long resident = (long long)kSMs * (cmask ? AGCF_SPMM_CM_MINB(D) : AGCF_SPMM_MINB(D));
+    blocks = blocks < resident ? blocks : resident;
+  }
   if constexpr (C::EPL == 1) {
-    if (p.col_mask != nullptr && p.noise == nullptr)
-      return launch_kernel_pdl(spmm_colmask_kernel<D, LPR, AGCF_SPMM_CM_MINB(D)>, (unsigned)blocks, C::THREADS, st, pdl, p);
+    if (cmask) {
+      spmm_colmask_kernel<D, LPR, AGCF_SPMM_CM_MINB(D)><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+      AGCF_LAUNCH_OK();
+      return AGCF_OK;
+    }
   }
   if (p.noise != nullptr)
-    return launch_kernel_pdl(spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true>, (unsigned)blocks, C::THREADS, st, pdl, p);
-  return launch_kernel_pdl(spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), false>, (unsigned)blocks, C::THREADS, st, pdl, p);
+    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+  else
+    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
 }
 
 // ------------------------------------------------------------------------ SDDMM
@@ -679,15 +697,16 @@ extern "C" int agcf_spmm_csr_f32_ex(const agcf_spmm_args* a, agcf_stream_t strea
   p.adam_coefs = a->adam_coefs;
   p.beta1 = a->adam_beta1; p.beta2 = a->adam_beta2; p.adam_eps = a->adam_eps;
   p.zero_rows = a->zero_acc_in ? reinterpret_cast<float4*>(const_cast<float*>(a->acc_in)) : nullptr;
-  const bool pdl = (a->flags & AGCF_SPMM_PDL) != 0;
+  if (a->flags != 0) return AGCF_EINVAL;
+  p.sched = a->sched;
   cudaStream_t st = (cudaStream_t)stream;
   switch (a->d) {
-    case 8: return launch_spmm<8>(p, pdl, st);
-    case 16: return launch_spmm<16>(p, pdl, st);
-    case 32: return launch_spmm<32>(p, pdl, st);
-    case 64: return launch_spmm<64>(p, pdl, st);
-    case 128: return launch_spmm<128>(p, pdl, st);
-    case 256: return launch_spmm<256>(p, pdl, st);
+    case 8: return launch_spmm<8>(p, st);
+    case 16: return launch_spmm<16>(p, st);
+    case 32: return launch_spmm<32>(p, st);
+    case 64: return launch_spmm<64>(p, st);
+    case 128: return launch_spmm<128>(p, st);
+    case 256: return launch_spmm<256>(p, st);
   }
   return AGCF_EUNSUPPORTED;
 }

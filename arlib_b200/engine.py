@@ -188,9 +188,6 @@ class LightGCNEngine:
         # where the updated rows also go to the peers)
         self.fuse_adam = self.mode != "rows" and flag("ARLIB_B200_FUSE_ADAM")
         self.adam_coefs = torch.zeros(2, dtype=torch.float32, device=dev)
-        # programmatic dependent launch of the SpMM chain (the next launch's descriptor / index fetch overlaps
-        # the previous kernel's tail)
-        self.pdl = flag("ARLIB_B200_PDL", "0")
         self.out4 = torch.zeros((nbmax, 4), dtype=torch.float32, device=dev)
         self.coef = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.ws = torch.zeros(ops.bpr_ws_bytes(self.B), dtype=torch.uint8, device=dev)
@@ -203,7 +200,7 @@ class LightGCNEngine:
             self.launches_per_step -= 2 if self.L > 1 else 1
         self._refresh_adam_coefs()
 
-    WL_SEGMENT = 64
+    WL_SEGMENT = int(__import__('os').environ.get('ARLIB_B200_WL_SEGMENT', '64'))
 
     def _init_worklists(self, nbmax, dev):
         """Capacity of a batch's work list = the 3B rows with the most segments (an upper bound for any batch)."""
@@ -310,7 +307,7 @@ class LightGCNEngine:
                      acc_div=float(self.L + 1) if last else 1.0, row_mask=row_mask if (last and wl is None) else None,
                      peer_Y=None if last else self._peers(name), peer_acc=self._peers("F") if last else None,
                      mc_Y=0 if last else self._mcast(name), mc_acc=self._mcast("F") if last else 0,
-                     worklist=wl, pdl=self.pdl and k > 1)
+                     worklist=wl)
             self._barrier()
             x = y
         return F
@@ -339,7 +336,7 @@ class LightGCNEngine:
             if k > 1:
                 nxt = self.bw[k % 2]
                 ops.spmm(self.g, H, Y=nxt, addend=self.G, col_mask=mask if k == L else None,
-                         peer_Y=self._peers("bw%d" % (k % 2)), mc_Y=self._mcast("bw%d" % (k % 2)), pdl=self.pdl)
+                         peer_Y=self._peers("bw%d" % (k % 2)), mc_Y=self._mcast("bw%d" % (k % 2)))
                 self._barrier()
                 H = nxt
             elif self.fuse_adam:
@@ -347,10 +344,10 @@ class LightGCNEngine:
                 # batch's rows of G back to zero (not when L == 1: G is then also the gathered operand)
                 ops.spmm(self.g, H, acc_in=self.G, acc_div=float(L + 1), col_mask=mask if k == L else None,
                          adam=(self.E0, self.m, self.v, self.adam_coefs, self.betas[0], self.betas[1], self.adam_eps),
-                         zero_acc_in=L > 1, pdl=self.pdl)
+                         zero_acc_in=L > 1)
             else:
                 ops.spmm(self.g, H, acc_in=self.G, acc_out=self.dE0, acc_div=float(L + 1),
-                         col_mask=mask if k == L else None, pdl=self.pdl)
+                         col_mask=mask if k == L else None)
         if self.fuse_adam:
             if L == 1:
                 ops.zero_rows(seg_node, n_seg, 3 * nb, self.G)

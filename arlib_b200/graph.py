@@ -27,6 +27,10 @@ from . import _lib
 # slices, 64 is (quarter partition: 16.5 us vs 24.7 us; d = 8 slices: 27 us vs 55 us).
 SEGMENT_ENV = os.environ.get("ARLIB_B200_SEGMENT")
 SPLIT_ENV = os.environ.get("ARLIB_B200_SPLIT_ABOVE")
+# persistent CTAs + dynamic block scheduling in the SpMM launches (default 0: one CTA per block of 8 warps' work
+# items -- measured on B200 at the Gowalla shape: 0.2538 ms / step vs 0.2613 ms with persistent CTAs; the hardware
+# CTA scheduler already refills SM slots without a visible gap, profiles/r1_summary.md)
+PERSISTENT_ENV = os.environ.get("ARLIB_B200_PERSISTENT", "0")
 
 
 def default_segment(local_nnz, d=64):
@@ -113,6 +117,9 @@ class DeviceGraph:
         self.local_nnz = int(deg.sum())
         self.max_segments = int(nseg.max()) if nseg.numel() else 0
         self.tickets = torch.zeros(max(self.n_partial, 1), dtype=torch.int32, device=dev)
+        # dynamic block scheduler of the persistent launch mode: {next block, CTAs done}, self-resetting
+        self.sched = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.persistent = PERSISTENT_ENV == "1"
 
     def partial_scratch(self, d):
         """[n_partial, d] fp32 scratch for the partial sums of multi-segment rows (one per width, reused by

@@ -36,13 +36,14 @@ def _p(t):
 
 def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_div=1.0, noise=None, eps=0.0,
          row_mask=None, col_mask=None, peer_Y=None, peer_acc=None, mc_Y=None, mc_acc=None,
-         worklist=None, adam=None, zero_acc_in=False, pdl=False):
+         worklist=None, adam=None, zero_acc_in=False, persistent=None):
     """agcf_spmm_csr_f32_ex: t = A X (+addend) (+noise perturbation); Y = t;
     acc_out = (acc_in + t) / acc_div.
 
     worklist = (vrows [cap,4], vpart [cap], count [1], partial [cap,d], tickets [cap]): a per-batch plan
     (spmm_batch_worklists) instead of the graph's; adam = (p, m, v, coefs, beta1, beta2, eps): the optimizer
-    fused into the epilogue; zero_acc_in: re-zero the non-zero rows of acc_in; pdl: programmatic dependent launch."""
+    fused into the epilogue; zero_acc_in: re-zero the non-zero rows of acc_in; persistent (default: the graph's
+    setting): persistent CTAs with dynamic block scheduling instead of one CTA per block."""
     lib = _lib.load()
     _f32(X, "X"); _f32(Y, "Y"); _f32(addend, "addend"); _f32(acc_in, "acc_in"); _f32(acc_out, "acc_out"); _f32(noise, "noise")
     if X.shape[0] != g.n_rows:
@@ -84,7 +85,9 @@ def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_
         a.adam_beta1, a.adam_beta2, a.adam_eps = float(b1), float(b2), float(aeps)
     a.zero_acc_in = 1 if zero_acc_in else 0
     a.d = d
-    a.flags = _lib.SPMM_PDL if pdl else 0
+    if g.persistent if persistent is None else persistent:
+        a.sched = g.sched.data_ptr()
+    a.flags = 0
     _lib.check(lib.agcf_spmm_csr_f32_ex(ctypes.byref(a), _lib.stream_ptr()), "agcf_spmm_csr_f32_ex")
 
 

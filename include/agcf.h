@@ -109,12 +109,13 @@ int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int32_t n_vrow
  *                 acc_out may then be null (the gradient table is never written).  Same bits as agcf_adam_step_f32;
  *   zero_acc_in   != 0: rows of acc_in that were non-zero are set to zero after they were read (acc_in is the batch
  *                 gradient G, non-zero on <= 3B rows: replaces agcf_zero_rows); acc_in must not be X;
- *   flags         AGCF_SPMM_PDL: launch with programmatic stream serialization -- the grid may start while the
- *                 previous kernel in the stream drains; it reads only the plan / work list / bitmaps before its
- *                 griddepcontrol.wait, so those must not be written by the immediately preceding kernel.
+ *   sched         nullable device int32[2], zero on entry and zero again on exit: the launch then runs PERSISTENT CTAs
+ *                 (148 x resident CTAs per SM) that take blocks of work items from this counter in plan order instead
+ *                 of one CTA per block -- no CTA turnover gaps and no tail of idle SMs; launches sharing it must be
+ *                 stream-ordered;
+ *   flags         reserved, must be 0.
  * A launch with col_mask (and no noise) at d >= 64 runs the sparse variant (ballot over the live entries of a
  * chunk, twice the resident warps): identical results. */
-#define AGCF_SPMM_PDL 1
 typedef struct agcf_spmm_args {
   const int32_t* vrows; const int32_t* vpart; int32_t n_vrows; const int32_t* n_vrows_dev;
   const int32_t* col; const float* val; float* partial; int32_t* tickets;
@@ -127,6 +128,7 @@ typedef struct agcf_spmm_args {
   float* adam_p; float* adam_m; float* adam_v; const float* adam_coefs;
   float adam_beta1; float adam_beta2; float adam_eps;
   int32_t zero_acc_in;
+  int32_t* sched;
   int32_t d;
   int32_t flags;
 } agcf_spmm_args;

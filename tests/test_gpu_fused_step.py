@@ -1,8 +1,8 @@
 """GPU parity of the fused training-step variants: per-batch work lists (last forward
 layer), the sparse column-masked kernel (first backward layer), Adam + re-zeroing of G
-fused into the last backward SpMM, programmatic dependent launch.  Each must reproduce
-the plain launch sequence (recommender/LightGCN.py:50-64): the optimizer / PDL variants
-bit for bit, the work lists up to the association of a row's partial sums."""
+fused into the last backward SpMM, persistent CTAs with dynamic block scheduling.  Each
+must reproduce the plain launch sequence (recommender/LightGCN.py:50-64): the optimizer /
+scheduling variants bit for bit, the work lists up to the association of a row's partial sums."""
 import numpy as np
 import pytest
 import torch
@@ -179,19 +179,21 @@ def _run_epoch(golden, monkeypatch, flags, use_graph, L=2):
     return table.clone(), losses, eng.m.clone(), eng.v.clone()
 
 
-PLAIN = {"ARLIB_B200_WORKLISTS": "0", "ARLIB_B200_FUSE_ADAM": "0", "ARLIB_B200_PDL": "0"}
+PLAIN = {"ARLIB_B200_WORKLISTS": "0", "ARLIB_B200_FUSE_ADAM": "0"}
 
 
 @pytest.mark.parametrize("L", [1, 2, 3])
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_fused_step_variants_reproduce_the_plain_step(golden, monkeypatch, use_graph, L):
+    import arlib_b200.graph as graphmod
+    monkeypatch.setattr(graphmod, "PERSISTENT_ENV", "0")
     ref = _run_epoch(golden, monkeypatch, PLAIN, use_graph, L)
-    for flags in ({"ARLIB_B200_FUSE_ADAM": "1"}, {"ARLIB_B200_PDL": "1"},
-                  {"ARLIB_B200_FUSE_ADAM": "1", "ARLIB_B200_PDL": "1"}):
-        got = _run_epoch(golden, monkeypatch, dict(PLAIN, **flags), use_graph, L)
-        for a, b in zip(ref, got):
-            assert torch.equal(a, b), flags
-    got = _run_epoch(golden, monkeypatch, {"ARLIB_B200_WORKLISTS": "1", "ARLIB_B200_FUSE_ADAM": "1", "ARLIB_B200_PDL": "1"},
-                     use_graph, L)
+    for persistent in ("0", "1"):
+        monkeypatch.setattr(graphmod, "PERSISTENT_ENV", persistent)
+        for flags in ({}, {"ARLIB_B200_FUSE_ADAM": "1"}):
+            got = _run_epoch(golden, monkeypatch, dict(PLAIN, **flags), use_graph, L)
+            for a, b in zip(ref, got):
+                assert torch.equal(a, b), (persistent, flags)
+    got = _run_epoch(golden, monkeypatch, {"ARLIB_B200_WORKLISTS": "1", "ARLIB_B200_FUSE_ADAM": "1"}, use_graph, L)
     torch.testing.assert_close(got[1], ref[1], rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(got[0], ref[0], rtol=1e-5, atol=1e-7)
