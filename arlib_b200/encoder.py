@@ -165,6 +165,15 @@ def spmm_autograd(graph, x):
 
 
 # --------------------------------------------------------------------- modules
+def unique_ids_like_reference(ids, dev):
+    """``torch.unique(torch.Tensor(ids).type(torch.long))`` of recommender/SimGCL.py:213-214 / XSimGCL.py:40-41: the
+    ids pass through float32 (exact below 2**24).  Accepts the reference's Python lists or the
+    device LongTensors of the Philox sampler."""
+    if torch.is_tensor(ids):
+        return torch.unique(ids.to(dev).to(torch.float32).to(torch.long))
+    return torch.unique(torch.Tensor(ids).type(torch.long)).to(dev)
+
+
 class TorchGraphInterface(object):
     """recommender/LightGCN.py:243-252 -- kept for callers that import it."""
 
@@ -302,8 +311,7 @@ class SimGCL_Encoder(GraphEncoderBase):
         torch.Tensor(list) there)."""
         from .util.loss import InfoNCE
         dev = self.embedding_dict['user_emb'].device
-        u_idx = torch.unique(torch.Tensor(idx[0]).type(torch.long)).to(dev)
-        i_idx = torch.unique(torch.Tensor(idx[1]).type(torch.long)).to(dev)
+        u_idx, i_idx = unique_ids_like_reference(idx[0], dev), unique_ids_like_reference(idx[1], dev)
         u1, i1 = self.forward(perturbed=True)
         u2, i2 = self.forward(perturbed=True)
         return InfoNCE(u1[u_idx], u2[u_idx], 0.2) + InfoNCE(i1[i_idx], i2[i_idx], 0.2)

@@ -39,8 +39,8 @@ class LightGCN(GraphRecommender):
         self._grad_buffers(requires_adjgrad, requires_embgrad, model)
         dev = model.embedding_dict['user_emb'].device
         for epoch in range(maxEpoch):
-            for n, batch in enumerate(next_batch_pairwise(self.data, self.args.batch_size)):
-                user_idx, pos_idx, neg_idx = (torch.tensor(x, dtype=torch.long, device=dev) for x in batch)
+            for n, batch in enumerate(self._epoch_batches(dev)):
+                user_idx, pos_idx, neg_idx = (torch.as_tensor(x, dtype=torch.long, device=dev) for x in batch)
                 model.train()
                 rec_user_emb, rec_item_emb = model()
                 user_emb, pos_item_emb, neg_item_emb = rec_user_emb[user_idx], rec_item_emb[pos_idx], rec_item_emb[neg_idx]
@@ -72,7 +72,7 @@ class LightGCN(GraphRecommender):
         seed = int(getattr(self.args, 'seed', 0) or 0)
         for epoch in range(maxEpoch):
             if mode == 'device':
-                eng.sample_epoch(ts, seed, epoch)
+                eng.sample_epoch(ts, seed, self._next_sample_epoch())
             else:                                   # host sampler: the reference's RNG consumption
                 us, is_, js = [], [], []
                 for u, i, j in next_batch_pairwise(self.data, self.args.batch_size):

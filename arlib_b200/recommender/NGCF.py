@@ -25,8 +25,8 @@ class NGCF(GraphRecommender):
         maxEpoch = Epoch if Epoch else self.args.maxEpoch
         dev = model.embedding_dict['user_emb'].device
         for epoch in range(maxEpoch):
-            for n, batch in enumerate(next_batch_pairwise(self.data, self.args.batch_size)):
-                user_idx, pos_idx, neg_idx = (torch.tensor(x, dtype=torch.long, device=dev) for x in batch)
+            for n, batch in enumerate(self._epoch_batches(dev)):
+                user_idx, pos_idx, neg_idx = (torch.as_tensor(x, dtype=torch.long, device=dev) for x in batch)
                 model.train()
                 rec_user_emb, rec_item_emb = model()
                 user_emb, pos_item_emb, neg_item_emb = rec_user_emb[user_idx], rec_item_emb[pos_idx], rec_item_emb[neg_idx]

@@ -30,9 +30,9 @@ class SimGCL(GraphRecommender):
         maxEpoch = Epoch if Epoch else self.args.maxEpoch
         dev = model.embedding_dict['user_emb'].device
         for epoch in range(maxEpoch):
-            for n, batch in enumerate(next_batch_pairwise(self.data, self.args.batch_size)):
+            for n, batch in enumerate(self._epoch_batches(dev)):
                 user_idx, pos_idx, neg_idx = batch
-                ut, pt, nt = (torch.tensor(x, dtype=torch.long, device=dev) for x in batch)
+                ut, pt, nt = (torch.as_tensor(x, dtype=torch.long, device=dev) for x in batch)
                 model.train()
                 rec_user_emb, rec_item_emb = model()
                 user_emb, pos_item_emb, neg_item_emb = rec_user_emb[ut], rec_item_emb[pt], rec_item_emb[nt]

@@ -4,7 +4,7 @@
 agcf_spmm_csr_f32 (noise fused into the epilogue, the layer_cl view kept)."""
 import torch
 
-from ..encoder import TorchGraphInterface, XSimGCL_Encoder  # noqa: F401
+from ..encoder import TorchGraphInterface, XSimGCL_Encoder, unique_ids_like_reference  # noqa: F401
 from ..util.loss import InfoNCE, bpr_loss, l2_reg_loss
 from ..util.sampler import next_batch_pairwise
 from ._base import GraphRecommender
@@ -24,8 +24,7 @@ class XSimGCL(GraphRecommender):
     def cal_cl_loss(self, idx, user_view1, user_view2, item_view1, item_view2):
         """recommender/XSimGCL.py:39-44 (ids pass through float32 like torch.Tensor(list))"""
         dev = user_view1.device
-        u_idx = torch.unique(torch.Tensor(idx[0]).type(torch.long)).to(dev)
-        i_idx = torch.unique(torch.Tensor(idx[1]).type(torch.long)).to(dev)
+        u_idx, i_idx = unique_ids_like_reference(idx[0], dev), unique_ids_like_reference(idx[1], dev)
         return InfoNCE(user_view1[u_idx], user_view2[u_idx], self.temp) + \
             InfoNCE(item_view1[i_idx], item_view2[i_idx], self.temp)
 
@@ -39,9 +38,9 @@ class XSimGCL(GraphRecommender):
         maxEpoch = Epoch if Epoch else self.args.maxEpoch
         dev = model.embedding_dict['user_emb'].device
         for epoch in range(maxEpoch):
-            for n, batch in enumerate(next_batch_pairwise(self.data, self.args.batch_size)):
+            for n, batch in enumerate(self._epoch_batches(dev)):
                 user_idx, pos_idx, neg_idx = batch
-                ut, pt, nt = (torch.tensor(x, dtype=torch.long, device=dev) for x in batch)
+                ut, pt, nt = (torch.as_tensor(x, dtype=torch.long, device=dev) for x in batch)
                 model.train()
                 rec_user_emb, rec_item_emb, cl_user_emb, cl_item_emb = model(True)
                 user_emb, pos_item_emb, neg_item_emb = rec_user_emb[ut], rec_item_emb[pt], rec_item_emb[nt]

@@ -51,10 +51,45 @@ class GraphRecommender(object):
     def __getstate__(self):           # device mirrors are derived data: keep pickles / deepcopies lean
         st = dict(self.__dict__)
         st['_evaluator'] = None
+        st['_train_set'] = None
         return st
 
     def _sampler_mode(self):
         return str(getattr(self.args, 'sampler', os.environ.get('ARLIB_B200_SAMPLER', 'device'))).lower()
+
+    def _next_sample_epoch(self):
+        """Philox stream id of the next sampled epoch: keeps counting across train() calls on one instance (an
+        attack that retrains the same recommender must not see the same triples again, like the reference's
+        global Python RNG that simply keeps advancing)."""
+        k = getattr(self, '_epochs_sampled', 0)
+        self._epochs_sampled = k + 1
+        return k
+
+    def _epoch_batches(self, dev):
+        """The batches of one epoch for the reference-shaped training loops (caller's optimizer, gradient export,
+        NGCF / SimGCL / XSimGCL): ``(user_idx, pos_idx, neg_idx)`` as device LongTensors drawn by the on-device
+        Philox sampler (agcf_bpr_sample_epoch, util/sampler.py:4-30), or -- sampler mode 'host' -- the reference's
+        Python lists from util.sampler.next_batch_pairwise (same RNG consumption, in-place shuffle)."""
+        from ..engine import DeviceTrainSet
+        from ..util.sampler import next_batch_pairwise
+        B = self.args.batch_size
+        if self._sampler_mode() != 'device':
+            yield from next_batch_pairwise(self.data, B)
+            return
+        key = (id(self.data), len(self.data.training_data), self.data.user_num, self.data.item_num)
+        cached = getattr(self, '_train_set', None)
+        if cached is None or cached[0] != key:
+            cached = (key, DeviceTrainSet(self.data, dev))
+            self._train_set = cached
+        ts = cached[1]
+        n = ts.n_edges
+        u, i, j = (torch.empty(max(n, 1), dtype=torch.int32, device=dev) for _ in range(3))
+        seed = int(getattr(self.args, 'seed', 0) or 0)
+        ops.bpr_sample_epoch(ts.e_user, ts.e_item, ts.rej_rowptr, ts.rej_items, ts.n_items, seed,
+                             self._next_sample_epoch(), u, i, j)
+        u, i, j = u.long(), i.long(), j.long()
+        for lo in range(0, n, B):
+            yield u[lo:lo + B], i[lo:lo + B], j[lo:lo + B]
 
     # ------------------------------------------------------------------ reference API
     def save(self):

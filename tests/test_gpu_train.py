@@ -134,8 +134,9 @@ def test_dropin_general_path_external_optimizer_and_grad_export(golden_rows):
     assert fu.shape == (data.user_num, 64) and fi.requires_grad
 
 
+@pytest.mark.parametrize("sampler", ["host", "device"])
 @pytest.mark.parametrize("name", ["NGCF", "SimGCL", "XSimGCL"])
-def test_other_graph_recommenders_train_and_eval(name, golden_rows):
+def test_other_graph_recommenders_train_and_eval(name, sampler, golden_rows):
     """The three other drop-in classes run their reference loop on the agcf kernels:
     loss decreases, metrics improve over random, API shape holds."""
     import importlib
@@ -144,7 +145,7 @@ def test_other_graph_recommenders_train_and_eval(name, golden_rows):
     data = DataLoader.from_rows([list(r) for r in train[:20000]], (), test)
     random.seed(3); torch.manual_seed(3)
     cls = getattr(importlib.import_module("arlib_b200.recommender." + name), name)
-    rec = cls(_args(model_name=name, maxEpoch=2), data)
+    rec = cls(_args(model_name=name, maxEpoch=2, sampler=sampler), data)
     rec.train(evalNum=1)
     rec_list, measure = rec.test()
     assert len(rec_list) == len(data.test_set) and measure[0] == "Top 50\n"
