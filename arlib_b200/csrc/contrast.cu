@@ -1,0 +1,360 @@
+// contrast.cu -- InfoNCE contrastive loss of SimGCL / XSimGCL, forward and backward, on B200.
+//
+// Reference: util/loss.py:42-49
+//     view1, view2 = F.normalize(view1, dim=1), F.normalize(view2, dim=1)
+//     pos = exp(<v1_r, v2_r> / t);  ttl = sum_c exp(<v1_r, v2_c> / t);  loss = mean_r -log(pos_r / ttl_r)
+// called on the <= B unique users and <= B unique positive items of a batch
+// (recommender/SimGCL.py:212-219, XSimGCL.py:39-44).
+//
+// The n x n logit matrix is never written to memory: tiles of it are produced in registers, exponentiated and
+// reduced on the spot (forward: row sums; backward: P = exp(S)/ttl goes through shared memory straight into the
+// second product P.V).  fp32 CUDA cores on purpose: the logits are multiplied by 1/t = 5..10 and exponentiated, a
+// TF32 product (10-bit mantissa) would put ~1e-2 relative error on exp(S) -- outside the 1e-4 parity bar -- and the
+// whole problem is 2 x 2048^2 x 64 MACs (~10 us), nowhere near a tensor-pipe bound.
+// Work is split over (row tile) x (SPLIT slices of the reduced dimension); partial sums are combined in slice order
+// by a finishing kernel: deterministic, no floating-point atomics.
+#include "common.cuh"
+
+namespace agcf {
+
+constexpr int kNceThreads = 256;           // 16 x 16 thread grid per CTA
+
+template <int D>
+struct NceCfg {
+  static constexpr int TM = D <= 64 ? 64 : 32;      // vectors per tile (own side and reduced side)
+  static constexpr int RS = TM / 16;                // tile rows / cols per thread in the logit product
+  static constexpr int KS = D / 16;                 // embedding columns per thread in the second product
+  static constexpr int LD = D + 1;                  // padded row stride: conflict-free column walks
+  static constexpr int PLD = TM + 1;
+  static constexpr size_t smem_fwd = (size_t)(2 * TM * LD) * sizeof(float);
+  static constexpr size_t smem_bwd = (size_t)(2 * TM * LD + TM * PLD + 2 * TM) * sizeof(float);
+};
+
+// rows [row0, row0 + TM) of a [n, D] table into a padded shared tile (rows >= n are zero)
+template <int D>
+__device__ __forceinline__ void nce_load_tile(float* __restrict__ sm, const float* __restrict__ g, int row0, int n) {
+  using C = NceCfg<D>;
+  for (int idx = threadIdx.x; idx < C::TM * D; idx += kNceThreads) {
+    const int r = idx / D, k = idx - r * D;
+    sm[r * C::LD + k] = (row0 + r < n) ? __ldg(g + (size_t)(row0 + r) * D + k) : 0.f;
+  }
+}
+
+// s[a][b] = <own[ty + 16a], other[tx + 16b]>, k ascending
+template <int D>
+__device__ __forceinline__ void nce_logits(const float* __restrict__ own, const float* __restrict__ other, int ty, int tx,
+                                           float (&s)[NceCfg<D>::RS][NceCfg<D>::RS]) {
+  using C = NceCfg<D>;
+#pragma unroll
+  for (int a = 0; a < C::RS; ++a)
+#pragma unroll
+    for (int b = 0; b < C::RS; ++b) s[a][b] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < D; ++k) {
+    float av[C::RS], bv[C::RS];
+#pragma unroll
+    for (int a = 0; a < C::RS; ++a) av[a] = own[(ty + 16 * a) * C::LD + k];
+#pragma unroll
+    for (int b = 0; b < C::RS; ++b) bv[b] = other[(tx + 16 * b) * C::LD + k];
+#pragma unroll
+    for (int a = 0; a < C::RS; ++a)
+#pragma unroll
+      for (int b = 0; b < C::RS; ++b) s[a][b] = fmaf(av[a], bv[b], s[a][b]);
+  }
+}
+
+// ---------------------------------------------------------------- normalize
+// F.normalize(v, dim=1): v / max(||v||, 1e-12); one warp per row, both views in one launch
+__global__ void __launch_bounds__(256) nce_normalize_kernel(const float* __restrict__ v1, const float* __restrict__ v2,
+                                                            int n, int d, float* __restrict__ h1, float* __restrict__ h2,
+                                                            float* __restrict__ inv1, float* __restrict__ inv2) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= 2 * n) return;
+  const bool second = w >= n;
+  const int r = second ? w - n : w;
+  const float* v = (second ? v2 : v1) + (size_t)r * d;
+  float* h = (second ? h2 : h1) + (size_t)r * d;
+  float ss = 0.f;
+  for (int k = lane; k < d; k += 32) { const float x = __ldg(v + k); ss = fmaf(x, x, ss); }
+  ss = group_sum<32>(ss);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  for (int k = lane; k < d; k += 32) h[k] = __fdiv_rn(__ldg(v + k), nrm);
+  if (lane == 0) (second ? inv2 : inv1)[r] = __fdiv_rn(1.f, nrm);
+}
+
+// ------------------------------------------------------------------ forward
+// partial[sp][r] = sum over the column tiles of slice sp of exp(<h1_r, h2_c> / t)
+template <int D>
+__global__ void __launch_bounds__(kNceThreads) nce_rowsum_kernel(const float* __restrict__ h1, const float* __restrict__ h2,
+                                                                 int n, float inv_t, int split, float* __restrict__ partial) {
+  using C = NceCfg<D>;
+  extern __shared__ float sm[];
+  float* own = sm;
+  float* other = sm + C::TM * C::LD;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int row0 = blockIdx.x * C::TM, sp = blockIdx.y;
+  const int n_tiles = (n + C::TM - 1) / C::TM;
+  nce_load_tile<D>(own, h1, row0, n);
+  float rs[C::RS];
+#pragma unroll
+  for (int a = 0; a < C::RS; ++a) rs[a] = 0.f;
+  for (int ct = sp; ct < n_tiles; ct += split) {
+    __syncthreads();                                        // previous tile fully consumed (and `own` visible)
+    nce_load_tile<D>(other, h2, ct * C::TM, n);
+    __syncthreads();
+    float s[C::RS][C::RS];
+    nce_logits<D>(own, other, ty, tx, s);
+#pragma unroll
+    for (int a = 0; a < C::RS; ++a)
+#pragma unroll
+      for (int b = 0; b < C::RS; ++b)
+        if (ct * C::TM + tx + 16 * b < n) rs[a] += expf(s[a][b] * inv_t);
+  }
+#pragma unroll
+  for (int a = 0; a < C::RS; ++a) {
+    const float tot = group_sum<16>(rs[a]);                 // the 16 threads that share row ty + 16a
+    const int r = row0 + ty + 16 * a;
+    if (tx == 0 && r < n) partial[(size_t)sp * n + r] = tot;
+  }
+}
+
+// ttl_r = sum_sp partial (slice order); loss = mean_r -log(exp(<h1_r, h2_r>/t) / ttl_r); one CTA, fixed-order reduction
+__global__ void __launch_bounds__(1024) nce_loss_kernel(const float* __restrict__ h1, const float* __restrict__ h2, int n, int d,
+                                                        float inv_t, int split, const float* __restrict__ partial,
+                                                        float* __restrict__ ttl, float* __restrict__ loss) {
+  __shared__ double red[1024];
+  double mine = 0.0;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    float t = 0.f;
+    for (int sp = 0; sp < split; ++sp) t += partial[(size_t)sp * n + r];
+    ttl[r] = t;
+    float dot = 0.f;
+    for (int k = 0; k < d; ++k) dot = fmaf(h1[(size_t)r * d + k], h2[(size_t)r * d + k], dot);
+    const float pos = expf(dot * inv_t);
+    mine += (double)(-logf(__fdiv_rn(pos, t)));
+  }
+  red[threadIdx.x] = mine;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = (float)(red[0] / (double)n);
+}
+
+// ----------------------------------------------------------------- backward
+// SIDE 0: own = h1 rows r, reduced = h2 rows c:  acc_r = sum_c P_rc h2_c,  P_rc = exp(S_rc) / ttl_r
+// SIDE 1: own = h2 rows c, reduced = h1 rows r:  acc_c = sum_r P_rc h1_r  (ttl of the REDUCED index)
+// partial_acc[sp][own row][:] for the tiles of slice sp.
+template <int D, int SIDE>
+__global__ void __launch_bounds__(kNceThreads) nce_bwd_kernel(const float* __restrict__ h_own, const float* __restrict__ h_red,
+                                                              const float* __restrict__ ttl, int n, float inv_t, int split,
+                                                              float* __restrict__ partial_acc) {
+  using C = NceCfg<D>;
+  extern __shared__ float sm[];
+  float* own = sm;
+  float* other = own + C::TM * C::LD;
+  float* Ps = other + C::TM * C::LD;
+  float* ttl_own = Ps + C::TM * C::PLD;
+  float* ttl_red = ttl_own + C::TM;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int row0 = blockIdx.x * C::TM, sp = blockIdx.y;
+  const int n_tiles = (n + C::TM - 1) / C::TM;
+  nce_load_tile<D>(own, h_own, row0, n);
+  if (threadIdx.x < C::TM) ttl_own[threadIdx.x] = (row0 + (int)threadIdx.x < n) ? ttl[row0 + threadIdx.x] : 1.f;
+  float acc[C::RS][C::KS];
+#pragma unroll
+  for (int a = 0; a < C::RS; ++a)
+#pragma unroll
+    for (int b = 0; b < C::KS; ++b) acc[a][b] = 0.f;
+  for (int ct = sp; ct < n_tiles; ct += split) {
+    __syncthreads();                                        // previous tile (other, Ps) fully consumed
+    nce_load_tile<D>(other, h_red, ct * C::TM, n);
+    if (threadIdx.x < C::TM) ttl_red[threadIdx.x] = (ct * C::TM + (int)threadIdx.x < n) ? ttl[ct * C::TM + threadIdx.x] : 1.f;
+    __syncthreads();
+    float s[C::RS][C::RS];
+    nce_logits<D>(own, other, ty, tx, s);
+#pragma unroll
+    for (int a = 0; a < C::RS; ++a)
+#pragma unroll
+      for (int b = 0; b < C::RS; ++b) {
+        const int o = ty + 16 * a, x = tx + 16 * b;
+        const float den = SIDE == 0 ? ttl_own[o] : ttl_red[x];
+        Ps[o * C::PLD + x] = (ct * C::TM + x < n) ? __fdiv_rn(expf(s[a][b] * inv_t), den) : 0.f;
+      }
+    __syncthreads();
+    // acc[o][k] += sum_x P[o][x] * other[x][k];  thread (ty, tx) owns o = ty + 16a, k = tx + 16b
+    for (int x = 0; x < C::TM; ++x) {
+      float pv[C::RS], ov[C::KS];
+#pragma unroll
+      for (int a = 0; a < C::RS; ++a) pv[a] = Ps[(ty + 16 * a) * C::PLD + x];
+#pragma unroll
+      for (int b = 0; b < C::KS; ++b) ov[b] = other[x * C::LD + tx + 16 * b];
+#pragma unroll
+      for (int a = 0; a < C::RS; ++a)
+#pragma unroll
+        for (int b = 0; b < C::KS; ++b) acc[a][b] = fmaf(pv[a], ov[b], acc[a][b]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < C::RS; ++a) {
+    const int r = row0 + ty + 16 * a;
+    if (r >= n) continue;
+#pragma unroll
+    for (int b = 0; b < C::KS; ++b) partial_acc[((size_t)sp * n + r) * D + tx + 16 * b] = acc[a][b];
+  }
+}
+
+// d_hat = coef * (sum_sp partial_acc - partner_hat), coef = g / (n t);  through F.normalize:
+// d_v = (d_hat - h <h, d_hat>) / max(||v||, eps).  One warp per row.
+__global__ void __launch_bounds__(256) nce_bwd_finish_kernel(const float* __restrict__ partial_acc, int split,
+                                                             const float* __restrict__ h, const float* __restrict__ partner,
+                                                             const float* __restrict__ inv_norm, const float* __restrict__ g_loss,
+                                                             float scale, int n, int d, float* __restrict__ grad) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float coef = __ldg(g_loss) * scale;
+  float dh[8];                                               // d <= 256: up to 8 columns per lane
+  float dot = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int k = lane + 32 * q;
+    dh[q] = 0.f;
+    if (k < d) {
+      float a = 0.f;
+      for (int sp = 0; sp < split; ++sp) a += partial_acc[((size_t)sp * n + r) * d + k];
+      dh[q] = coef * (a - partner[(size_t)r * d + k]);
+      dot = fmaf(h[(size_t)r * d + k], dh[q], dot);
+    }
+  }
+  dot = group_sum<32>(dot);
+  const float inv = inv_norm[r];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int k = lane + 32 * q;
+    if (k < d) grad[(size_t)r * d + k] = (dh[q] - h[(size_t)r * d + k] * dot) * inv;
+  }
+}
+
+// workspace layout (floats): h1 [n,d] | h2 [n,d] | inv1 [n] | inv2 [n] | ttl [n] | partial [split,n] | acc [split,n,d]
+struct NceWs {
+  float *h1, *h2, *inv1, *inv2, *ttl, *partial, *acc;
+  int split;
+};
+
+static int nce_tile(int d) { return d <= 64 ? 64 : 32; }
+
+static int nce_split(int n, int d) {
+  const int nt = (n + nce_tile(d) - 1) / nce_tile(d);
+  int s = (2 * kSMs + nt - 1) / nt;                          // ~2 CTAs per SM in flight
+  s = s < 1 ? 1 : s;
+  s = s > nt ? nt : s;
+  return s > 16 ? 16 : s;
+}
+
+static int64_t nce_ws_floats(int n, int d) {
+  const int64_t s = nce_split(n, d);
+  return 2ll * n * d + 3ll * n + s * n + s * (int64_t)n * d + 16;
+}
+
+static NceWs nce_carve(void* ws, int n, int d) {
+  NceWs w;
+  float* p = reinterpret_cast<float*>(ws);
+  w.split = nce_split(n, d);
+  w.h1 = p; p += (size_t)n * d;
+  w.h2 = p; p += (size_t)n * d;
+  w.inv1 = p; p += n;
+  w.inv2 = p; p += n;
+  w.ttl = p; p += n;
+  w.partial = p; p += (size_t)w.split * n;
+  w.acc = p;
+  return w;
+}
+
+template <int D>
+static int nce_forward_d(const float* v1, const float* v2, int n, float inv_t, float* loss, const NceWs& w, cudaStream_t st) {
+  using C = NceCfg<D>;
+  static thread_local bool attr = false;
+  if (!attr) {
+    AGCF_CUDA_OK(cudaFuncSetAttribute(nce_rowsum_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_fwd));
+    attr = true;
+  }
+  nce_normalize_kernel<<<(2 * n * 32 + 255) / 256, 256, 0, st>>>(v1, v2, n, D, w.h1, w.h2, w.inv1, w.inv2);
+  AGCF_LAUNCH_OK();
+  const dim3 grid((n + C::TM - 1) / C::TM, w.split);
+  nce_rowsum_kernel<D><<<grid, kNceThreads, C::smem_fwd, st>>>(w.h1, w.h2, n, inv_t, w.split, w.partial);
+  AGCF_LAUNCH_OK();
+  nce_loss_kernel<<<1, 1024, 0, st>>>(w.h1, w.h2, n, D, inv_t, w.split, w.partial, w.ttl, loss);
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+template <int D>
+static int nce_backward_d(int n, float inv_t, const float* g_loss, const NceWs& w, float* g1, float* g2, cudaStream_t st) {
+  using C = NceCfg<D>;
+  static thread_local bool attr = false;
+  if (!attr) {
+    AGCF_CUDA_OK(cudaFuncSetAttribute(nce_bwd_kernel<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bwd));
+    AGCF_CUDA_OK(cudaFuncSetAttribute(nce_bwd_kernel<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_bwd));
+    attr = true;
+  }
+  const dim3 grid((n + C::TM - 1) / C::TM, w.split);
+  const float scale = inv_t / (float)n;
+  const unsigned fin_blocks = (unsigned)(((long long)n * 32 + 255) / 256);
+  if (g1 != nullptr) {
+    nce_bwd_kernel<D, 0><<<grid, kNceThreads, C::smem_bwd, st>>>(w.h1, w.h2, w.ttl, n, inv_t, w.split, w.acc);
+    AGCF_LAUNCH_OK();
+    nce_bwd_finish_kernel<<<fin_blocks, 256, 0, st>>>(w.acc, w.split, w.h1, w.h2, w.inv1, g_loss, scale, n, D, g1);
+    AGCF_LAUNCH_OK();
+  }
+  if (g2 != nullptr) {
+    nce_bwd_kernel<D, 1><<<grid, kNceThreads, C::smem_bwd, st>>>(w.h2, w.h1, w.ttl, n, inv_t, w.split, w.acc);
+    AGCF_LAUNCH_OK();
+    nce_bwd_finish_kernel<<<fin_blocks, 256, 0, st>>>(w.acc, w.split, w.h2, w.h1, w.inv2, g_loss, scale, n, D, g2);
+    AGCF_LAUNCH_OK();
+  }
+  return AGCF_OK;
+}
+
+}  // namespace agcf
+
+using namespace agcf;
+
+extern "C" int64_t agcf_infonce_ws_bytes(int32_t n, int32_t d) {
+  if (n <= 0 || !supported_d(d)) return n == 0 ? 64 : AGCF_EUNSUPPORTED;
+  return nce_ws_floats(n, d) * (int64_t)sizeof(float);
+}
+
+extern "C" int agcf_infonce_forward(const float* view1, const float* view2, int32_t n, int32_t d, float temperature,
+                                    float* loss, void* ws, int64_t ws_bytes, agcf_stream_t stream) {
+  if (!view1 || !view2 || !loss || !ws || n <= 0 || !(temperature > 0.f)) return AGCF_EINVAL;
+  if (!supported_d(d)) return AGCF_EUNSUPPORTED;
+  if (ws_bytes < agcf_infonce_ws_bytes(n, d)) return AGCF_EWORKSPACE;
+  const NceWs w = nce_carve(ws, n, d);
+  const float inv_t = 1.f / temperature;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d) {
+    case 32: return nce_forward_d<32>(view1, view2, n, inv_t, loss, w, st);
+    case 64: return nce_forward_d<64>(view1, view2, n, inv_t, loss, w, st);
+    case 128: return nce_forward_d<128>(view1, view2, n, inv_t, loss, w, st);
+    case 256: return nce_forward_d<256>(view1, view2, n, inv_t, loss, w, st);
+  }
+  return AGCF_EUNSUPPORTED;
+}
+
+extern "C" int agcf_infonce_backward(int32_t n, int32_t d, float temperature, const float* grad_loss, void* ws,
+                                     int64_t ws_bytes, float* grad_view1, float* grad_view2, agcf_stream_t stream) {
+  if (!grad_loss || !ws || n <= 0 || !(temperature > 0.f) || (!grad_view1 && !grad_view2)) return AGCF_EINVAL;
+  if (!supported_d(d)) return AGCF_EUNSUPPORTED;
+  if (ws_bytes < agcf_infonce_ws_bytes(n, d)) return AGCF_EWORKSPACE;
+  const NceWs w = nce_carve(ws, n, d);
+  const float inv_t = 1.f / temperature;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d) {
+    case 32: return nce_backward_d<32>(n, inv_t, grad_loss, w, grad_view1, grad_view2, st);
+    case 64: return nce_backward_d<64>(n, inv_t, grad_loss, w, grad_view1, grad_view2, st);
+    case 128: return nce_backward_d<128>(n, inv_t, grad_loss, w, grad_view1, grad_view2, st);
+    case 256: return nce_backward_d<256>(n, inv_t, grad_loss, w, grad_view1, grad_view2, st);
+  }
+  return AGCF_EUNSUPPORTED;
+}

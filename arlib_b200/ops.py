@@ -195,6 +195,34 @@ def zero_rows(seg_node, n_seg, max_seg, G):
                                   _lib.stream_ptr()), "agcf_zero_rows")
 
 
+def infonce_forward(view1, view2, temperature):
+    """agcf_infonce_forward -> (loss [1] fp32, workspace) ; the workspace feeds infonce_backward."""
+    lib = _lib.load()
+    _f32(view1, "view1"); _f32(view2, "view2")
+    if view1.shape != view2.shape or view1.dim() != 2:
+        raise ValueError("views must be two [n, d] tensors of equal shape")
+    n, d = view1.shape
+    need = int(lib.agcf_infonce_ws_bytes(n, d))
+    if need < 0:
+        _lib.check(need, "agcf_infonce_ws_bytes")
+    ws = torch.empty(need, dtype=torch.uint8, device=view1.device)
+    loss = torch.empty(1, dtype=torch.float32, device=view1.device)
+    _lib.check(lib.agcf_infonce_forward(view1.data_ptr(), view2.data_ptr(), n, d, float(temperature), loss.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "agcf_infonce_forward")
+    return loss, ws
+
+
+def infonce_backward(n, d, temperature, grad_loss, ws, need1=True, need2=True):
+    """agcf_infonce_backward -> (d loss / d view1, d loss / d view2)."""
+    lib = _lib.load()
+    _f32(grad_loss, "grad_loss")
+    g1 = torch.empty((n, d), dtype=torch.float32, device=ws.device) if need1 else None
+    g2 = torch.empty((n, d), dtype=torch.float32, device=ws.device) if need2 else None
+    _lib.check(lib.agcf_infonce_backward(n, d, float(temperature), grad_loss.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _p(g1), _p(g2), _lib.stream_ptr()), "agcf_infonce_backward")
+    return g1, g2
+
+
 def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0, step_dev=None, peer_p=None, mc_p=None):
     lib = _lib.load()
     _f32(p, "p"); _f32(g, "g"); _f32(m, "m"); _f32(v, "v")

@@ -25,8 +25,33 @@ def l2_reg_loss(reg, *args):
     return total * reg
 
 
+class _InfoNCE(torch.autograd.Function):
+    """agcf_infonce_forward / agcf_infonce_backward as one differentiable op."""
+
+    @staticmethod
+    def forward(ctx, view1, view2, temperature):
+        from .. import ops
+        loss, ws = ops.infonce_forward(view1, view2, temperature)
+        ctx.ws, ctx.shape, ctx.temperature = ws, tuple(view1.shape), float(temperature)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, grad):
+        from .. import ops
+        n, d = ctx.shape
+        g = grad.detach().to(torch.float32).reshape(1).contiguous()
+        g1, g2 = ops.infonce_backward(n, d, ctx.temperature, g, ctx.ws, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return g1, g2, None
+
+
 def InfoNCE(view1, view2, temperature):
-    """util/loss.py:42-49"""
+    """util/loss.py:42-49.  CUDA fp32 views (what SimGCL / XSimGCL.cal_cl_loss pass) run the fused kernels of
+    csrc/contrast.cu -- the n x n logit matrix never reaches memory -- and raise if the library is missing; tensors a
+    caller keeps on the CPU are evaluated with the reference's own torch expression."""
+    if view1.is_cuda and view1.shape[0] > 0:
+        v1 = view1.to(torch.float32).contiguous()
+        v2 = view2.to(torch.float32).contiguous()
+        return _InfoNCE.apply(v1, v2, float(temperature))
     view1, view2 = F.normalize(view1, dim=1), F.normalize(view2, dim=1)
     pos = torch.exp((view1 * view2).sum(dim=-1) / temperature)
     ttl = torch.exp(torch.matmul(view1, view2.transpose(0, 1)) / temperature).sum(dim=1)

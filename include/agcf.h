@@ -235,6 +235,22 @@ int agcf_bpr_backward(const float* F, const int32_t* u, const int32_t* i, const 
 int agcf_zero_rows(const int32_t* seg_node, const int32_t* n_seg, int32_t max_seg,
                    float* G, int32_t d, agcf_stream_t stream);
 
+/* ---------------------------------------------------------------- contrastive loss
+ * InfoNCE between two views [n, d] of the same n rows (util/loss.py:42-49; callers recommender/SimGCL.py:212-219,
+ * XSimGCL.py:39-44 with the batch's unique users / positive items, n <= batch size):
+ *   h = v / max(||v||, 1e-12) per row;  S = h1 h2^T / temperature;
+ *   loss[0] = mean_r -log( exp(S_rr) / sum_c exp(S_rc) )        (no max-subtraction, like the reference)
+ * The n x n logits never reach memory (tiles in registers / shared memory, fp32 CUDA cores: a TF32 product would
+ * put ~1e-2 relative error on exp(S)).  `ws` (agcf_infonce_ws_bytes(n, d) bytes) receives the normalized views, the
+ * row sums and scratch; agcf_infonce_backward takes the SAME workspace, untouched since the forward call, and
+ * writes d loss / d view1, d loss / d view2 ([n, d], either nullable) scaled by grad_loss[0] (device scalar).
+ * Deterministic (partials combined in a fixed order).  d in {32, 64, 128, 256}. */
+int64_t agcf_infonce_ws_bytes(int32_t n, int32_t d);
+int agcf_infonce_forward(const float* view1, const float* view2, int32_t n, int32_t d, float temperature,
+                         float* loss, void* ws, int64_t ws_bytes, agcf_stream_t stream);
+int agcf_infonce_backward(int32_t n, int32_t d, float temperature, const float* grad_loss, void* ws, int64_t ws_bytes,
+                          float* grad_view1, float* grad_view2, agcf_stream_t stream);
+
 /* ------------------------------------------------------------------ optimizer
  * torch.optim.Adam step (defaults: amsgrad=False, weight_decay=0, maximize=False)
  * over n contiguous fp32 elements:

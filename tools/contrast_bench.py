@@ -1,0 +1,56 @@
+"""BASELINE.json configs[2]: SimGCL / XSimGCL (noise-perturbed propagation + InfoNCE) on a synthetic
+Yelp2018-shaped graph, through the drop-in recommender classes (reference training loop, torch.optim.Adam,
+agcf SpMM forward/backward with the noise fused, fused InfoNCE kernels, on-device Philox sampler).
+Prints one JSON line per model: ms per training step and triples/s over N timed batches, + full-rank eval."""
+import json, os, sys, time, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+
+from arlib_b200.util.DataLoader import DataLoader
+from arlib_b200.util.synth import SHAPES, synth_edges
+
+name = sys.argv[1] if len(sys.argv) > 1 else "yelp2018"
+n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+models = sys.argv[3].split(",") if len(sys.argv) > 3 else ["XSimGCL", "SimGCL", "NGCF", "LightGCN"]
+U, I, E = SHAPES[name]
+tu, ti, su, si = synth_edges(U, I, E, 0.5, 0.5, 0)
+t0 = time.perf_counter()
+data = DataLoader.from_arrays(tu, ti, su, si, name=name)
+t_load = time.perf_counter() - t0
+dev = torch.device("cuda:0")
+
+for model in models:
+    import importlib
+    cls = getattr(importlib.import_module("arlib_b200.recommender." + model), model)
+    args = types.SimpleNamespace(topK="50", emb_size=64, n_layers=2, batch_size=2048, lRate=0.005, reg=1e-4, maxEpoch=1,
+                                 seed=2018, sampler="device", model_name=model)
+    torch.manual_seed(2018)
+    rec = cls(args, data)
+    m = rec.model.cuda()
+    opt = torch.optim.Adam(m.parameters(), lr=args.lRate)
+    # time N steps of the class's own epoch loop by cutting the batch generator short
+    orig = rec._epoch_batches
+    times = {}
+
+    def limited(dev_, n=n_steps + 5):
+        for k, b in enumerate(orig(dev_)):
+            if k == 5:
+                torch.cuda.synchronize(); times["t0"] = time.perf_counter()
+            if k >= n:
+                break
+            yield b
+        torch.cuda.synchronize(); times["t1"] = time.perf_counter()
+
+    rec._epoch_batches = limited
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        rec.train(Epoch=1, optimizer=opt, evalNum=1)
+    step_ms = (times["t1"] - times["t0"]) / n_steps * 1e3
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        rec_list, measure = rec.test()
+    torch.cuda.synchronize(); t_test = time.perf_counter() - t0
+    print(json.dumps({"workload": name, "model": model, "U": U, "I": I, "E": E, "batch": 2048, "steps_timed": n_steps,
+                      "ms_per_step": step_ms, "triples_per_s": 2048 / (step_ms * 1e-3),
+                      "test_s": t_test, "test_users": len(data.test_set), "dataloader_s": t_load,
+                      "measure": [x.strip() for x in measure]}), flush=True)
