@@ -36,7 +36,7 @@ def test_infonce_forward_backward_match_the_reference_expression(n, d, tau):
     assert abs(float(got) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
     for g_, r_ in ((ag.grad.cpu(), ar.grad), (bg.grad.cpu(), br.grad)):
         scale = float(r_.abs().max()) + 1e-30
-        assert float((g_ - r_).abs().max()) <= 1e-4 * scale + 1e-9
+        assert float((g_ - r_).abs().max()) <= 1e-4 * scale + 1e-7
 
 
 def test_infonce_small_norm_rows_and_determinism():

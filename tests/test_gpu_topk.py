@@ -231,3 +231,35 @@ def test_attack_metric_matches_reference_formulas():
             np.testing.assert_allclose(got, ref[name], rtol=1e-12, atol=0)
     with pytest.raises(TypeError):
         AttackMetric(types.SimpleNamespace(data=rec.data, user_emb=ue.cpu(), item_emb=ie.cpu()), targets).precision()
+
+
+def test_masked_score_topk_equals_the_attacks_dense_topk():
+    """attack/White/CLeaR.py:75-81 -- dense scores, interaction entries := -10e8, torch.topk."""
+    import scipy.sparse as sp
+    from arlib_b200.util.algorithm import masked_score_topk
+    rng = np.random.default_rng(4)
+    U, I, d, K = 500, 1300, 64, 50
+    Pu = torch.from_numpy(rng.standard_normal((U, d)).astype(np.float32))
+    Pi = torch.from_numpy(rng.standard_normal((I, d)).astype(np.float32))
+    inter = sp.random(U, I, density=0.05, random_state=1, format="lil", dtype=np.float32)
+    inter[3, :] = 1.0                                  # a user with everything masked
+    inter[4, :I - 7] = 1.0                             # fewer free items than K
+    inter = inter.tocsr()
+    inter.data[::11] = 0.0                             # explicitly stored zeros are NOT masked (.nonzero())
+    scores = Pu.double() @ Pi.double().T
+    nz = inter.nonzero()
+    scores[nz[0], nz[1]] = -10e8
+    ref_v, ref_i = torch.topk(scores, K)
+    vals, idx = masked_score_topk(Pu.cuda(), Pi.cuda(), K, inter)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (U, K)
+    idx, vals = idx.cpu(), vals.cpu()
+    for u in range(U):
+        if u == 3:
+            assert bool((vals[u] == -10e8).all())
+            continue
+        assert_topk_matches(idx[u].numpy(), scores[u].numpy(), K, 1e-4)
+        free = int((ref_v[u] > -1e8).sum())
+        np.testing.assert_allclose(vals[u, :free].numpy(), ref_v[u, :free].numpy(), rtol=1e-5, atol=1e-5)
+    vals2, idx2 = masked_score_topk(Pu.cuda(), Pi.cuda(), K, None)
+    ref_v2, _ = torch.topk(Pu.double() @ Pi.double().T, K)
+    np.testing.assert_allclose(vals2.cpu().numpy(), ref_v2.numpy(), rtol=1e-5, atol=1e-5)
