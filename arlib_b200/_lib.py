@@ -30,6 +30,7 @@ class SpmmArgs(ctypes.Structure):
         ("X", P), ("Y", P), ("addend", P),
         ("acc_in", P), ("acc_out", P), ("acc_div", F32),
         ("noise", P), ("eps", F32),
+        ("noise_seed", U64), ("noise_stream", ctypes.c_uint32), ("noise_step", P),
         ("row_mask", P), ("col_mask", P),
         ("peer_Y_host", P), ("peer_acc_host", P), ("n_peers", I32),
         ("mc_Y", P), ("mc_acc", P),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "agcf_concat_rows_f32": (c_int32, [P, I64, P, I64, P, I32, P]),
     "agcf_bpr_sample_epoch": (c_int32, [P, P, I32, P, P, I32, U64, U64, P, P, P, P]),
     "agcf_bpr_group_batches": (c_int32, [P, P, P, I32, I32, I32, P, P, P, P, I32, P, P]),
+    "agcf_bpr_cl_ids": (c_int32, [P, P, P, P, I32, I32, I32, P, P, P, P]),
     "agcf_bpr_ws_bytes": (c_int64, [I32]),
     "agcf_bpr_forward": (c_int32, [P, P, P, P, I32, I32, I32, F32, P, P, P, P]),
     "agcf_bpr_xchg_bytes": (c_int64, [I32]),
@@ -67,8 +69,8 @@ SIGNATURES = {
     "agcf_bpr_backward": (c_int32, [P, P, P, P, I32, I32, I32, F32, F32, P, P, P, P, P, P, P, P]),
     "agcf_zero_rows": (c_int32, [P, P, I32, P, I32, P]),
     "agcf_infonce_ws_bytes": (c_int64, [I32, I32]),
-    "agcf_infonce_forward": (c_int32, [P, P, I32, I32, F32, P, P, I64, P]),
-    "agcf_infonce_backward": (c_int32, [I32, I32, F32, P, P, I64, P, P, P]),
+    "agcf_infonce_forward": (c_int32, [P, P, P, I32, P, I32, F32, P, P, I64, P]),
+    "agcf_infonce_backward": (c_int32, [I32, P, I32, F32, P, F32, P, I64, P, P, I32, P, P, I32, P]),
     "agcf_adam_step_f32": (c_int32, [P, P, P, P, I64, F32, F32, F32, F32, I32, P, P, I32, P, P]),
     "agcf_increment_i32": (c_int32, [P, P]),
     "agcf_score_topk_ws_bytes": (c_int64, [I32, I32, I32, I32]),

@@ -481,6 +481,70 @@ __global__ void adam_coefs_kernel(int32_t* step_dev, int increment, float lr, fl
   coefs[1] = (float)sqrt(bc2);
 }
 
+// ==================================================== contrastive-loss id lists (SimGCL / XSimGCL)
+// torch.unique of the batch's users and of its POSITIVE items (recommender/SimGCL.py:213-214, XSimGCL.py:40-41) from
+// the grouping of agcf_bpr_group_batches: the distinct nodes are already sorted; a user node is any node < n_users, an
+// item node counts if its first occurrence id (occurrences are sorted inside a segment) is a positive one
+// (nb <= k < 2 nb).  One CTA per batch, ordered compaction by block scan; ids are TABLE rows (items: n_users + item).
+__global__ void __launch_bounds__(1024) bpr_cl_ids_kernel(const int32_t* __restrict__ occ, const int32_t* __restrict__ seg_off,
+                                                          const int32_t* __restrict__ seg_node, const int32_t* __restrict__ n_seg,
+                                                          int n_triples, int batch, int n_users,
+                                                          int32_t* __restrict__ cl_users, int32_t* __restrict__ cl_items,
+                                                          int32_t* __restrict__ n_cl) {
+  __shared__ int warp_u[32], warp_i[32];
+  const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nb = min(batch, n_triples - b * batch);
+  const int32_t* occ_b = occ + (size_t)b * 3 * batch;
+  const int32_t* off_b = seg_off + (size_t)b * (3 * batch + 1);
+  const int32_t* node_b = seg_node + (size_t)b * 3 * batch;
+  const int n = n_seg[b];
+  const int per = (n + nthr - 1) / nthr;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  auto kind = [&](int s) {                                    // 0 user, 1 positive item, 2 neither
+    if (node_b[s] < n_users) return 0;
+    return occ_b[off_b[s]] < 2 * nb ? 1 : 2;
+  };
+  int cu = 0, ci = 0;
+  for (int s = lo; s < hi; ++s) {
+    const int k = kind(s);
+    cu += k == 0;
+    ci += k == 1;
+  }
+  int iu = cu, ii = ci;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int yu = __shfl_up_sync(0xffffffffu, iu, o);
+    const int yi = __shfl_up_sync(0xffffffffu, ii, o);
+    if (lane >= o) { iu += yu; ii += yi; }
+  }
+  if (lane == 31) { warp_u[warp] = iu; warp_i[warp] = ii; }
+  __syncthreads();
+  if (warp == 0) {
+    const int wu = lane < (nthr >> 5) ? warp_u[lane] : 0;
+    const int wi = lane < (nthr >> 5) ? warp_i[lane] : 0;
+    int su = wu, si = wi;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int yu = __shfl_up_sync(0xffffffffu, su, o);
+      const int yi = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) { su += yu; si += yi; }
+    }
+    warp_u[lane] = su - wu;
+    warp_i[lane] = si - wi;
+    if (lane == 31) { n_cl[2 * b] = su; n_cl[2 * b + 1] = si; }
+  }
+  __syncthreads();
+  int pu = warp_u[warp] + iu - cu, pi = warp_i[warp] + ii - ci;
+  int32_t* out_u = cl_users + (size_t)b * batch;
+  int32_t* out_i = cl_items + (size_t)b * batch;
+  for (int s = lo; s < hi; ++s) {
+    const int k = kind(s);
+    if (k == 0) out_u[pu++] = node_b[s];
+    else if (k == 1) out_i[pi++] = node_b[s];
+  }
+}
+
 }  // namespace agcf
 
 using namespace agcf;
@@ -521,6 +585,19 @@ extern "C" int agcf_bpr_group_batches(const int32_t* u, const int32_t* i, const 
   const unsigned blocks = (unsigned)((n_triples + batch - 1) / batch);
   bpr_group_kernel<<<blocks, 1024, smem, (cudaStream_t)stream>>>(u, i, j, n_triples, batch, n_users, pow2,
                                                                  occ, seg_off, seg_node, n_seg, (n_nodes + 31) / 32, node_mask);
+  AGCF_LAUNCH_OK();
+  return AGCF_OK;
+}
+
+extern "C" int agcf_bpr_cl_ids(const int32_t* occ, const int32_t* seg_off, const int32_t* seg_node, const int32_t* n_seg,
+                               int32_t n_triples, int32_t batch, int32_t n_users,
+                               int32_t* cl_users, int32_t* cl_items, int32_t* n_cl, agcf_stream_t stream) {
+  if (!occ || !seg_off || !seg_node || !n_seg || !cl_users || !cl_items || !n_cl) return AGCF_EINVAL;
+  if (n_triples < 0 || batch <= 0 || n_users < 0 || 3 * (long long)batch > 16384) return AGCF_EINVAL;
+  if (n_triples == 0) return AGCF_OK;
+  const unsigned blocks = (unsigned)((n_triples + batch - 1) / batch);
+  bpr_cl_ids_kernel<<<blocks, 1024, 0, (cudaStream_t)stream>>>(occ, seg_off, seg_node, n_seg, n_triples, batch, n_users,
+                                                               cl_users, cl_items, n_cl);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
 }

@@ -65,14 +65,25 @@ __device__ __forceinline__ void nce_logits(const float* __restrict__ own, const 
 
 // ---------------------------------------------------------------- normalize
 // F.normalize(v, dim=1): v / max(||v||, 1e-12); one warp per row, both views in one launch
+// rows: nullable gather list (row r of the view is row rows[r] of the table); n_dev: nullable device row count
+__device__ __forceinline__ int nce_rows(int n_max, const int32_t* __restrict__ n_dev) {
+  if (n_dev == nullptr) return n_max;
+  const int n = __ldg(n_dev);
+  return n < n_max ? n : n_max;
+}
+
 __global__ void __launch_bounds__(256) nce_normalize_kernel(const float* __restrict__ v1, const float* __restrict__ v2,
-                                                            int n, int d, float* __restrict__ h1, float* __restrict__ h2,
+                                                            const int32_t* __restrict__ rows, int n_max,
+                                                            const int32_t* __restrict__ n_dev, int d,
+                                                            float* __restrict__ h1, float* __restrict__ h2,
                                                             float* __restrict__ inv1, float* __restrict__ inv2) {
+  const int n = nce_rows(n_max, n_dev);
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= 2 * n) return;
   const bool second = w >= n;
   const int r = second ? w - n : w;
-  const float* v = (second ? v2 : v1) + (size_t)r * d;
+  const size_t src = rows != nullptr ? (size_t)__ldg(rows + r) : (size_t)r;
+  const float* v = (second ? v2 : v1) + src * d;
   float* h = (second ? h2 : h1) + (size_t)r * d;
   float ss = 0.f;
   for (int k = lane; k < d; k += 32) { const float x = __ldg(v + k); ss = fmaf(x, x, ss); }
@@ -86,13 +97,16 @@ __global__ void __launch_bounds__(256) nce_normalize_kernel(const float* __restr
 // partial[sp][r] = sum over the column tiles of slice sp of exp(<h1_r, h2_c> / t)
 template <int D>
 __global__ void __launch_bounds__(kNceThreads) nce_rowsum_kernel(const float* __restrict__ h1, const float* __restrict__ h2,
-                                                                 int n, float inv_t, int split, float* __restrict__ partial) {
+                                                                 int n_max, const int32_t* __restrict__ n_dev, float inv_t,
+                                                                 int split, float* __restrict__ partial) {
   using C = NceCfg<D>;
   extern __shared__ float sm[];
   float* own = sm;
   float* other = sm + C::TM * C::LD;
+  const int n = nce_rows(n_max, n_dev);
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const int row0 = blockIdx.x * C::TM, sp = blockIdx.y;
+  if (row0 >= n) return;
   const int n_tiles = (n + C::TM - 1) / C::TM;
   nce_load_tile<D>(own, h1, row0, n);
   float rs[C::RS];
@@ -114,19 +128,23 @@ __global__ void __launch_bounds__(kNceThreads) nce_rowsum_kernel(const float* __
   for (int a = 0; a < C::RS; ++a) {
     const float tot = group_sum<16>(rs[a]);                 // the 16 threads that share row ty + 16a
     const int r = row0 + ty + 16 * a;
-    if (tx == 0 && r < n) partial[(size_t)sp * n + r] = tot;
+    if (tx == 0 && r < n) partial[(size_t)sp * n_max + r] = tot;
   }
 }
 
 // ttl_r = sum_sp partial (slice order); loss = mean_r -log(exp(<h1_r, h2_r>/t) / ttl_r); one CTA, fixed-order reduction
-__global__ void __launch_bounds__(1024) nce_loss_kernel(const float* __restrict__ h1, const float* __restrict__ h2, int n, int d,
+__global__ void __launch_bounds__(1024) nce_loss_kernel(const float* __restrict__ h1, const float* __restrict__ h2, int n_max,
+                                                        const int32_t* __restrict__ n_dev, int d,
                                                         float inv_t, int split, const float* __restrict__ partial,
                                                         float* __restrict__ ttl, float* __restrict__ loss) {
   __shared__ double red[1024];
+  const int n = nce_rows(n_max, n_dev);
   double mine = 0.0;
   for (int r = threadIdx.x; r < n; r += blockDim.x) {
     float t = 0.f;
-    for (int sp = 0; sp < split; ++sp) t += partial[(size_t)sp * n + r];
+    // slices beyond the row tiles that exist at this n hold nothing for row r only if the slice had no column
+    // tile: every slice sp < split writes all rows < n (possibly 0), see nce_rowsum_kernel
+    for (int sp = 0; sp < split; ++sp) t += partial[(size_t)sp * n_max + r];
     ttl[r] = t;
     float dot = 0.f;
     for (int k = 0; k < d; ++k) dot = fmaf(h1[(size_t)r * d + k], h2[(size_t)r * d + k], dot);
@@ -139,7 +157,7 @@ __global__ void __launch_bounds__(1024) nce_loss_kernel(const float* __restrict_
     if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *loss = (float)(red[0] / (double)n);
+  if (threadIdx.x == 0) *loss = n > 0 ? (float)(red[0] / (double)n) : 0.f;
 }
 
 // ----------------------------------------------------------------- backward
@@ -148,7 +166,8 @@ __global__ void __launch_bounds__(1024) nce_loss_kernel(const float* __restrict_
 // partial_acc[sp][own row][:] for the tiles of slice sp.
 template <int D, int SIDE>
 __global__ void __launch_bounds__(kNceThreads) nce_bwd_kernel(const float* __restrict__ h_own, const float* __restrict__ h_red,
-                                                              const float* __restrict__ ttl, int n, float inv_t, int split,
+                                                              const float* __restrict__ ttl, int n_max,
+                                                              const int32_t* __restrict__ n_dev, float inv_t, int split,
                                                               float* __restrict__ partial_acc) {
   using C = NceCfg<D>;
   extern __shared__ float sm[];
@@ -157,8 +176,10 @@ __global__ void __launch_bounds__(kNceThreads) nce_bwd_kernel(const float* __res
   float* Ps = other + C::TM * C::LD;
   float* ttl_own = Ps + C::TM * C::PLD;
   float* ttl_red = ttl_own + C::TM;
+  const int n = nce_rows(n_max, n_dev);
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   const int row0 = blockIdx.x * C::TM, sp = blockIdx.y;
+  if (row0 >= n) return;
   const int n_tiles = (n + C::TM - 1) / C::TM;
   nce_load_tile<D>(own, h_own, row0, n);
   if (threadIdx.x < C::TM) ttl_own[threadIdx.x] = (row0 + (int)threadIdx.x < n) ? ttl[row0 + threadIdx.x] : 1.f;
@@ -201,19 +222,23 @@ __global__ void __launch_bounds__(kNceThreads) nce_bwd_kernel(const float* __res
     const int r = row0 + ty + 16 * a;
     if (r >= n) continue;
 #pragma unroll
-    for (int b = 0; b < C::KS; ++b) partial_acc[((size_t)sp * n + r) * D + tx + 16 * b] = acc[a][b];
+    for (int b = 0; b < C::KS; ++b) partial_acc[((size_t)sp * n_max + r) * D + tx + 16 * b] = acc[a][b];
   }
 }
 
-// d_hat = coef * (sum_sp partial_acc - partner_hat), coef = g / (n t);  through F.normalize:
-// d_v = (d_hat - h <h, d_hat>) / max(||v||, eps).  One warp per row.
+// d_hat = coef * (sum_sp partial_acc - partner_hat), coef = g * scale / (n t);  through F.normalize:
+// d_v = (d_hat - h <h, d_hat>) / max(||v||, eps).  One warp per row.  Output: grad[r] (dense [n, d]) or, with a
+// gather list, row rows[r] of a TABLE (the ids are unique, so rows never collide); accumulate != 0 adds.
 __global__ void __launch_bounds__(256) nce_bwd_finish_kernel(const float* __restrict__ partial_acc, int split,
                                                              const float* __restrict__ h, const float* __restrict__ partner,
                                                              const float* __restrict__ inv_norm, const float* __restrict__ g_loss,
-                                                             float scale, int n, int d, float* __restrict__ grad) {
+                                                             float scale, int n_max, const int32_t* __restrict__ n_dev, int d,
+                                                             const int32_t* __restrict__ rows, int accumulate,
+                                                             float* __restrict__ grad) {
+  const int n = nce_rows(n_max, n_dev);
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= n) return;
-  const float coef = __ldg(g_loss) * scale;
+  const float coef = (g_loss != nullptr ? __ldg(g_loss) : 1.f) * scale / (float)n;
   float dh[8];                                               // d <= 256: up to 8 columns per lane
   float dot = 0.f;
 #pragma unroll
@@ -222,17 +247,21 @@ __global__ void __launch_bounds__(256) nce_bwd_finish_kernel(const float* __rest
     dh[q] = 0.f;
     if (k < d) {
       float a = 0.f;
-      for (int sp = 0; sp < split; ++sp) a += partial_acc[((size_t)sp * n + r) * d + k];
+      for (int sp = 0; sp < split; ++sp) a += partial_acc[((size_t)sp * n_max + r) * d + k];
       dh[q] = coef * (a - partner[(size_t)r * d + k]);
       dot = fmaf(h[(size_t)r * d + k], dh[q], dot);
     }
   }
   dot = group_sum<32>(dot);
   const float inv = inv_norm[r];
+  float* out = grad + (rows != nullptr ? (size_t)__ldg(rows + r) : (size_t)r) * d;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int k = lane + 32 * q;
-    if (k < d) grad[(size_t)r * d + k] = (dh[q] - h[(size_t)r * d + k] * dot) * inv;
+    if (k < d) {
+      const float gv = (dh[q] - h[(size_t)r * d + k] * dot) * inv;
+      out[k] = accumulate ? out[k] + gv : gv;
+    }
   }
 }
 
@@ -271,26 +300,35 @@ static NceWs nce_carve(void* ws, int n, int d) {
   return w;
 }
 
+struct NceGrad {             // where one view's gradient goes
+  float* out;                // dense [n, d], or a table when rows != nullptr; nullptr = not wanted
+  const int32_t* rows;
+  int accumulate;
+};
+
 template <int D>
-static int nce_forward_d(const float* v1, const float* v2, int n, float inv_t, float* loss, const NceWs& w, cudaStream_t st) {
+static int nce_forward_d(const float* v1, const float* v2, const int32_t* rows, int n, const int32_t* n_dev, float inv_t,
+                         float* loss, const NceWs& w, cudaStream_t st) {
   using C = NceCfg<D>;
   static thread_local bool attr = false;
   if (!attr) {
     AGCF_CUDA_OK(cudaFuncSetAttribute(nce_rowsum_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_fwd));
     attr = true;
   }
-  nce_normalize_kernel<<<(2 * n * 32 + 255) / 256, 256, 0, st>>>(v1, v2, n, D, w.h1, w.h2, w.inv1, w.inv2);
+  nce_normalize_kernel<<<(unsigned)((2ll * n * 32 + 255) / 256), 256, 0, st>>>(v1, v2, rows, n, n_dev, D, w.h1, w.h2, w.inv1,
+                                                                              w.inv2);
   AGCF_LAUNCH_OK();
   const dim3 grid((n + C::TM - 1) / C::TM, w.split);
-  nce_rowsum_kernel<D><<<grid, kNceThreads, C::smem_fwd, st>>>(w.h1, w.h2, n, inv_t, w.split, w.partial);
+  nce_rowsum_kernel<D><<<grid, kNceThreads, C::smem_fwd, st>>>(w.h1, w.h2, n, n_dev, inv_t, w.split, w.partial);
   AGCF_LAUNCH_OK();
-  nce_loss_kernel<<<1, 1024, 0, st>>>(w.h1, w.h2, n, D, inv_t, w.split, w.partial, w.ttl, loss);
+  nce_loss_kernel<<<1, 1024, 0, st>>>(w.h1, w.h2, n, n_dev, D, inv_t, w.split, w.partial, w.ttl, loss);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
 }
 
 template <int D>
-static int nce_backward_d(int n, float inv_t, const float* g_loss, const NceWs& w, float* g1, float* g2, cudaStream_t st) {
+static int nce_backward_d(int n, const int32_t* n_dev, float inv_t, const float* g_loss, float scale, const NceWs& w,
+                          const NceGrad& g1, const NceGrad& g2, cudaStream_t st) {
   using C = NceCfg<D>;
   static thread_local bool attr = false;
   if (!attr) {
@@ -299,18 +337,20 @@ static int nce_backward_d(int n, float inv_t, const float* g_loss, const NceWs& 
     attr = true;
   }
   const dim3 grid((n + C::TM - 1) / C::TM, w.split);
-  const float scale = inv_t / (float)n;
+  const float s = scale * inv_t;                              // the finishing kernel divides by the (device) n
   const unsigned fin_blocks = (unsigned)(((long long)n * 32 + 255) / 256);
-  if (g1 != nullptr) {
-    nce_bwd_kernel<D, 0><<<grid, kNceThreads, C::smem_bwd, st>>>(w.h1, w.h2, w.ttl, n, inv_t, w.split, w.acc);
+  if (g1.out != nullptr) {
+    nce_bwd_kernel<D, 0><<<grid, kNceThreads, C::smem_bwd, st>>>(w.h1, w.h2, w.ttl, n, n_dev, inv_t, w.split, w.acc);
     AGCF_LAUNCH_OK();
-    nce_bwd_finish_kernel<<<fin_blocks, 256, 0, st>>>(w.acc, w.split, w.h1, w.h2, w.inv1, g_loss, scale, n, D, g1);
+    nce_bwd_finish_kernel<<<fin_blocks, 256, 0, st>>>(w.acc, w.split, w.h1, w.h2, w.inv1, g_loss, s, n, n_dev, D, g1.rows,
+                                                      g1.accumulate, g1.out);
     AGCF_LAUNCH_OK();
   }
-  if (g2 != nullptr) {
-    nce_bwd_kernel<D, 1><<<grid, kNceThreads, C::smem_bwd, st>>>(w.h2, w.h1, w.ttl, n, inv_t, w.split, w.acc);
+  if (g2.out != nullptr) {
+    nce_bwd_kernel<D, 1><<<grid, kNceThreads, C::smem_bwd, st>>>(w.h2, w.h1, w.ttl, n, n_dev, inv_t, w.split, w.acc);
     AGCF_LAUNCH_OK();
-    nce_bwd_finish_kernel<<<fin_blocks, 256, 0, st>>>(w.acc, w.split, w.h2, w.h1, w.inv2, g_loss, scale, n, D, g2);
+    nce_bwd_finish_kernel<<<fin_blocks, 256, 0, st>>>(w.acc, w.split, w.h2, w.h1, w.inv2, g_loss, s, n, n_dev, D, g2.rows,
+                                                      g2.accumulate, g2.out);
     AGCF_LAUNCH_OK();
   }
   return AGCF_OK;
@@ -325,8 +365,9 @@ extern "C" int64_t agcf_infonce_ws_bytes(int32_t n, int32_t d) {
   return nce_ws_floats(n, d) * (int64_t)sizeof(float);
 }
 
-extern "C" int agcf_infonce_forward(const float* view1, const float* view2, int32_t n, int32_t d, float temperature,
-                                    float* loss, void* ws, int64_t ws_bytes, agcf_stream_t stream) {
+extern "C" int agcf_infonce_forward(const float* view1, const float* view2, const int32_t* rows, int32_t n,
+                                    const int32_t* n_dev, int32_t d, float temperature, float* loss, void* ws,
+                                    int64_t ws_bytes, agcf_stream_t stream) {
   if (!view1 || !view2 || !loss || !ws || n <= 0 || !(temperature > 0.f)) return AGCF_EINVAL;
   if (!supported_d(d)) return AGCF_EUNSUPPORTED;
   if (ws_bytes < agcf_infonce_ws_bytes(n, d)) return AGCF_EWORKSPACE;
@@ -334,27 +375,31 @@ extern "C" int agcf_infonce_forward(const float* view1, const float* view2, int3
   const float inv_t = 1.f / temperature;
   cudaStream_t st = (cudaStream_t)stream;
   switch (d) {
-    case 32: return nce_forward_d<32>(view1, view2, n, inv_t, loss, w, st);
-    case 64: return nce_forward_d<64>(view1, view2, n, inv_t, loss, w, st);
-    case 128: return nce_forward_d<128>(view1, view2, n, inv_t, loss, w, st);
-    case 256: return nce_forward_d<256>(view1, view2, n, inv_t, loss, w, st);
+    case 32: return nce_forward_d<32>(view1, view2, rows, n, n_dev, inv_t, loss, w, st);
+    case 64: return nce_forward_d<64>(view1, view2, rows, n, n_dev, inv_t, loss, w, st);
+    case 128: return nce_forward_d<128>(view1, view2, rows, n, n_dev, inv_t, loss, w, st);
+    case 256: return nce_forward_d<256>(view1, view2, rows, n, n_dev, inv_t, loss, w, st);
   }
   return AGCF_EUNSUPPORTED;
 }
 
-extern "C" int agcf_infonce_backward(int32_t n, int32_t d, float temperature, const float* grad_loss, void* ws,
-                                     int64_t ws_bytes, float* grad_view1, float* grad_view2, agcf_stream_t stream) {
-  if (!grad_loss || !ws || n <= 0 || !(temperature > 0.f) || (!grad_view1 && !grad_view2)) return AGCF_EINVAL;
+extern "C" int agcf_infonce_backward(int32_t n, const int32_t* n_dev, int32_t d, float temperature,
+                                     const float* grad_loss, float scale, void* ws, int64_t ws_bytes,
+                                     float* grad_view1, const int32_t* rows1, int32_t accumulate1,
+                                     float* grad_view2, const int32_t* rows2, int32_t accumulate2,
+                                     agcf_stream_t stream) {
+  if (!ws || n <= 0 || !(temperature > 0.f) || (!grad_view1 && !grad_view2)) return AGCF_EINVAL;
   if (!supported_d(d)) return AGCF_EUNSUPPORTED;
   if (ws_bytes < agcf_infonce_ws_bytes(n, d)) return AGCF_EWORKSPACE;
   const NceWs w = nce_carve(ws, n, d);
   const float inv_t = 1.f / temperature;
+  const NceGrad g1 = {grad_view1, rows1, accumulate1}, g2 = {grad_view2, rows2, accumulate2};
   cudaStream_t st = (cudaStream_t)stream;
   switch (d) {
-    case 32: return nce_backward_d<32>(n, inv_t, grad_loss, w, grad_view1, grad_view2, st);
-    case 64: return nce_backward_d<64>(n, inv_t, grad_loss, w, grad_view1, grad_view2, st);
-    case 128: return nce_backward_d<128>(n, inv_t, grad_loss, w, grad_view1, grad_view2, st);
-    case 256: return nce_backward_d<256>(n, inv_t, grad_loss, w, grad_view1, grad_view2, st);
+    case 32: return nce_backward_d<32>(n, n_dev, inv_t, grad_loss, scale, w, g1, g2, st);
+    case 64: return nce_backward_d<64>(n, n_dev, inv_t, grad_loss, scale, w, g1, g2, st);
+    case 128: return nce_backward_d<128>(n, n_dev, inv_t, grad_loss, scale, w, g1, g2, st);
+    case 256: return nce_backward_d<256>(n, n_dev, inv_t, grad_loss, scale, w, g1, g2, st);
   }
   return AGCF_EUNSUPPORTED;
 }

@@ -51,6 +51,11 @@ struct SpmmParams {
   float acc_div;
   const float4* noise;
   float eps;
+  // in-kernel noise (noise == nullptr, noise_seed != 0): U[0,1) from Philox4x32-10, key = seed, counter =
+  // (float4 slot of the element, step << 32 | stream) -- nothing is read, a replayed graph draws fresh noise every step
+  unsigned long long noise_seed;
+  uint32_t noise_stream;
+  const int32_t* noise_step;
   const uint32_t* row_mask;   // nullable bitmap over rows: only rows with their bit set are computed / written
   const uint32_t* col_mask;   // nullable bitmap over columns: rows of X outside it are known to be zero (skipped)
   // fused all-gather: the same rows are also stored into the peer GPUs' copies of Y / acc_out
@@ -115,9 +120,22 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
   if (NOISE) {
     float4 nz[C::VPL];
     float ss = 0.f;
+    unsigned long long ctr_hi = 0ull;
+    if (p.noise == nullptr)
+      ctr_hi = ((unsigned long long)(uint32_t)(p.noise_step != nullptr ? __ldg(p.noise_step) : 0) << 32) | p.noise_stream;
 #pragma unroll
     for (int v = 0; v < C::VPL; ++v) {
-      nz[v] = valid ? ld_stream_f4(p.noise + rbase + v * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+      nz[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        if (p.noise != nullptr) {
+          nz[v] = ld_stream_f4(p.noise + rbase + v * C::LPR + gl);
+        } else {
+          uint32_t r4[4];
+          Philox::gen(p.noise_seed, (unsigned long long)(rbase + v * C::LPR + gl), ctr_hi, r4);
+          nz[v] = make_float4((float)(r4[0] >> 8) * 5.9604644775390625e-8f, (float)(r4[1] >> 8) * 5.9604644775390625e-8f,
+                              (float)(r4[2] >> 8) * 5.9604644775390625e-8f, (float)(r4[3] >> 8) * 5.9604644775390625e-8f);
+        }
+      }
       ss += dot4(nz[v], nz[v]);
     }
     ss = group_sum<C::LPR>(ss);
@@ -473,7 +491,7 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   if (blocks <= 0) return AGCF_OK;
   if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
   bool cmask = false;
-  if constexpr (C::EPL == 1) cmask = p.col_mask != nullptr && p.noise == nullptr;
+  if constexpr (C::EPL == 1) cmask = p.col_mask != nullptr && p.noise == nullptr && p.noise_seed == 0ull;
   if (p.sched != nullptr) {                                  // persistent: every CTA resident at once
     const long long resident = (long long)kSMs * (cmask ? AGCF_SPMM_CM_MINB(D) : AGCF_SPMM_MINB(D));
     blocks = blocks < resident ? blocks : resident;
@@ -485,7 +503,7 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
       return AGCF_OK;
     }
   }
-  if (p.noise != nullptr)
+  if (p.noise != nullptr || p.noise_seed != 0ull)
     spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
   else
     spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
@@ -683,6 +701,7 @@ extern "C" int agcf_spmm_csr_f32_ex(const agcf_spmm_args* a, agcf_stream_t strea
   p.acc_div = a->acc_div;
   p.noise = reinterpret_cast<const float4*>(a->noise);
   p.eps = a->eps;
+  p.noise_seed = a->noise_seed; p.noise_stream = a->noise_stream; p.noise_step = a->noise_step;
   p.row_mask = a->row_mask; p.col_mask = a->col_mask;
   p.mc_Y = a->Y != nullptr ? reinterpret_cast<float4*>(a->mc_Y) : nullptr;
   p.mc_acc = a->acc_out != nullptr ? reinterpret_cast<float4*>(a->mc_acc) : nullptr;

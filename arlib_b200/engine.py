@@ -489,3 +489,149 @@ class LightGCNEngine:
             slot["step_done"].record(main)
         torch.cuda.synchronize()
         return {"nb": nb, "slots": slots, "next": 0, "side": side}
+
+
+class ContrastiveEngine(LightGCNEngine):
+    """Fused SimGCL / XSimGCL training step (single GPU): the body of recommender/SimGCL.py:46-64 and
+    recommender/XSimGCL.py:56-75 as a fixed kernel sequence, capturable in a CUDA graph.
+
+    * propagation without layer 0 in the mean, the perturbation ``E += sign(E) * normalize(noise) * eps`` fused into
+      the SpMM epilogue, the noise drawn there by Philox (or read from injected tables: ``noise_tables[(pass, layer)]``,
+      the parity-test hook); last layers only compute the batch's rows;
+    * BPR + L2 on the rec view (agcf_bpr_forward / backward), InfoNCE on the batch's unique users and unique positive
+      items (agcf_bpr_cl_ids -> agcf_infonce_forward / backward with device-side counts, the ``emb[idx]`` gathers and
+      the gradient scatter fused);
+    * backward: sign() has zero gradient, so every view backpropagates through the SAME linear operator
+      ``(A + ... + A^L) / L``.  SimGCL's three passes therefore need ONE backward propagation of the summed gradient
+      (autograd runs three); XSimGCL adds the layer_cl view's gradient where that layer enters.  Adam is fused into
+      the last backward SpMM.
+
+    kind "xsimgcl": one perturbed pass, rec view F' = mean(E'_1..E'_L), CL between F' and E'_{layer_cl} (layer_cl < L).
+    kind "simgcl": clean pass for the rec view + two perturbed passes for the CL views."""
+
+    def __init__(self, graph, table, n_users, kind, n_layers, eps, cl_rate, tau, lr, reg, batch_size, max_triples,
+                 layer_cl=1, noise_seed=0x5eed5eed, noise_tables=None):
+        if kind not in ("simgcl", "xsimgcl"):
+            raise ValueError("kind must be 'simgcl' or 'xsimgcl'")
+        if kind == "xsimgcl" and not (1 <= layer_cl < n_layers):
+            raise ValueError("the fused XSimGCL step needs 1 <= layer_cl < n_layers")
+        super().__init__(graph, table, n_users, n_layers, lr, reg, batch_size, max_triples)
+        if not self.sparse_layers:
+            raise ValueError("graph too large for the per-batch bitmaps of the fused contrastive step")
+        dev = table.device
+        self.kind, self.eps, self.cl_rate, self.tau, self.layer_cl = kind, float(eps), float(cl_rate), float(tau), int(layer_cl)
+        self.noise_seed = int(noise_seed) or 1
+        self.noise_tables = noise_tables
+        self.fuse_adam = True
+        f = lambda: torch.empty_like(table)
+        if self.L > 1 and not self.fw:
+            self.fw, self.bw = [f(), f()], [f(), f()]
+        if kind == "xsimgcl":
+            self.Ecl = f()
+            self.Gcl = torch.zeros_like(table)
+        else:
+            self.Va, self.Vb = f(), f()
+        nbmax = (self.cap + self.B - 1) // self.B
+        i32 = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=dev)
+        self.cl_users, self.cl_items, self.n_cl = i32(nbmax, self.B), i32(nbmax, self.B), i32(nbmax, 2)
+        self.cl_out = torch.zeros((nbmax, 2), dtype=torch.float32, device=dev)
+        self.nce_ws = [ops.infonce_ws(self.B, self.d, dev), ops.infonce_ws(self.B, self.d, dev)]
+        n_prop = 1 if kind == "xsimgcl" else 3
+        # SpMM (n_prop * L forward + L backward) + bpr fwd/bwd + 2 x (3 InfoNCE fwd + 2 x 2 bwd) + zero rows + coefs
+        self.launches_per_step = (n_prop + 1) * self.L + 2 + 2 * 7 + (2 if kind == "xsimgcl" else 1) + 1
+
+    # ------------------------------------------------------------------ set-up
+    def _group(self, first_triple, n):
+        super()._group(first_triple, n)
+        if n <= 0:
+            return
+        b0 = first_triple // self.B
+        ops.bpr_cl_ids(self.occ[b0 * 3 * self.B:], self.seg_off[b0 * (3 * self.B + 1):], self.seg_node[b0 * 3 * self.B:],
+                       self.n_seg[b0:], n, self.B, self.U, self.cl_users[b0:], self.cl_items[b0:], self.n_cl[b0:])
+
+    # ------------------------------------------------------------- propagation
+    def _noise_kw(self, pass_id, k):
+        if pass_id is None:
+            return {}
+        if self.noise_tables is not None:
+            return {"noise": self.noise_tables[(pass_id, k)], "eps": self.eps}
+        return {"philox": (self.noise_seed, pass_id * 64 + k, self.step_dev), "eps": self.eps}
+
+    def _propagate(self, F, pass_id=None, mask=None, worklist=None, keep_layer=0, keep_into=None):
+        """E_k = A E_{k-1} (perturbed if pass_id is not None); F = mean(E_1 .. E_L) (layer 0 excluded,
+        recommender/SimGCL.py:198-210); layer ``keep_layer`` is kept in ``keep_into``.  With a mask / work list the
+        LAST layer (and so F) is only computed on the batch's rows."""
+        x = self.E0
+        for k in range(1, self.L + 1):
+            last = k == self.L
+            if k == keep_layer:
+                y = keep_into
+            else:
+                y = None if last else self.fw[(k - 1) % 2]
+            wl = worklist if last else None
+            ops.spmm(self.g, x, Y=y, acc_in=None if k == 1 else F, acc_out=F, acc_div=float(self.L) if last else 1.0,
+                     row_mask=mask if (last and wl is None) else None, worklist=wl, **self._noise_kw(pass_id, k))
+            x = y
+        return F
+
+    def forward_table(self, out=None, row_mask=None, worklist=None):
+        """the unperturbed encoder forward (model() of the reference): what predict / test read"""
+        return self._propagate(self.F if out is None else out, None, row_mask, worklist)
+
+    # ---------------------------------------------------------------- one step
+    def _launch_step(self, b):
+        B, L = self.B, self.L
+        t0 = b * B
+        nb = min(B, self.T - t0)
+        u, i, j = self.tu[t0:], self.ti[t0:], self.tj[t0:]
+        occ = self.occ[b * 3 * B:]
+        seg_off = self.seg_off[b * (3 * B + 1):]
+        seg_node = self.seg_node[b * 3 * B:]
+        n_seg = self.n_seg[b:]
+        out4 = self.out4[b]
+        mask = self.node_mask[b * self.mask_words:]
+        wl = self._worklist(b)
+        if self.kind == "xsimgcl":
+            F = self._propagate(self.F, 0, mask, wl, keep_layer=self.layer_cl, keep_into=self.Ecl)
+            v1, v2 = F, self.Ecl
+        else:
+            F = self._propagate(self.F, None, mask, wl)
+            v1 = self._propagate(self.Va, 1, mask, wl)
+            v2 = self._propagate(self.Vb, 2, mask, wl)
+        ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)
+        ops.bpr_backward(F, u, i, j, nb, self.U, self.reg, 1.0, out4, self.coef, occ, seg_off, seg_node, n_seg, self.G)
+        # contrastive terms: gradients land on the rows of G (rec / SimGCL views) and, pre-scaled by L, of Gcl
+        g2_table = self.Gcl if self.kind == "xsimgcl" else self.G
+        g2_scale = self.cl_rate * (L if self.kind == "xsimgcl" else 1)
+        for side, rows in ((0, self.cl_users[b]), (1, self.cl_items[b])):
+            n_dev = self.n_cl[b, side:side + 1]
+            ws = self.nce_ws[side]
+            ops.infonce_forward(v1, v2, self.tau, rows=rows, n=B, n_dev=n_dev, loss=self.cl_out[b, side:side + 1], ws=ws)
+            ops.infonce_backward(B, self.d, self.tau, ws, scale=self.cl_rate, n_dev=n_dev, grad1=self.G, rows1=rows, acc1=True)
+            ops.infonce_backward(B, self.d, self.tau, ws, scale=g2_scale, n_dev=n_dev, grad2=g2_table, rows2=rows,
+                                 acc2=self.kind != "xsimgcl")
+        # backward: D_L = G;  D_{k-1} = A D_k + G (+ Gcl where layer k-1 is the CL view);  dE0 = A D_1 / L
+        adam = (self.E0, self.m, self.v, self.adam_coefs, self.betas[0], self.betas[1], self.adam_eps)
+        H = self.G
+        for k in range(L, 0, -1):
+            cm = mask if k == L else None
+            if k == 1:
+                ops.spmm(self.g, H, acc_div=float(L), col_mask=cm, adam=adam)
+                break
+            nxt = self.bw[k % 2]
+            if self.kind == "xsimgcl" and k - 1 == self.layer_cl:
+                ops.spmm(self.g, H, addend=self.G, acc_in=self.Gcl, acc_out=nxt, col_mask=cm)
+            else:
+                ops.spmm(self.g, H, Y=nxt, addend=self.G, col_mask=cm)
+            H = nxt
+        ops.zero_rows(seg_node, n_seg, 3 * nb, self.G)
+        if self.kind == "xsimgcl":
+            ops.zero_rows(seg_node, n_seg, 3 * nb, self.Gcl)
+        ops.adam_coefs(self.step_dev, self.adam_coefs, self.lr, self.betas[0], self.betas[1], increment=True)
+
+    def losses(self, first_batch=0, n=None):
+        """(rec_loss, cl_loss) per batch like the reference prints them (recommender/SimGCL.py:52-55)"""
+        n = self.n_batches - first_batch if n is None else n
+        rec = self.out4[first_batch:first_batch + n, 1]
+        cl = self.cl_rate * self.cl_out[first_batch:first_batch + n].sum(1)
+        return rec, cl

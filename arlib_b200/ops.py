@@ -36,14 +36,15 @@ def _p(t):
 
 def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_div=1.0, noise=None, eps=0.0,
          row_mask=None, col_mask=None, peer_Y=None, peer_acc=None, mc_Y=None, mc_acc=None,
-         worklist=None, adam=None, zero_acc_in=False, persistent=None):
+         worklist=None, adam=None, zero_acc_in=False, persistent=None, philox=None):
     """agcf_spmm_csr_f32_ex: t = A X (+addend) (+noise perturbation); Y = t;
     acc_out = (acc_in + t) / acc_div.
 
     worklist = (vrows [cap,4], vpart [cap], count [1], partial [cap,d], tickets [cap]): a per-batch plan
     (spmm_batch_worklists) instead of the graph's; adam = (p, m, v, coefs, beta1, beta2, eps): the optimizer
     fused into the epilogue; zero_acc_in: re-zero the non-zero rows of acc_in; persistent (default: the graph's
-    setting): persistent CTAs with dynamic block scheduling instead of one CTA per block."""
+    setting): persistent CTAs with dynamic block scheduling instead of one CTA per block; philox = (seed, stream,
+    step_dev or None): draw the perturbation noise in the epilogue instead of reading ``noise``."""
     lib = _lib.load()
     _f32(X, "X"); _f32(Y, "Y"); _f32(addend, "addend"); _f32(acc_in, "acc_in"); _f32(acc_out, "acc_out"); _f32(noise, "noise")
     if X.shape[0] != g.n_rows:
@@ -70,6 +71,10 @@ def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_
     a.X, a.Y, a.addend = X.data_ptr(), _p(Y), _p(addend)
     a.acc_in, a.acc_out, a.acc_div = _p(acc_in), _p(acc_out), float(acc_div)
     a.noise, a.eps = _p(noise), float(eps)
+    if philox is not None:
+        if noise is not None or int(philox[0]) == 0:
+            raise ValueError("philox noise needs a non-zero seed and no noise table")
+        a.noise_seed, a.noise_stream, a.noise_step = int(philox[0]) & (2 ** 64 - 1), int(philox[1]), _p(philox[2])
     a.row_mask, a.col_mask = _p(row_mask), _p(col_mask)
     a.peer_Y_host = ctypes.cast(py, ctypes.c_void_p) if py is not None else None
     a.peer_acc_host = ctypes.cast(pa, ctypes.c_void_p) if pa is not None else None
@@ -151,6 +156,13 @@ def bpr_group_batches(u, i, j, n_triples, batch, n_users, occ, seg_off, seg_node
                "agcf_bpr_group_batches")
 
 
+def bpr_cl_ids(occ, seg_off, seg_node, n_seg, n_triples, batch, n_users, cl_users, cl_items, n_cl):
+    """agcf_bpr_cl_ids: per batch, the sorted unique user rows and positive-item rows of the contrastive loss."""
+    _lib.check(_lib.load().agcf_bpr_cl_ids(occ.data_ptr(), seg_off.data_ptr(), seg_node.data_ptr(), n_seg.data_ptr(),
+                                           int(n_triples), int(batch), int(n_users), cl_users.data_ptr(),
+                                           cl_items.data_ptr(), n_cl.data_ptr(), _lib.stream_ptr()), "agcf_bpr_cl_ids")
+
+
 def bpr_ws_bytes(nb):
     return int(_lib.load().agcf_bpr_ws_bytes(int(nb)))
 
@@ -195,32 +207,42 @@ def zero_rows(seg_node, n_seg, max_seg, G):
                                   _lib.stream_ptr()), "agcf_zero_rows")
 
 
-def infonce_forward(view1, view2, temperature):
-    """agcf_infonce_forward -> (loss [1] fp32, workspace) ; the workspace feeds infonce_backward."""
-    lib = _lib.load()
-    _f32(view1, "view1"); _f32(view2, "view2")
-    if view1.shape != view2.shape or view1.dim() != 2:
-        raise ValueError("views must be two [n, d] tensors of equal shape")
-    n, d = view1.shape
-    need = int(lib.agcf_infonce_ws_bytes(n, d))
+def infonce_ws(n, d, device):
+    need = int(_lib.load().agcf_infonce_ws_bytes(int(n), int(d)))
     if need < 0:
         _lib.check(need, "agcf_infonce_ws_bytes")
-    ws = torch.empty(need, dtype=torch.uint8, device=view1.device)
-    loss = torch.empty(1, dtype=torch.float32, device=view1.device)
-    _lib.check(lib.agcf_infonce_forward(view1.data_ptr(), view2.data_ptr(), n, d, float(temperature), loss.data_ptr(),
-                                        ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "agcf_infonce_forward")
+    return torch.empty(need, dtype=torch.uint8, device=device)
+
+
+def infonce_forward(view1, view2, temperature, rows=None, n=None, n_dev=None, loss=None, ws=None):
+    """agcf_infonce_forward -> (loss [1] fp32, workspace); the workspace feeds infonce_backward.
+    With ``rows`` the views are rows[r] of the TABLES view1 / view2; n = capacity, n_dev = device row count."""
+    lib = _lib.load()
+    _f32(view1, "view1"); _f32(view2, "view2"); _i32(rows, "rows"); _i32(n_dev, "n_dev")
+    if view1.shape != view2.shape or view1.dim() != 2:
+        raise ValueError("views must be two [n, d] tensors of equal shape")
+    d = view1.shape[1]
+    if n is None:
+        n = rows.numel() if rows is not None else view1.shape[0]
+    if ws is None:
+        ws = infonce_ws(n, d, view1.device)
+    if loss is None:
+        loss = torch.empty(1, dtype=torch.float32, device=view1.device)
+    _lib.check(lib.agcf_infonce_forward(view1.data_ptr(), view2.data_ptr(), _p(rows), int(n), _p(n_dev), d,
+                                        float(temperature), loss.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        _lib.stream_ptr()), "agcf_infonce_forward")
     return loss, ws
 
 
-def infonce_backward(n, d, temperature, grad_loss, ws, need1=True, need2=True):
-    """agcf_infonce_backward -> (d loss / d view1, d loss / d view2)."""
+def infonce_backward(n, d, temperature, ws, grad_loss=None, scale=1.0, n_dev=None, grad1=None, rows1=None, acc1=False,
+                     grad2=None, rows2=None, acc2=False):
+    """agcf_infonce_backward: scale * grad_loss * d loss / d view into grad1 / grad2 ([n, d], or tables with rowsK)."""
     lib = _lib.load()
-    _f32(grad_loss, "grad_loss")
-    g1 = torch.empty((n, d), dtype=torch.float32, device=ws.device) if need1 else None
-    g2 = torch.empty((n, d), dtype=torch.float32, device=ws.device) if need2 else None
-    _lib.check(lib.agcf_infonce_backward(n, d, float(temperature), grad_loss.data_ptr(), ws.data_ptr(), ws.numel(),
-                                         _p(g1), _p(g2), _lib.stream_ptr()), "agcf_infonce_backward")
-    return g1, g2
+    _f32(grad_loss, "grad_loss"); _f32(grad1, "grad1"); _f32(grad2, "grad2")
+    _lib.check(lib.agcf_infonce_backward(int(n), _p(n_dev), int(d), float(temperature), _p(grad_loss), float(scale),
+                                         ws.data_ptr(), ws.numel(), _p(grad1), _p(rows1), 1 if acc1 else 0,
+                                         _p(grad2), _p(rows2), 1 if acc2 else 0, _lib.stream_ptr()),
+               "agcf_infonce_backward")
 
 
 def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0, step_dev=None, peer_p=None, mc_p=None):

@@ -28,7 +28,7 @@ class LightGCN(GraphRecommender):
         self.bestPerformance = []
         model = self.model.cuda()
         maxEpoch = Epoch if Epoch else self.args.maxEpoch
-        if optimizer is None and not requires_adjgrad and not requires_embgrad:
+        if optimizer is None and not requires_adjgrad and not requires_embgrad and self._fused_ok():
             self._train_fused(model, maxEpoch, evalNum)
             self.user_emb, self.item_emb = self.best_user_emb, self.best_item_emb
             return None

@@ -24,6 +24,11 @@ class SimGCL(GraphRecommender):
               evalNum=5):
         self.bestPerformance = []
         model = self.model.cuda()
+        maxEpoch = Epoch if Epoch else self.args.maxEpoch
+        if optimizer is None and not requires_adjgrad and not requires_embgrad and self._fused_ok():
+            self._train_fused_contrastive(model, maxEpoch, evalNum, "simgcl")
+            self.user_emb, self.item_emb = self.best_user_emb, self.best_item_emb
+            return None
         if optimizer is None:
             optimizer = torch.optim.Adam(model.parameters(), lr=self.args.lRate)
         self._grad_buffers(requires_adjgrad, requires_embgrad, model)

@@ -57,6 +57,12 @@ class GraphRecommender(object):
     def _sampler_mode(self):
         return str(getattr(self.args, 'sampler', os.environ.get('ARLIB_B200_SAMPLER', 'device'))).lower()
 
+    def _fused_ok(self):
+        """the fused engines take the batch sizes the single-CTA grouping sorts (3 B <= 16384) and are switched off
+        by args.fused = False / ARLIB_B200_FUSED=0 (then the reference-shaped loop runs on the same kernels)"""
+        on = getattr(self.args, 'fused', os.environ.get('ARLIB_B200_FUSED', '1'))
+        return str(on).lower() not in ('0', 'false') and 3 * self.args.batch_size <= 16384
+
     def _next_sample_epoch(self):
         """Philox stream id of the next sampled epoch: keeps counting across train() calls on one instance (an
         attack that retrains the same recommender must not see the same triples again, like the reference's
@@ -155,6 +161,44 @@ class GraphRecommender(object):
         return rec_list, measure
 
     # ------------------------------------------------------------------ training
+    def _train_fused_contrastive(self, model, maxEpoch, evalNum, kind, layer_cl=1):
+        """SimGCL / XSimGCL training when the recommender owns the optimizer and no gradient is exported: the fused
+        engine (arlib_b200.engine.ContrastiveEngine) -- device sampling (or the host sampler for seed parity), one
+        CUDA-graph replay per epoch, Adam state owned by the engine.  Same mathematics as the reference loop
+        (recommender/SimGCL.py:36-85, XSimGCL.py:46-95); the perturbation noise comes from Philox in the SpMM
+        epilogue instead of torch.rand_like."""
+        from ..engine import ContrastiveEngine, DeviceTrainSet
+        from ..util.sampler import next_batch_pairwise
+        table = model.parameter_table()
+        dev = table.device
+        seed = int(getattr(self.args, 'seed', 0) or 0)
+        tau = self.temp if kind == "xsimgcl" else 0.2
+        eng = ContrastiveEngine(model._graph, table, self.data.user_num, kind, self.n_layers, self.eps, self.cl_rate, tau,
+                                self.args.lRate, self.args.reg, self.args.batch_size, len(self.data.training_data),
+                                layer_cl=layer_cl, noise_seed=(seed * 2654435761 + 12345) & 0xffffffffffff or 1)
+        mode = self._sampler_mode()
+        ts = DeviceTrainSet(self.data, dev) if mode == 'device' else None
+        for epoch in range(maxEpoch):
+            if mode == 'device':
+                eng.sample_epoch(ts, seed, self._next_sample_epoch())
+            else:
+                us, is_, js = [], [], []
+                for u, i, j in next_batch_pairwise(self.data, self.args.batch_size):
+                    us += u; is_ += i; js += j
+                eng.set_triples(us, is_, js)
+            eng.run_steps(0)
+            rec, cl = eng.losses()
+            rec, cl = rec[::100].cpu().tolist(), cl[::100].cpu().tolist()
+            for k, (r, c) in enumerate(zip(rec, cl)):
+                print('training:', epoch + 1, 'batch', k * 100, 'rec_loss:', r, 'cl_loss', c)
+            model.eval()
+            with torch.no_grad():
+                f = eng.forward_table(out=torch.empty_like(table))
+                self.user_emb, self.item_emb = f[:self.data.user_num], f[self.data.user_num:]
+            if epoch % evalNum == 0:
+                self.evaluate(epoch)
+        self.last_train_losses = torch.stack(eng.losses(), 1).clone()
+
     def _grad_buffers(self, requires_adjgrad, requires_embgrad, model):
         """recommender/LightGCN.py:36-43.  The reference allocates a DENSE N x N Matgrad
         (20 GB at Gowalla shape); here the adjacency gradient is accumulated on the stored

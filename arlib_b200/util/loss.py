@@ -40,7 +40,10 @@ class _InfoNCE(torch.autograd.Function):
         from .. import ops
         n, d = ctx.shape
         g = grad.detach().to(torch.float32).reshape(1).contiguous()
-        g1, g2 = ops.infonce_backward(n, d, ctx.temperature, g, ctx.ws, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        g1 = torch.empty((n, d), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[0] else None
+        g2 = torch.empty((n, d), dtype=torch.float32, device=g.device) if ctx.needs_input_grad[1] else None
+        if g1 is not None or g2 is not None:
+            ops.infonce_backward(n, d, ctx.temperature, ctx.ws, grad_loss=g, grad1=g1, grad2=g2)
         return g1, g2, None
 
 

@@ -109,6 +109,11 @@ int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int32_t n_vrow
  *                 acc_out may then be null (the gradient table is never written).  Same bits as agcf_adam_step_f32;
  *   zero_acc_in   != 0: rows of acc_in that were non-zero are set to zero after they were read (acc_in is the batch
  *                 gradient G, non-zero on <= 3B rows: replaces agcf_zero_rows); acc_in must not be X;
+ *   noise_seed    != 0 (and noise == null): the U[0,1) noise of the SimGCL / XSimGCL perturbation is drawn IN the
+ *                 epilogue -- Philox4x32-10, key = noise_seed, counter = (float4 slot of the element,
+ *                 *noise_step << 32 | noise_stream) -- instead of read from an [rows, d] table; noise_stream tells
+ *                 layers / passes apart, noise_step (nullable device int32) is the training-step counter, so a
+ *                 replayed CUDA graph perturbs every step differently;
  *   sched         nullable device int32[2], zero on entry and zero again on exit: the launch then runs PERSISTENT CTAs
  *                 (148 x resident CTAs per SM) that take blocks of work items from this counter in plan order instead
  *                 of one CTA per block -- no CTA turnover gaps and no tail of idle SMs; launches sharing it must be
@@ -122,6 +127,7 @@ typedef struct agcf_spmm_args {
   const float* X; float* Y; const float* addend;
   const float* acc_in; float* acc_out; float acc_div;
   const float* noise; float eps;
+  uint64_t noise_seed; uint32_t noise_stream; const int32_t* noise_step;
   const uint32_t* row_mask; const uint32_t* col_mask;
   void* const* peer_Y_host; void* const* peer_acc_host; int32_t n_peers;
   void* mc_Y; void* mc_acc;
@@ -231,25 +237,41 @@ int agcf_bpr_backward(const float* F, const int32_t* u, const int32_t* i, const 
                       const int32_t* occ, const int32_t* seg_off, const int32_t* seg_node,
                       const int32_t* n_seg, float* G, agcf_stream_t stream);
 
+/* The id lists of the contrastive loss of SimGCL / XSimGCL -- torch.unique of the batch's users and of its
+ * POSITIVE items (recommender/SimGCL.py:213-214, XSimGCL.py:40-41) -- for every batch, from the grouping above:
+ * cl_users[b*batch ..] / cl_items[b*batch ..] = sorted TABLE rows (items: n_users + item), n_cl[2b], n_cl[2b+1] =
+ * their counts.  (The reference passes the ids through float32; exact below 2^24.) */
+int agcf_bpr_cl_ids(const int32_t* occ, const int32_t* seg_off, const int32_t* seg_node, const int32_t* n_seg,
+                    int32_t n_triples, int32_t batch, int32_t n_users,
+                    int32_t* cl_users, int32_t* cl_items, int32_t* n_cl, agcf_stream_t stream);
+
 /* G[seg_node[s],:] = 0 for s < *n_seg (undo of agcf_bpr_backward's writes) */
 int agcf_zero_rows(const int32_t* seg_node, const int32_t* n_seg, int32_t max_seg,
                    float* G, int32_t d, agcf_stream_t stream);
 
 /* ---------------------------------------------------------------- contrastive loss
- * InfoNCE between two views [n, d] of the same n rows (util/loss.py:42-49; callers recommender/SimGCL.py:212-219,
+ * InfoNCE between two views of the same n rows (util/loss.py:42-49; callers recommender/SimGCL.py:212-219,
  * XSimGCL.py:39-44 with the batch's unique users / positive items, n <= batch size):
  *   h = v / max(||v||, 1e-12) per row;  S = h1 h2^T / temperature;
  *   loss[0] = mean_r -log( exp(S_rr) / sum_c exp(S_rc) )        (no max-subtraction, like the reference)
+ * view1 / view2 are [n, d] matrices, or -- with `rows` (n device int32 ids) -- TABLES whose rows rows[r] form the
+ * views (the gather of `emb[idx]` fused into the normalisation).  n_dev (nullable device int32): the actual row
+ * count, <= n; grids and the workspace are sized for n, so a launch sequence captured in a CUDA graph serves
+ * batches whose number of unique ids differs.
  * The n x n logits never reach memory (tiles in registers / shared memory, fp32 CUDA cores: a TF32 product would
  * put ~1e-2 relative error on exp(S)).  `ws` (agcf_infonce_ws_bytes(n, d) bytes) receives the normalized views, the
- * row sums and scratch; agcf_infonce_backward takes the SAME workspace, untouched since the forward call, and
- * writes d loss / d view1, d loss / d view2 ([n, d], either nullable) scaled by grad_loss[0] (device scalar).
+ * row sums and scratch; agcf_infonce_backward takes the SAME workspace, untouched since the forward call (same n,
+ * n_dev), and produces scale * grad_loss[0] * d loss / d view (grad_loss nullable = 1): grad_viewK is [n, d], or
+ * -- with rowsK -- a table whose rows rowsK[r] receive the rows of the gradient (ids must be unique);
+ * accumulateK != 0 adds to what is there.  Either gradient may be null.
  * Deterministic (partials combined in a fixed order).  d in {32, 64, 128, 256}. */
 int64_t agcf_infonce_ws_bytes(int32_t n, int32_t d);
-int agcf_infonce_forward(const float* view1, const float* view2, int32_t n, int32_t d, float temperature,
-                         float* loss, void* ws, int64_t ws_bytes, agcf_stream_t stream);
-int agcf_infonce_backward(int32_t n, int32_t d, float temperature, const float* grad_loss, void* ws, int64_t ws_bytes,
-                          float* grad_view1, float* grad_view2, agcf_stream_t stream);
+int agcf_infonce_forward(const float* view1, const float* view2, const int32_t* rows, int32_t n, const int32_t* n_dev,
+                         int32_t d, float temperature, float* loss, void* ws, int64_t ws_bytes, agcf_stream_t stream);
+int agcf_infonce_backward(int32_t n, const int32_t* n_dev, int32_t d, float temperature, const float* grad_loss,
+                          float scale, void* ws, int64_t ws_bytes,
+                          float* grad_view1, const int32_t* rows1, int32_t accumulate1,
+                          float* grad_view2, const int32_t* rows2, int32_t accumulate2, agcf_stream_t stream);
 
 /* ------------------------------------------------------------------ optimizer
  * torch.optim.Adam step (defaults: amsgrad=False, weight_decay=0, maximize=False)

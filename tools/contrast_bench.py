@@ -54,3 +54,36 @@ for model in models:
                       "ms_per_step": step_ms, "triples_per_s": 2048 / (step_ms * 1e-3),
                       "test_s": t_test, "test_users": len(data.test_set), "dataloader_s": t_load,
                       "measure": [x.strip() for x in measure]}), flush=True)
+
+# ---- the fused engines on the same graph (what train() runs when the recommender owns the optimizer)
+from arlib_b200.engine import ContrastiveEngine, DeviceTrainSet, LightGCNEngine
+from arlib_b200.graph import DeviceGraph
+import scipy.sparse as sp
+
+N = U + I
+half = sp.csr_matrix((np.ones(E, dtype=np.float32), (tu, ti + U)), shape=(N, N), dtype=np.float32)
+g = DeviceGraph.from_dataloader_adj(half + half.T, dev)
+ts = DeviceTrainSet.from_arrays(tu, ti, U, I, dev)
+gen = torch.Generator().manual_seed(2018)
+a = (6.0 / (N + 64)) ** 0.5
+for kind in ("xsimgcl", "simgcl", "lightgcn"):
+    table = ((torch.rand(N, 64, generator=gen) * 2 - 1) * a).to(dev)
+    if kind == "lightgcn":
+        eng = LightGCNEngine(g, table, U, 2, 0.005, 1e-4, 2048, E)
+    else:
+        eng = ContrastiveEngine(g, table, U, kind, 2, 0.1, 0.2, 0.1 if kind == "xsimgcl" else 0.2, 0.005, 1e-4, 2048, E)
+    eng.sample_epoch(ts, 2018, 0)
+    K = min(500, E // 2048)
+    eng.run_steps(0, 3, use_graph=False)
+    eng.run_steps(0, K)                                    # capture + warm replay
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); eng.run_steps(0, K); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    extra = {}
+    if kind != "lightgcn":
+        rec, cl = eng.losses(0, K)
+        extra = {"rec_loss_last": float(rec[-1]), "cl_loss_last": float(cl[-1])}
+    print(json.dumps(dict({"workload": name, "engine": kind, "steps_timed": K, "ms_per_step": ms,
+                           "triples_per_s": 2048 / (ms * 1e-3), "launches_per_step": eng.launches_per_step}, **extra)),
+          flush=True)
