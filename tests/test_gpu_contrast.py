@@ -66,11 +66,12 @@ def test_infonce_one_sided_gradient_and_shared_input():
     # gathered rows of ONE table on both sides (XSimGCL: rec view vs layer_cl view of the same pass)
     t = torch.randn(500, 64)
     idx = torch.unique(torch.randint(0, 500, (300,)))
-    tr = t.clone().requires_grad_(True)
-    port.infonce(tr[idx], tr[idx] * 0.9 + 0.01, 0.1).backward()
+    mix = torch.randn(idx.numel(), 64)                     # (a second view that is not a rescaling of the first:
+    tr = t.clone().requires_grad_(True)                    #  F.normalize would cancel that and leave a ~0 gradient)
+    port.infonce(tr[idx], torch.tanh(tr[idx]) + 0.5 * mix, 0.1).backward()
     tg = t.to(DEV).requires_grad_(True)
-    InfoNCE(tg[idx.to(DEV)], tg[idx.to(DEV)] * 0.9 + 0.01, 0.1).backward()
-    assert float((tg.grad.cpu() - tr.grad).abs().max()) <= 1e-4 * float(tr.grad.abs().max())
+    InfoNCE(tg[idx.to(DEV)], torch.tanh(tg[idx.to(DEV)]) + 0.5 * mix.to(DEV), 0.1).backward()
+    assert float((tg.grad.cpu() - tr.grad).abs().max()) <= 1e-4 * float(tr.grad.abs().max()) + 1e-7
 
 
 def test_infonce_rejects_unsupported_width():

@@ -241,11 +241,13 @@ def test_masked_score_topk_equals_the_attacks_dense_topk():
     U, I, d, K = 500, 1300, 64, 50
     Pu = torch.from_numpy(rng.standard_normal((U, d)).astype(np.float32))
     Pi = torch.from_numpy(rng.standard_normal((I, d)).astype(np.float32))
-    inter = sp.random(U, I, density=0.05, random_state=1, format="lil", dtype=np.float32)
-    inter[3, :] = 1.0                                  # a user with everything masked
-    inter[4, :I - 7] = 1.0                             # fewer free items than K
-    inter = inter.tocsr()
-    inter.data[::11] = 0.0                             # explicitly stored zeros are NOT masked (.nonzero())
+    dense = sp.random(U, I, density=0.05, random_state=1, dtype=np.float32).toarray()
+    dense[3, :] = 1.0                                  # a user with everything masked
+    dense[4, :I - 7] = 1.0                             # fewer free items than K
+    inter = sp.csr_matrix(dense)
+    rows_of = np.repeat(np.arange(U), np.diff(inter.indptr))
+    stored_zero = (np.arange(inter.nnz) % 11 == 0) & (rows_of != 3) & (rows_of != 4)
+    inter.data[stored_zero] = 0.0                      # explicitly stored zeros are NOT masked (.nonzero())
     scores = Pu.double() @ Pi.double().T
     nz = inter.nonzero()
     scores[nz[0], nz[1]] = -10e8

@@ -11,11 +11,11 @@ from arlib_b200.util.synth import SHAPES, synth_edges
 
 name = sys.argv[1] if len(sys.argv) > 1 else "yelp2018"
 n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
-models = sys.argv[3].split(",") if len(sys.argv) > 3 else ["XSimGCL", "SimGCL", "NGCF", "LightGCN"]
+models = [m for m in sys.argv[3].split(",") if m != "none"] if len(sys.argv) > 3 else ["XSimGCL", "SimGCL", "NGCF", "LightGCN"]
 U, I, E = SHAPES[name]
 tu, ti, su, si = synth_edges(U, I, E, 0.5, 0.5, 0)
 t0 = time.perf_counter()
-data = DataLoader.from_arrays(tu, ti, su, si, name=name)
+data = DataLoader.from_arrays(tu, ti, su, si, name=name) if models else None
 t_load = time.perf_counter() - t0
 dev = torch.device("cuda:0")
 
@@ -73,7 +73,7 @@ for kind in ("xsimgcl", "simgcl", "lightgcn"):
     else:
         eng = ContrastiveEngine(g, table, U, kind, 2, 0.1, 0.2, 0.1 if kind == "xsimgcl" else 0.2, 0.005, 1e-4, 2048, E)
     eng.sample_epoch(ts, 2018, 0)
-    K = min(500, E // 2048)
+    K = min(int(os.environ.get('CONTRAST_STEPS', '500')), E // 2048)
     eng.run_steps(0, 3, use_graph=False)
     eng.run_steps(0, K)                                    # capture + warm replay
     torch.cuda.synchronize()
