@@ -30,7 +30,8 @@ class SpmmArgs(ctypes.Structure):
         ("X", P), ("Y", P), ("addend", P),
         ("acc_in", P), ("acc_out", P), ("acc_div", F32),
         ("noise", P), ("eps", F32),
-        ("noise_seed", U64), ("noise_stream", ctypes.c_uint32), ("noise_step", P),
+        ("noise_seed", U64), ("noise_stream", ctypes.c_uint32), ("noise_step", P), ("noise_main", I32),
+        ("aux_Y", P * 2), ("aux_noise", P * 2), ("aux_stream", ctypes.c_uint32 * 2),
         ("row_mask", P), ("col_mask", P),
         ("peer_Y_host", P), ("peer_acc_host", P), ("n_peers", I32),
         ("mc_Y", P), ("mc_acc", P),

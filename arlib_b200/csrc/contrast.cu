@@ -24,23 +24,25 @@ struct NceCfg {
   static constexpr int TM = D <= 64 ? 64 : 32;      // vectors per tile (own side and reduced side)
   static constexpr int RS = TM / 16;                // tile rows / cols per thread in the logit product
   static constexpr int KS = D / 16;                 // embedding columns per thread in the second product
-  static constexpr int LD = D + 1;                  // padded row stride: conflict-free column walks
-  static constexpr int PLD = TM + 1;
+  static constexpr int LD = D + 4;                  // padded row stride (floats): 16-byte aligned rows whose float4
+  static constexpr int PLD = TM + 4;                // reads by 16 different rows need the minimal 2 wavefronts
   static constexpr size_t smem_fwd = (size_t)(2 * TM * LD) * sizeof(float);
   static constexpr size_t smem_bwd = (size_t)(2 * TM * LD + TM * PLD + 2 * TM) * sizeof(float);
 };
 
-// rows [row0, row0 + TM) of a [n, D] table into a padded shared tile (rows >= n are zero)
+// rows [row0, row0 + TM) of a [n, D] table into a padded shared tile (rows >= n are zero); 16 bytes per thread
 template <int D>
 __device__ __forceinline__ void nce_load_tile(float* __restrict__ sm, const float* __restrict__ g, int row0, int n) {
   using C = NceCfg<D>;
-  for (int idx = threadIdx.x; idx < C::TM * D; idx += kNceThreads) {
-    const int r = idx / D, k = idx - r * D;
-    sm[r * C::LD + k] = (row0 + r < n) ? __ldg(g + (size_t)(row0 + r) * D + k) : 0.f;
+  for (int idx = threadIdx.x; idx < C::TM * (D / 4); idx += kNceThreads) {
+    const int r = idx / (D / 4), k4 = idx - r * (D / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < n) v = __ldg(reinterpret_cast<const float4*>(g + (size_t)(row0 + r) * D) + k4);
+    *reinterpret_cast<float4*>(sm + r * C::LD + 4 * k4) = v;
   }
 }
 
-// s[a][b] = <own[ty + 16a], other[tx + 16b]>, k ascending
+// s[a][b] = <own[ty + 16a], other[tx + 16b]>, k ascending; operands read 4 columns at a time (LDS.128)
 template <int D>
 __device__ __forceinline__ void nce_logits(const float* __restrict__ own, const float* __restrict__ other, int ty, int tx,
                                            float (&s)[NceCfg<D>::RS][NceCfg<D>::RS]) {
@@ -49,17 +51,24 @@ __device__ __forceinline__ void nce_logits(const float* __restrict__ own, const 
   for (int a = 0; a < C::RS; ++a)
 #pragma unroll
     for (int b = 0; b < C::RS; ++b) s[a][b] = 0.f;
-#pragma unroll 8
-  for (int k = 0; k < D; ++k) {
-    float av[C::RS], bv[C::RS];
+#pragma unroll 4
+  for (int k4 = 0; k4 < D / 4; ++k4) {
+    float4 av[C::RS], bv[C::RS];
 #pragma unroll
-    for (int a = 0; a < C::RS; ++a) av[a] = own[(ty + 16 * a) * C::LD + k];
+    for (int a = 0; a < C::RS; ++a) av[a] = *reinterpret_cast<const float4*>(own + (ty + 16 * a) * C::LD + 4 * k4);
 #pragma unroll
-    for (int b = 0; b < C::RS; ++b) bv[b] = other[(tx + 16 * b) * C::LD + k];
+    for (int b = 0; b < C::RS; ++b) bv[b] = *reinterpret_cast<const float4*>(other + (tx + 16 * b) * C::LD + 4 * k4);
 #pragma unroll
     for (int a = 0; a < C::RS; ++a)
 #pragma unroll
-      for (int b = 0; b < C::RS; ++b) s[a][b] = fmaf(av[a], bv[b], s[a][b]);
+      for (int b = 0; b < C::RS; ++b) {
+        float t = s[a][b];
+        t = fmaf(av[a].x, bv[b].x, t);
+        t = fmaf(av[a].y, bv[b].y, t);
+        t = fmaf(av[a].z, bv[b].z, t);
+        t = fmaf(av[a].w, bv[b].w, t);
+        s[a][b] = t;
+      }
   }
 }
 
@@ -100,7 +109,7 @@ __global__ void __launch_bounds__(kNceThreads) nce_rowsum_kernel(const float* __
                                                                  int n_max, const int32_t* __restrict__ n_dev, float inv_t,
                                                                  int split, float* __restrict__ partial) {
   using C = NceCfg<D>;
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* own = sm;
   float* other = sm + C::TM * C::LD;
   const int n = nce_rows(n_max, n_dev);
@@ -132,25 +141,32 @@ __global__ void __launch_bounds__(kNceThreads) nce_rowsum_kernel(const float* __
   }
 }
 
-// ttl_r = sum_sp partial (slice order); loss = mean_r -log(exp(<h1_r, h2_r>/t) / ttl_r); one CTA, fixed-order reduction
-__global__ void __launch_bounds__(1024) nce_loss_kernel(const float* __restrict__ h1, const float* __restrict__ h2, int n_max,
-                                                        const int32_t* __restrict__ n_dev, int d,
-                                                        float inv_t, int split, const float* __restrict__ partial,
-                                                        float* __restrict__ ttl, float* __restrict__ loss) {
+// ttl_r = sum_sp partial (slice order); rowloss_r = -log(exp(<h1_r, h2_r>/t) / ttl_r); one warp per row
+__global__ void __launch_bounds__(256) nce_rowloss_kernel(const float* __restrict__ h1, const float* __restrict__ h2, int n_max,
+                                                          const int32_t* __restrict__ n_dev, int d, float inv_t, int split,
+                                                          const float* __restrict__ partial, float* __restrict__ ttl,
+                                                          float* __restrict__ rowloss) {
+  const int n = nce_rows(n_max, n_dev);
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float dot = 0.f;
+  for (int k = lane; k < d; k += 32) dot = fmaf(h1[(size_t)r * d + k], h2[(size_t)r * d + k], dot);
+  dot = group_sum<32>(dot);
+  if (lane == 0) {
+    float t = 0.f;
+    for (int sp = 0; sp < split; ++sp) t += partial[(size_t)sp * n_max + r];
+    ttl[r] = t;
+    rowloss[r] = -logf(__fdiv_rn(expf(dot * inv_t), t));
+  }
+}
+
+// loss = mean_r rowloss_r: one CTA, double accumulation in a fixed order
+__global__ void __launch_bounds__(1024) nce_loss_kernel(const float* __restrict__ rowloss, int n_max,
+                                                        const int32_t* __restrict__ n_dev, float* __restrict__ loss) {
   __shared__ double red[1024];
   const int n = nce_rows(n_max, n_dev);
   double mine = 0.0;
-  for (int r = threadIdx.x; r < n; r += blockDim.x) {
-    float t = 0.f;
-    // slices beyond the row tiles that exist at this n hold nothing for row r only if the slice had no column
-    // tile: every slice sp < split writes all rows < n (possibly 0), see nce_rowsum_kernel
-    for (int sp = 0; sp < split; ++sp) t += partial[(size_t)sp * n_max + r];
-    ttl[r] = t;
-    float dot = 0.f;
-    for (int k = 0; k < d; ++k) dot = fmaf(h1[(size_t)r * d + k], h2[(size_t)r * d + k], dot);
-    const float pos = expf(dot * inv_t);
-    mine += (double)(-logf(__fdiv_rn(pos, t)));
-  }
+  for (int r = threadIdx.x; r < n; r += blockDim.x) mine += (double)rowloss[r];
   red[threadIdx.x] = mine;
   __syncthreads();
   for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
@@ -170,7 +186,7 @@ __global__ void __launch_bounds__(kNceThreads) nce_bwd_kernel(const float* __res
                                                               const int32_t* __restrict__ n_dev, float inv_t, int split,
                                                               float* __restrict__ partial_acc) {
   using C = NceCfg<D>;
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* own = sm;
   float* other = own + C::TM * C::LD;
   float* Ps = other + C::TM * C::LD;
@@ -204,25 +220,42 @@ __global__ void __launch_bounds__(kNceThreads) nce_bwd_kernel(const float* __res
         Ps[o * C::PLD + x] = (ct * C::TM + x < n) ? __fdiv_rn(expf(s[a][b] * inv_t), den) : 0.f;
       }
     __syncthreads();
-    // acc[o][k] += sum_x P[o][x] * other[x][k];  thread (ty, tx) owns o = ty + 16a, k = tx + 16b
-    for (int x = 0; x < C::TM; ++x) {
-      float pv[C::RS], ov[C::KS];
+    // acc[o][k] += sum_x P[o][x] * other[x][k];  thread (ty, tx) owns o = ty + 16a and the KS consecutive columns
+    // k = KS tx + b; P is read 4 x at a time, the operand row KS floats at a time (x ascending in every accumulator)
+    for (int x4 = 0; x4 < C::TM; x4 += 4) {
+      float4 pv[C::RS];
 #pragma unroll
-      for (int a = 0; a < C::RS; ++a) pv[a] = Ps[(ty + 16 * a) * C::PLD + x];
+      for (int a = 0; a < C::RS; ++a) pv[a] = *reinterpret_cast<const float4*>(Ps + (ty + 16 * a) * C::PLD + x4);
 #pragma unroll
-      for (int b = 0; b < C::KS; ++b) ov[b] = other[x * C::LD + tx + 16 * b];
+      for (int xx = 0; xx < 4; ++xx) {
+        float ov[C::KS];
+        const float* orow = other + (x4 + xx) * C::LD + C::KS * tx;
+        if constexpr (C::KS % 4 == 0) {
 #pragma unroll
-      for (int a = 0; a < C::RS; ++a)
+          for (int q = 0; q < C::KS / 4; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(orow + 4 * q);
+            ov[4 * q] = t4.x; ov[4 * q + 1] = t4.y; ov[4 * q + 2] = t4.z; ov[4 * q + 3] = t4.w;
+          }
+        } else {
+          const float2 t2 = *reinterpret_cast<const float2*>(orow);
+          ov[0] = t2.x; ov[1] = t2.y;
+        }
 #pragma unroll
-        for (int b = 0; b < C::KS; ++b) acc[a][b] = fmaf(pv[a], ov[b], acc[a][b]);
+        for (int a = 0; a < C::RS; ++a) {
+          const float pa = xx == 0 ? pv[a].x : (xx == 1 ? pv[a].y : (xx == 2 ? pv[a].z : pv[a].w));
+#pragma unroll
+          for (int b = 0; b < C::KS; ++b) acc[a][b] = fmaf(pa, ov[b], acc[a][b]);
+        }
+      }
     }
   }
 #pragma unroll
   for (int a = 0; a < C::RS; ++a) {
     const int r = row0 + ty + 16 * a;
     if (r >= n) continue;
+    float* dst = partial_acc + ((size_t)sp * n_max + r) * D + C::KS * tx;
 #pragma unroll
-    for (int b = 0; b < C::KS; ++b) partial_acc[((size_t)sp * n_max + r) * D + tx + 16 * b] = acc[a][b];
+    for (int b = 0; b < C::KS; ++b) dst[b] = acc[a][b];
   }
 }
 
@@ -265,9 +298,9 @@ __global__ void __launch_bounds__(256) nce_bwd_finish_kernel(const float* __rest
   }
 }
 
-// workspace layout (floats): h1 [n,d] | h2 [n,d] | inv1 [n] | inv2 [n] | ttl [n] | partial [split,n] | acc [split,n,d]
+// workspace layout (floats): h1 [n,d] | h2 [n,d] | inv1 [n] | inv2 [n] | ttl [n] | rowloss [n] | partial [split,n] | acc [split,n,d]
 struct NceWs {
-  float *h1, *h2, *inv1, *inv2, *ttl, *partial, *acc;
+  float *h1, *h2, *inv1, *inv2, *ttl, *rowloss, *partial, *acc;
   int split;
 };
 
@@ -283,7 +316,7 @@ static int nce_split(int n, int d) {
 
 static int64_t nce_ws_floats(int n, int d) {
   const int64_t s = nce_split(n, d);
-  return 2ll * n * d + 3ll * n + s * n + s * (int64_t)n * d + 16;
+  return 2ll * n * d + 4ll * (n + 4) + s * n + s * (int64_t)n * d + 16;
 }
 
 static NceWs nce_carve(void* ws, int n, int d) {
@@ -292,10 +325,12 @@ static NceWs nce_carve(void* ws, int n, int d) {
   w.split = nce_split(n, d);
   w.h1 = p; p += (size_t)n * d;
   w.h2 = p; p += (size_t)n * d;
-  w.inv1 = p; p += n;
-  w.inv2 = p; p += n;
-  w.ttl = p; p += n;
-  w.partial = p; p += (size_t)w.split * n;
+  const size_t n4 = ((size_t)n + 3) & ~(size_t)3;               // keeps every table 16-byte aligned
+  w.inv1 = p; p += n4;
+  w.inv2 = p; p += n4;
+  w.ttl = p; p += n4;
+  w.rowloss = p; p += n4;
+  w.partial = p; p += ((size_t)w.split * n + 3) & ~(size_t)3;
   w.acc = p;
   return w;
 }
@@ -321,7 +356,10 @@ static int nce_forward_d(const float* v1, const float* v2, const int32_t* rows, 
   const dim3 grid((n + C::TM - 1) / C::TM, w.split);
   nce_rowsum_kernel<D><<<grid, kNceThreads, C::smem_fwd, st>>>(w.h1, w.h2, n, n_dev, inv_t, w.split, w.partial);
   AGCF_LAUNCH_OK();
-  nce_loss_kernel<<<1, 1024, 0, st>>>(w.h1, w.h2, n, n_dev, D, inv_t, w.split, w.partial, w.ttl, loss);
+  nce_rowloss_kernel<<<(unsigned)(((long long)n * 32 + 255) / 256), 256, 0, st>>>(w.h1, w.h2, n, n_dev, D, inv_t, w.split,
+                                                                                 w.partial, w.ttl, w.rowloss);
+  AGCF_LAUNCH_OK();
+  nce_loss_kernel<<<1, 1024, 0, st>>>(w.rowloss, n, n_dev, loss);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
 }

@@ -56,6 +56,12 @@ struct SpmmParams {
   unsigned long long noise_seed;
   uint32_t noise_stream;
   const int32_t* noise_step;
+  int noise_main;             // perturb the main outputs (Y / acc_out) with the Philox stream `noise_stream`
+  // up to two extra outputs aux_Y[q] = t perturbed with their OWN noise (table aux_noise[q], else Philox stream
+  // aux_stream[q]): SimGCL's clean pass and its two perturbed passes share A E0, one launch writes all three
+  float4* aux_Y[2];
+  const float4* aux_noise[2];
+  uint32_t aux_stream[2];
   const uint32_t* row_mask;   // nullable bitmap over rows: only rows with their bit set are computed / written
   const uint32_t* col_mask;   // nullable bitmap over columns: rows of X outside it are known to be zero (skipped)
   // fused all-gather: the same rows are also stored into the peer GPUs' copies of Y / acc_out
@@ -108,6 +114,43 @@ __device__ __forceinline__ void adam_update(float& pp, float gg, float& mm, floa
   pp = pp - step_size * __fdiv_rn(mm, denom);
 }
 
+// t += sign(t) * normalize(noise) * eps for one row held by a lane group (recommender/SimGCL.py:204-205); the U[0,1)
+// noise row comes from a table or from Philox (key = seed, counter = (float4 slot, step << 32 | stream)).  Every lane
+// of the warp must call it (the row norm is a lane-group reduction); invalid rows see zero noise.
+template <typename C>
+__device__ __forceinline__ void spmm_perturb(const SpmmParams& p, size_t rbase, bool valid, int gl,
+                                             const float4* __restrict__ noise_tab, uint32_t stream, float4 (&t)[C::VPL]) {
+  float4 nz[C::VPL];
+  float ss = 0.f;
+  unsigned long long ctr_hi = 0ull;
+  if (noise_tab == nullptr)
+    ctr_hi = ((unsigned long long)(uint32_t)(p.noise_step != nullptr ? __ldg(p.noise_step) : 0) << 32) | stream;
+#pragma unroll
+  for (int v = 0; v < C::VPL; ++v) {
+    nz[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+      if (noise_tab != nullptr) {
+        nz[v] = ld_stream_f4(noise_tab + rbase + v * C::LPR + gl);
+      } else {
+        uint32_t r4[4];
+        Philox::gen(p.noise_seed, (unsigned long long)(rbase + v * C::LPR + gl), ctr_hi, r4);
+        nz[v] = make_float4((float)(r4[0] >> 8) * 5.9604644775390625e-8f, (float)(r4[1] >> 8) * 5.9604644775390625e-8f,
+                            (float)(r4[2] >> 8) * 5.9604644775390625e-8f, (float)(r4[3] >> 8) * 5.9604644775390625e-8f);
+      }
+    }
+    ss += dot4(nz[v], nz[v]);
+  }
+  ss = group_sum<C::LPR>(ss);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);   // F.normalize(dim=-1, eps=1e-12)
+#pragma unroll
+  for (int v = 0; v < C::VPL; ++v) {
+    t[v].x = t[v].x + __fmul_rn(__fmul_rn(sgnf(t[v].x), __fdiv_rn(nz[v].x, nrm)), p.eps);
+    t[v].y = t[v].y + __fmul_rn(__fmul_rn(sgnf(t[v].y), __fdiv_rn(nz[v].y, nrm)), p.eps);
+    t[v].z = t[v].z + __fmul_rn(__fmul_rn(sgnf(t[v].z), __fdiv_rn(nz[v].z, nrm)), p.eps);
+    t[v].w = t[v].w + __fmul_rn(__fmul_rn(sgnf(t[v].w), __fdiv_rn(nz[v].w, nrm)), p.eps);
+  }
+}
+
 template <typename C, bool NOISE>
 __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool valid,
                                               float4 (&t)[C::VPL], int gl, const float4* pre_add = nullptr) {
@@ -118,35 +161,19 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
       t[v] = add4(t[v], pre_add != nullptr ? pre_add[v] : ld_stream_f4(p.addend + rbase + v * C::LPR + gl));
   }
   if (NOISE) {
-    float4 nz[C::VPL];
-    float ss = 0.f;
-    unsigned long long ctr_hi = 0ull;
-    if (p.noise == nullptr)
-      ctr_hi = ((unsigned long long)(uint32_t)(p.noise_step != nullptr ? __ldg(p.noise_step) : 0) << 32) | p.noise_stream;
 #pragma unroll
-    for (int v = 0; v < C::VPL; ++v) {
-      nz[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < 2; ++q) {
+      if (p.aux_Y[q] == nullptr) continue;
+      float4 tq[C::VPL];
+#pragma unroll
+      for (int v = 0; v < C::VPL; ++v) tq[v] = t[v];
+      spmm_perturb<C>(p, rbase, valid, gl, p.aux_noise[q], p.aux_stream[q], tq);
       if (valid) {
-        if (p.noise != nullptr) {
-          nz[v] = ld_stream_f4(p.noise + rbase + v * C::LPR + gl);
-        } else {
-          uint32_t r4[4];
-          Philox::gen(p.noise_seed, (unsigned long long)(rbase + v * C::LPR + gl), ctr_hi, r4);
-          nz[v] = make_float4((float)(r4[0] >> 8) * 5.9604644775390625e-8f, (float)(r4[1] >> 8) * 5.9604644775390625e-8f,
-                              (float)(r4[2] >> 8) * 5.9604644775390625e-8f, (float)(r4[3] >> 8) * 5.9604644775390625e-8f);
-        }
-      }
-      ss += dot4(nz[v], nz[v]);
-    }
-    ss = group_sum<C::LPR>(ss);
-    const float nrm = fmaxf(sqrtf(ss), 1e-12f);   // F.normalize(dim=-1, eps=1e-12)
 #pragma unroll
-    for (int v = 0; v < C::VPL; ++v) {
-      t[v].x = t[v].x + __fmul_rn(__fmul_rn(sgnf(t[v].x), __fdiv_rn(nz[v].x, nrm)), p.eps);
-      t[v].y = t[v].y + __fmul_rn(__fmul_rn(sgnf(t[v].y), __fdiv_rn(nz[v].y, nrm)), p.eps);
-      t[v].z = t[v].z + __fmul_rn(__fmul_rn(sgnf(t[v].z), __fdiv_rn(nz[v].z, nrm)), p.eps);
-      t[v].w = t[v].w + __fmul_rn(__fmul_rn(sgnf(t[v].w), __fdiv_rn(nz[v].w, nrm)), p.eps);
+        for (int v = 0; v < C::VPL; ++v) p.aux_Y[q][rbase + v * C::LPR + gl] = tq[v];
+      }
     }
+    if (p.noise != nullptr || p.noise_main) spmm_perturb<C>(p, rbase, valid, gl, p.noise, p.noise_stream, t);
   }
   if (!valid) return;
   if (p.Y != nullptr) {
@@ -491,7 +518,8 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   if (blocks <= 0) return AGCF_OK;
   if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
   bool cmask = false;
-  if constexpr (C::EPL == 1) cmask = p.col_mask != nullptr && p.noise == nullptr && p.noise_seed == 0ull;
+  if constexpr (C::EPL == 1)
+    cmask = p.col_mask != nullptr && p.noise == nullptr && !p.noise_main && p.aux_Y[0] == nullptr && p.aux_Y[1] == nullptr;
   if (p.sched != nullptr) {                                  // persistent: every CTA resident at once
     const long long resident = (long long)kSMs * (cmask ? AGCF_SPMM_CM_MINB(D) : AGCF_SPMM_MINB(D));
     blocks = blocks < resident ? blocks : resident;
@@ -503,7 +531,7 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
       return AGCF_OK;
     }
   }
-  if (p.noise != nullptr || p.noise_seed != 0ull)
+  if (p.noise != nullptr || p.noise_main || p.aux_Y[0] != nullptr || p.aux_Y[1] != nullptr)
     spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
   else
     spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
@@ -702,6 +730,15 @@ extern "C" int agcf_spmm_csr_f32_ex(const agcf_spmm_args* a, agcf_stream_t strea
   p.noise = reinterpret_cast<const float4*>(a->noise);
   p.eps = a->eps;
   p.noise_seed = a->noise_seed; p.noise_stream = a->noise_stream; p.noise_step = a->noise_step;
+  p.noise_main = (a->noise_main != 0 && a->noise == nullptr) ? 1 : 0;
+  if (p.noise_main && a->noise_seed == 0ull) return AGCF_EINVAL;
+  for (int q = 0; q < 2; ++q) {
+    p.aux_Y[q] = reinterpret_cast<float4*>(a->aux_Y[q]);
+    p.aux_noise[q] = reinterpret_cast<const float4*>(a->aux_noise[q]);
+    p.aux_stream[q] = a->aux_stream[q];
+    if (!aligned16(a->aux_Y[q]) || !aligned16(a->aux_noise[q]) || (a->aux_Y[q] != nullptr && a->aux_Y[q] == a->X)) return AGCF_EINVAL;
+    if (a->aux_Y[q] != nullptr && a->aux_noise[q] == nullptr && a->noise_seed == 0ull) return AGCF_EINVAL;
+  }
   p.row_mask = a->row_mask; p.col_mask = a->col_mask;
   p.mc_Y = a->Y != nullptr ? reinterpret_cast<float4*>(a->mc_Y) : nullptr;
   p.mc_acc = a->acc_out != nullptr ? reinterpret_cast<float4*>(a->mc_acc) : nullptr;

@@ -531,14 +531,19 @@ class ContrastiveEngine(LightGCNEngine):
             self.Gcl = torch.zeros_like(table)
         else:
             self.Va, self.Vb = f(), f()
+            if self.L > 1:               # layer-1 tables of the three passes (they share A E0: one launch writes them)
+                self.E1, self.E1a, self.E1b = f(), f(), f()
         nbmax = (self.cap + self.B - 1) // self.B
         i32 = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=dev)
         self.cl_users, self.cl_items, self.n_cl = i32(nbmax, self.B), i32(nbmax, self.B), i32(nbmax, 2)
         self.cl_out = torch.zeros((nbmax, 2), dtype=torch.float32, device=dev)
         self.nce_ws = [ops.infonce_ws(self.B, self.d, dev), ops.infonce_ws(self.B, self.d, dev)]
+        self._side_stream = torch.cuda.Stream(device=dev)
+        self._fork_ev, self._join_ev = torch.cuda.Event(), torch.cuda.Event()
         n_prop = 1 if kind == "xsimgcl" else 3
+        shared = 2 if (kind == "simgcl" and self.L > 1) else 0       # launches saved by the shared first layer
         # SpMM (n_prop * L forward + L backward) + bpr fwd/bwd + 2 x (3 InfoNCE fwd + 2 x 2 bwd) + zero rows + coefs
-        self.launches_per_step = (n_prop + 1) * self.L + 2 + 2 * 7 + (2 if kind == "xsimgcl" else 1) + 1
+        self.launches_per_step = (n_prop + 1) * self.L - shared + 2 + 2 * 8 + (2 if kind == "xsimgcl" else 1) + 1
 
     # ------------------------------------------------------------------ set-up
     def _group(self, first_triple, n):
@@ -574,6 +579,27 @@ class ContrastiveEngine(LightGCNEngine):
             x = y
         return F
 
+    def _propagate_simgcl(self, mask, worklist):
+        """The clean pass and the two perturbed passes of a SimGCL step (L >= 2).  Layer 1 of all three is A E0 -- the
+        perturbation is added AFTER the product -- so ONE launch writes E1 (clean) and the two perturbed copies;
+        layers 2..L run per pass, the last one on the batch's rows only.  4 + 3 (L - 2) full launches instead of 3 L."""
+        tabs = self.noise_tables
+        aux = [(self.E1a, None if tabs is None else tabs[(1, 1)], 64 + 1),
+               (self.E1b, None if tabs is None else tabs[(2, 1)], 128 + 1)]
+        ops.spmm(self.g, self.E0, Y=self.E1, aux=aux, eps=self.eps, philox=(self.noise_seed, None, self.step_dev))
+        outs = []
+        for pass_id, x, F in ((None, self.E1, self.F), (1, self.E1a, self.Va), (2, self.E1b, self.Vb)):
+            first = x
+            for k in range(2, self.L + 1):
+                last = k == self.L
+                y = None if last else self.fw[k % 2]
+                wl = worklist if last else None
+                ops.spmm(self.g, x, Y=y, acc_in=first if k == 2 else F, acc_out=F, acc_div=float(self.L) if last else 1.0,
+                         row_mask=mask if (last and wl is None) else None, worklist=wl, **self._noise_kw(pass_id, k))
+                x = y
+            outs.append(F)
+        return outs
+
     def forward_table(self, out=None, row_mask=None, worklist=None):
         """the unperturbed encoder forward (model() of the reference): what predict / test read"""
         return self._propagate(self.F if out is None else out, None, row_mask, worklist)
@@ -594,22 +620,37 @@ class ContrastiveEngine(LightGCNEngine):
         if self.kind == "xsimgcl":
             F = self._propagate(self.F, 0, mask, wl, keep_layer=self.layer_cl, keep_into=self.Ecl)
             v1, v2 = F, self.Ecl
-        else:
+        elif L == 1:
             F = self._propagate(self.F, None, mask, wl)
             v1 = self._propagate(self.Va, 1, mask, wl)
             v2 = self._propagate(self.Vb, 2, mask, wl)
+        else:
+            F, v1, v2 = self._propagate_simgcl(mask, wl)
         ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)
         ops.bpr_backward(F, u, i, j, nb, self.U, self.reg, 1.0, out4, self.coef, occ, seg_off, seg_node, n_seg, self.G)
         # contrastive terms: gradients land on the rows of G (rec / SimGCL views) and, pre-scaled by L, of Gcl
         g2_table = self.Gcl if self.kind == "xsimgcl" else self.G
         g2_scale = self.cl_rate * (L if self.kind == "xsimgcl" else 1)
+        # the user-side and the item-side InfoNCE touch disjoint rows and own their workspaces: they run as two
+        # parallel branches (a forked stream; inside a capture: two branches of the CUDA graph), each of them too
+        # small (n <= B rows) to fill the GPU alone
+        main = torch.cuda.current_stream()
+        self._fork_ev.record(main)
         for side, rows in ((0, self.cl_users[b]), (1, self.cl_items[b])):
-            n_dev = self.n_cl[b, side:side + 1]
-            ws = self.nce_ws[side]
-            ops.infonce_forward(v1, v2, self.tau, rows=rows, n=B, n_dev=n_dev, loss=self.cl_out[b, side:side + 1], ws=ws)
-            ops.infonce_backward(B, self.d, self.tau, ws, scale=self.cl_rate, n_dev=n_dev, grad1=self.G, rows1=rows, acc1=True)
-            ops.infonce_backward(B, self.d, self.tau, ws, scale=g2_scale, n_dev=n_dev, grad2=g2_table, rows2=rows,
-                                 acc2=self.kind != "xsimgcl")
+            stream = main if side == 0 else self._side_stream
+            if side == 1:
+                stream.wait_event(self._fork_ev)
+            with torch.cuda.stream(stream):
+                n_dev = self.n_cl[b, side:side + 1]
+                ws = self.nce_ws[side]
+                ops.infonce_forward(v1, v2, self.tau, rows=rows, n=B, n_dev=n_dev, loss=self.cl_out[b, side:side + 1], ws=ws)
+                ops.infonce_backward(B, self.d, self.tau, ws, scale=self.cl_rate, n_dev=n_dev, grad1=self.G, rows1=rows,
+                                     acc1=True)
+                ops.infonce_backward(B, self.d, self.tau, ws, scale=g2_scale, n_dev=n_dev, grad2=g2_table, rows2=rows,
+                                     acc2=self.kind != "xsimgcl")
+                if side == 1:
+                    self._join_ev.record(stream)
+        main.wait_event(self._join_ev)
         # backward: D_L = G;  D_{k-1} = A D_k + G (+ Gcl where layer k-1 is the CL view);  dE0 = A D_1 / L
         adam = (self.E0, self.m, self.v, self.adam_coefs, self.betas[0], self.betas[1], self.adam_eps)
         H = self.G

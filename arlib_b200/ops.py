@@ -36,7 +36,7 @@ def _p(t):
 
 def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_div=1.0, noise=None, eps=0.0,
          row_mask=None, col_mask=None, peer_Y=None, peer_acc=None, mc_Y=None, mc_acc=None,
-         worklist=None, adam=None, zero_acc_in=False, persistent=None, philox=None):
+         worklist=None, adam=None, zero_acc_in=False, persistent=None, philox=None, aux=None):
     """agcf_spmm_csr_f32_ex: t = A X (+addend) (+noise perturbation); Y = t;
     acc_out = (acc_in + t) / acc_div.
 
@@ -44,7 +44,9 @@ def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_
     (spmm_batch_worklists) instead of the graph's; adam = (p, m, v, coefs, beta1, beta2, eps): the optimizer
     fused into the epilogue; zero_acc_in: re-zero the non-zero rows of acc_in; persistent (default: the graph's
     setting): persistent CTAs with dynamic block scheduling instead of one CTA per block; philox = (seed, stream,
-    step_dev or None): draw the perturbation noise in the epilogue instead of reading ``noise``."""
+    step_dev or None): draw the perturbation noise in the epilogue instead of reading ``noise`` (stream None: no
+    main perturbation, the seed / step only serve ``aux``); aux = up to two (Y_q, noise table or None, stream) extra
+    outputs perturbed with their own noise."""
     lib = _lib.load()
     _f32(X, "X"); _f32(Y, "Y"); _f32(addend, "addend"); _f32(acc_in, "acc_in"); _f32(acc_out, "acc_out"); _f32(noise, "noise")
     if X.shape[0] != g.n_rows:
@@ -72,9 +74,16 @@ def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_
     a.acc_in, a.acc_out, a.acc_div = _p(acc_in), _p(acc_out), float(acc_div)
     a.noise, a.eps = _p(noise), float(eps)
     if philox is not None:
-        if noise is not None or int(philox[0]) == 0:
+        if int(philox[0]) == 0 or (noise is not None and philox[1] is not None):
             raise ValueError("philox noise needs a non-zero seed and no noise table")
-        a.noise_seed, a.noise_stream, a.noise_step = int(philox[0]) & (2 ** 64 - 1), int(philox[1]), _p(philox[2])
+        a.noise_seed, a.noise_step = int(philox[0]) & (2 ** 64 - 1), _p(philox[2])
+        if philox[1] is not None:
+            a.noise_stream, a.noise_main = int(philox[1]), 1
+    for q, (y_q, tab_q, stream_q) in enumerate(aux or ()):
+        _f32(y_q, "aux Y"); _f32(tab_q, "aux noise")
+        if tuple(y_q.shape) != (g.n_rows, d) or (tab_q is not None and tuple(tab_q.shape) != (g.n_rows, d)):
+            raise ValueError("aux operand shape mismatch")
+        a.aux_Y[q], a.aux_noise[q], a.aux_stream[q] = y_q.data_ptr(), _p(tab_q), int(stream_q or 0)
     a.row_mask, a.col_mask = _p(row_mask), _p(col_mask)
     a.peer_Y_host = ctypes.cast(py, ctypes.c_void_p) if py is not None else None
     a.peer_acc_host = ctypes.cast(pa, ctypes.c_void_p) if pa is not None else None

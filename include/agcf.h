@@ -109,9 +109,13 @@ int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int32_t n_vrow
  *                 acc_out may then be null (the gradient table is never written).  Same bits as agcf_adam_step_f32;
  *   zero_acc_in   != 0: rows of acc_in that were non-zero are set to zero after they were read (acc_in is the batch
  *                 gradient G, non-zero on <= 3B rows: replaces agcf_zero_rows); acc_in must not be X;
- *   noise_seed    != 0 (and noise == null): the U[0,1) noise of the SimGCL / XSimGCL perturbation is drawn IN the
+ *   noise_main    != 0: perturb the main outputs with the Philox stream below (instead of a `noise` table);
+ *   aux_Y[q]      q < 2, nullable: extra outputs aux_Y[q][i,:] = t[i,:] perturbed with their OWN noise (table aux_noise[q]
+ *                 if given, else Philox stream aux_stream[q]) while Y / acc_out stay clean (or take the main noise):
+ *                 SimGCL's clean pass and its two perturbed passes share A E0, one launch writes all three tables;
+ *   noise_seed    != 0: the U[0,1) noise of the SimGCL / XSimGCL perturbation is drawn IN the
  *                 epilogue -- Philox4x32-10, key = noise_seed, counter = (float4 slot of the element,
- *                 *noise_step << 32 | noise_stream) -- instead of read from an [rows, d] table; noise_stream tells
+ *                 *noise_step << 32 | noise_stream) -- instead of read from an [rows, d] table; noise_stream / aux_stream tell
  *                 layers / passes apart, noise_step (nullable device int32) is the training-step counter, so a
  *                 replayed CUDA graph perturbs every step differently;
  *   sched         nullable device int32[2], zero on entry and zero again on exit: the launch then runs PERSISTENT CTAs
@@ -127,7 +131,8 @@ typedef struct agcf_spmm_args {
   const float* X; float* Y; const float* addend;
   const float* acc_in; float* acc_out; float acc_div;
   const float* noise; float eps;
-  uint64_t noise_seed; uint32_t noise_stream; const int32_t* noise_step;
+  uint64_t noise_seed; uint32_t noise_stream; const int32_t* noise_step; int32_t noise_main;
+  float* aux_Y[2]; const float* aux_noise[2]; uint32_t aux_stream[2];
   const uint32_t* row_mask; const uint32_t* col_mask;
   void* const* peer_Y_host; void* const* peer_acc_host; int32_t n_peers;
   void* mc_Y; void* mc_acc;

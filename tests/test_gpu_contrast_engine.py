@@ -94,32 +94,33 @@ def test_contrastive_engine_matches_the_reference_loop(kind, tau, use_graph):
 
 
 @pytest.mark.parametrize("cl_rate", [0.2, 0.0, 5.0])
-@pytest.mark.parametrize("kind,tau", [("xsimgcl", 0.1), ("simgcl", 0.2)])
-def test_first_batch_gradient_is_the_reference_gradient(kind, tau, cl_rate, monkeypatch):
+@pytest.mark.parametrize("kind,tau,n_layers,layer_cl", [("xsimgcl", 0.1, 2, 1), ("simgcl", 0.2, 2, 0), ("xsimgcl", 0.1, 3, 1),
+                                                        ("xsimgcl", 0.1, 3, 2), ("simgcl", 0.2, 3, 0), ("simgcl", 0.2, 1, 0)])
+def test_first_batch_gradient_is_the_reference_gradient(kind, tau, n_layers, layer_cl, cl_rate):
     """The well-conditioned form of the parity check: dLoss/dE0 of one batch, recovered from Adam's first moment
-    after one step (m = 0.1 g), against torch autograd through the reference expressions: 1e-5 of the largest entry."""
-    import sys
+    after one step (m = 0.1 g), against torch autograd through the reference expressions: 1e-5 of the largest entry.
+    Also at depths the reference hard-codes away (n_layers = 1, 3; layer_cl = 2)."""
     from arlib_b200.engine import ContrastiveEngine
-    monkeypatch.setattr(sys.modules[__name__], "CL_RATE", cl_rate)
+    nl = n_layers
     g, adj, ue, ie, triples, noise = _setup()
     triples = tuple(x[:B] for x in triples)
-    keys = [(0, 1), (0, 2)] if kind == "xsimgcl" else [(1, 1), (1, 2), (2, 1), (2, 2)]
-    noises = {k: noise() for k in keys}
+    passes = (0,) if kind == "xsimgcl" else (1, 2)
+    noises = {(p, k): noise() for p in passes for k in range(1, nl + 1)}
     ue_, ie_ = ue.clone().requires_grad_(True), ie.clone().requires_grad_(True)
     u, i, j = (torch.from_numpy(x.astype(np.int64)) for x in triples)
     uu, ii = torch.unique(u), torch.unique(i)
     if kind == "xsimgcl":
-        ru, ri, cu, ci = port.xsimgcl_forward(adj, ue_, ie_, L, EPS, 1, [noises[(0, 1)], noises[(0, 2)]])
+        ru, ri, cu, ci = port.xsimgcl_forward(adj, ue_, ie_, nl, EPS, layer_cl, [noises[(0, k)] for k in range(1, nl + 1)])
         cl = port.infonce(ru[uu], cu[uu], tau) + port.infonce(ri[ii], ci[ii], tau)
     else:
-        ru, ri = port.simgcl_forward(adj, ue_, ie_, L, EPS, None)
-        au, ai = port.simgcl_forward(adj, ue_, ie_, L, EPS, [noises[(1, 1)], noises[(1, 2)]])
-        bu_, bi_ = port.simgcl_forward(adj, ue_, ie_, L, EPS, [noises[(2, 1)], noises[(2, 2)]])
+        ru, ri = port.simgcl_forward(adj, ue_, ie_, nl, EPS, None)
+        au, ai = port.simgcl_forward(adj, ue_, ie_, nl, EPS, [noises[(1, k)] for k in range(1, nl + 1)])
+        bu_, bi_ = port.simgcl_forward(adj, ue_, ie_, nl, EPS, [noises[(2, k)] for k in range(1, nl + 1)])
         cl = port.infonce(au[uu], bu_[uu], tau) + port.infonce(ai[ii], bi_[ii], tau)
     (port.bpr_loss(ru[u], ri[i], ri[j]) + port.l2_reg_loss(REG, ru[u], ri[i]) + cl_rate * cl).backward()
     gref = torch.cat([ue_.grad, ie_.grad])
     table = torch.cat([ue, ie]).to(DEV)
-    eng = ContrastiveEngine(g, table, U, kind, L, EPS, cl_rate, tau, LR, REG, B, B,
+    eng = ContrastiveEngine(g, table, U, kind, nl, EPS, cl_rate, tau, LR, REG, B, B, layer_cl=max(layer_cl, 1),
                             noise_tables={k: v.to(DEV) for k, v in noises.items()})
     eng.set_triples(*triples)
     eng.run_steps(0, 1, use_graph=False)
