@@ -314,8 +314,28 @@ def run_ours(args):
     for kind, a, b_ in spmm_ms:
         by_kind.setdefault(kind, []).append(a.elapsed_time(b_))
     # the roofline figure is for the FULL launches (the contract bytes B_spmm are those of a full propagation);
-    # the two batch-sparse launches of a step move fewer bytes and are reported beside it
-    spmm_avg_ms = float(np.mean(by_kind["full"]))
+    # the two batch-sparse launches of a step move fewer bytes and are reported beside it.  An event pair around a
+    # single eager launch also sees the launch gap (~5-8 us); the kernel's own duration inside the replayed graph is
+    # measured with one event pair around 100 back-to-back launches of each full-launch configuration of the step
+    # (forward layer 1, forward layer 2, a middle backward layer) on the engine's own tables.
+    eager_full_ms = float(np.mean(by_kind["full"]))
+    spmm_avg_ms = eager_full_ms
+    if eng.mode != "rows" and L > 1:
+        cfgs = [lambda: orig(eng.g, eng.E0, Y=eng.fw[0], acc_in=eng.E0, acc_out=eng.F),
+                lambda: orig(eng.g, eng.fw[0], Y=eng.fw[1], acc_in=eng.F, acc_out=eng.F),
+                lambda: orig(eng.g, eng.bw[0], Y=eng.bw[1], addend=eng.G)]
+        per_cfg = []
+        for fn in cfgs:
+            for _ in range(10):
+                fn()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for _ in range(100):
+                fn()
+            b1.record()
+            torch.cuda.synchronize()
+            per_cfg.append(b0.elapsed_time(b1) / 100)
+        spmm_avg_ms = float(np.mean(per_cfg))
     b_spmm, b_step = algorithmic_bytes(N, g.nnz, d, L, B)
     if eng.mode == "dshard":        # per-GPU launch: whole graph, a [N, d/P] slice of the tables
         b_spmm = g.nnz * 8 + (N + 1) * 4 + 2 * N * eng.d * 4
@@ -337,6 +357,7 @@ def run_ours(args):
     roofline = {"kernel": "spmm_csr_kernel<%d>" % eng.d, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": b_spmm, "avg_launch_ms": spmm_avg_ms,
+                "avg_launch_ms_eager_single": eager_full_ms,
                 "launches_per_step": 2 * L, "full_launches_per_step": len(by_kind["full"]) // max(1, min(K, 50)),
                 "batch_sparse_launch_ms": {k: float(np.mean(v)) for k, v in by_kind.items() if k != "full"},
                 "step_algorithmic_bytes": b_step,
