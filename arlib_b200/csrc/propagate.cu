@@ -331,51 +331,59 @@ extern "C" int agcf_debug_spmm_trace(unsigned long long* host_out) {
 template <typename C>
 __device__ __forceinline__ void spmm_accumulate_masked(const SpmmParams& p, int s, int len, int iters, int gl, int grp,
                                                        float4 (&acc)[C::VPL]) {
-  static_assert(C::EPL == 1, "masked path: one entry per lane and chunk");
-  int c_next = -1;
-  float v_next = 0.f;
+  // chunk layout as in the dense loop: lane gl holds entries k * LPR + gl (k < EPL) of a CH-entry chunk
+  int c_next[C::EPL];
+  float v_next[C::EPL];
   auto load_chunk = [&](int off) {
-    c_next = -1;
-    v_next = 0.f;
-    const int e = off + gl;
-    if (e < len) {
-      c_next = ld_stream_i32(p.col + s + e);
-      v_next = ld_stream_f32(p.val + s + e);
+#pragma unroll
+    for (int k = 0; k < C::EPL; ++k) {
+      c_next[k] = -1;
+      v_next[k] = 0.f;
+      const int e = off + k * C::LPR + gl;
+      if (e < len) {
+        c_next[k] = C::EPL > 1 ? __ldg(p.col + s + e) : ld_stream_i32(p.col + s + e);
+        v_next[k] = C::EPL > 1 ? __ldg(p.val + s + e) : ld_stream_f32(p.val + s + e);
+      }
     }
   };
   load_chunk(0);
-  for (int it = 0, off = 0; it < iters; ++it, off += C::LPR) {
-    const int c = c_next;
-    const float v = v_next;
-    load_chunk(off + C::LPR);
-    const bool live = c >= 0 && bit_set(p.col_mask, c);
-    unsigned bits = __ballot_sync(0xffffffffu, live);
-    if constexpr (C::LPR < 32) bits = (bits >> (grp * C::LPR)) & ((1u << C::LPR) - 1u);
-    while (__any_sync(0xffffffffu, bits != 0u)) {
-      // two live entries per trip: both gathers are in flight together
-      const bool on0 = bits != 0u;
-      const int t0 = on0 ? __ffs(bits) - 1 : 0;
-      bits &= bits - 1u;
-      const bool on1 = bits != 0u;
-      const int t1 = on1 ? __ffs(bits) - 1 : 0;
-      bits &= bits - 1u;
-      const int c0 = __shfl_sync(0xffffffffu, c, t0, C::LPR);
-      const float v0 = __shfl_sync(0xffffffffu, v, t0, C::LPR);
-      const int c1 = __shfl_sync(0xffffffffu, c, t1, C::LPR);
-      const float v1 = __shfl_sync(0xffffffffu, v, t1, C::LPR);
-      float4 x0[C::VPL], x1[C::VPL];
+  for (int it = 0, off = 0; it < iters; ++it, off += C::CH) {
+    int c[C::EPL];
+    float v[C::EPL];
 #pragma unroll
-      for (int vv = 0; vv < C::VPL; ++vv) {
-        x0[vv] = on0 ? ld_gather_f4(p.X + (size_t)c0 * C::V4 + vv * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
-        x1[vv] = on1 ? ld_gather_f4(p.X + (size_t)c1 * C::V4 + vv * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (on0) {
+    for (int k = 0; k < C::EPL; ++k) { c[k] = c_next[k]; v[k] = v_next[k]; }
+    load_chunk(off + C::CH);
 #pragma unroll
-        for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], v0, x0[vv]);
-      }
-      if (on1) {
+    for (int k = 0; k < C::EPL; ++k) {
+      const bool live = c[k] >= 0 && bit_set(p.col_mask, c[k]);
+      unsigned bits = __ballot_sync(0xffffffffu, live);
+      if constexpr (C::LPR < 32) bits = (bits >> (grp * C::LPR)) & ((1u << C::LPR) - 1u);
+      while (__any_sync(0xffffffffu, bits != 0u)) {
+        // two live entries per trip: both gathers are in flight together
+        const bool on0 = bits != 0u;
+        const int t0 = on0 ? __ffs(bits) - 1 : 0;
+        bits &= bits - 1u;
+        const bool on1 = bits != 0u;
+        const int t1 = on1 ? __ffs(bits) - 1 : 0;
+        bits &= bits - 1u;
+        const int c0 = __shfl_sync(0xffffffffu, c[k], t0, C::LPR);
+        const float v0 = __shfl_sync(0xffffffffu, v[k], t0, C::LPR);
+        const int c1 = __shfl_sync(0xffffffffu, c[k], t1, C::LPR);
+        const float v1 = __shfl_sync(0xffffffffu, v[k], t1, C::LPR);
+        float4 x0[C::VPL], x1[C::VPL];
 #pragma unroll
-        for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], v1, x1[vv]);
+        for (int vv = 0; vv < C::VPL; ++vv) {
+          x0[vv] = on0 ? ld_gather_f4(p.X + (size_t)c0 * C::V4 + vv * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+          x1[vv] = on1 ? ld_gather_f4(p.X + (size_t)c1 * C::V4 + vv * C::LPR + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (on0) {
+#pragma unroll
+          for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], v0, x0[vv]);
+        }
+        if (on1) {
+#pragma unroll
+          for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], v1, x1[vv]);
+        }
       }
     }
   }
@@ -411,7 +419,7 @@ __device__ __forceinline__ void spmm_block(const SpmmParams& p, const int n_v, c
   AGCF_TRACE_AFTER(1, maxlen + row);
   float4 pre[C::VPL];                                      // CMASK: the epilogue's addend row, fetched before the gathers
   if constexpr (CMASK) {
-    const int iters = (maxlen + C::LPR - 1) / C::LPR;      // warp-uniform
+    const int iters = (maxlen + C::CH - 1) / C::CH;        // warp-uniform
     const bool has_add = p.addend != nullptr && valid;
 #pragma unroll
     for (int v = 0; v < C::VPL; ++v)
@@ -505,7 +513,7 @@ __global__ void __launch_bounds__(256, MINB) spmm_colmask_kernel(const SpmmParam
 #define AGCF_SPMM_MINB(D) ((D) <= 64 ? 4 : ((D) == 128 ? 3 : 2))
 #endif
 #ifndef AGCF_SPMM_CM_MINB
-#define AGCF_SPMM_CM_MINB(D) ((D) <= 64 ? 5 : ((D) == 128 ? 4 : 3))
+#define AGCF_SPMM_CM_MINB(D) ((D) < 64 ? 4 : ((D) == 64 ? 5 : ((D) == 128 ? 4 : 3)))
 #endif
 
 template <int D>
@@ -517,19 +525,15 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   long long blocks = ((long long)p.n_v + C::RPB - 1) / C::RPB;
   if (blocks <= 0) return AGCF_OK;
   if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
-  bool cmask = false;
-  if constexpr (C::EPL == 1)
-    cmask = p.col_mask != nullptr && p.noise == nullptr && !p.noise_main && p.aux_Y[0] == nullptr && p.aux_Y[1] == nullptr;
+  const bool cmask = p.col_mask != nullptr && p.noise == nullptr && !p.noise_main && p.aux_Y[0] == nullptr && p.aux_Y[1] == nullptr;
   if (p.sched != nullptr) {                                  // persistent: every CTA resident at once
     const long long resident = (long long)kSMs * (cmask ? AGCF_SPMM_CM_MINB(D) : AGCF_SPMM_MINB(D));
     blocks = blocks < resident ? blocks : resident;
   }
-  if constexpr (C::EPL == 1) {
-    if (cmask) {
-      spmm_colmask_kernel<D, LPR, AGCF_SPMM_CM_MINB(D)><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
-      AGCF_LAUNCH_OK();
-      return AGCF_OK;
-    }
+  if (cmask) {
+    spmm_colmask_kernel<D, LPR, AGCF_SPMM_CM_MINB(D)><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+    AGCF_LAUNCH_OK();
+    return AGCF_OK;
   }
   if (p.noise != nullptr || p.noise_main || p.aux_Y[0] != nullptr || p.aux_Y[1] != nullptr)
     spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);

@@ -123,8 +123,8 @@ int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int32_t n_vrow
  *                 of one CTA per block -- no CTA turnover gaps and no tail of idle SMs; launches sharing it must be
  *                 stream-ordered;
  *   flags         reserved, must be 0.
- * A launch with col_mask (and no noise) at d >= 64 runs the sparse variant (ballot over the live entries of a
- * chunk, twice the resident warps): identical results. */
+ * A launch with col_mask (and no noise) runs the sparse variant (ballot over the live entries of a chunk, only
+ * those are gathered): identical results. */
 typedef struct agcf_spmm_args {
   const int32_t* vrows; const int32_t* vpart; int32_t n_vrows; const int32_t* n_vrows_dev;
   const int32_t* col; const float* val; float* partial; int32_t* tickets;
