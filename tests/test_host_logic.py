@@ -1,0 +1,77 @@
+"""CPU-side checks of host logic that needs no device: the util functions' CPU-tensor behaviour (the reference's
+own torch expressions), the no-CPU-fallback guards of the fused entry points, and the header <-> ctypes mirror
+of struct agcf_spmm_args."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_infonce_on_cpu_tensors_is_the_reference_expression():
+    from arlib_b200.util.loss import InfoNCE
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(40, 64, generator=g), torch.randn(40, 64, generator=g)
+    a1, b1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    a2, b2 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    l1, l2 = InfoNCE(a1, b1, 0.2), port.infonce(a2, b2, 0.2)
+    l1.backward(); l2.backward()
+    assert torch.equal(l1, l2) and torch.equal(a1.grad, a2.grad) and torch.equal(b1.grad, b2.grad)
+
+
+def test_device_only_entry_points_refuse_cpu_tensors():
+    """No CPU fallback: the fused helpers raise instead of silently computing on the host."""
+    from arlib_b200.util.algorithm import masked_score_topk
+    from arlib_b200.util.metrics import AttackMetric
+    with pytest.raises(TypeError):
+        masked_score_topk(torch.randn(4, 64), torch.randn(9, 64), 3)
+    rec = types.SimpleNamespace(user_emb=torch.randn(4, 64), item_emb=torch.randn(9, 64),
+                                data=types.SimpleNamespace(user={"a": 0}, item={"x": 0}))
+    with pytest.raises(TypeError):
+        AttackMetric(rec, ["x"], [3]).hitRate()
+
+
+def test_spmm_args_struct_mirrors_the_header_field_for_field():
+    from arlib_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "agcf.h")).read()
+    body = re.search(r"typedef struct agcf_spmm_args \{(.*?)\} agcf_spmm_args;", text, re.S).group(1)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.search(r"(\w+)(\[\d+\])?$", decl)
+        names.append(m.group(1))
+    assert names == [f[0] for f in _lib.SpmmArgs._fields_]
+    # natural C alignment on LP64: pointers and uint64 8 bytes, int32 / float 4 bytes
+    a = _lib.SpmmArgs()
+    assert ctypes.sizeof(a) % 8 == 0
+    assert _lib.SpmmArgs.noise_seed.offset % 8 == 0 and _lib.SpmmArgs.aux_Y.offset % 8 == 0
+
+
+def test_fused_path_selection_and_sample_epoch_counter():
+    from arlib_b200.recommender._base import GraphRecommender
+    rec = GraphRecommender.__new__(GraphRecommender)
+    rec.args = types.SimpleNamespace(batch_size=2048)
+    assert rec._fused_ok()
+    rec.args = types.SimpleNamespace(batch_size=6000)            # 3 B > 16384: the single-CTA grouping cannot sort it
+    assert not rec._fused_ok()
+    rec.args = types.SimpleNamespace(batch_size=2048, fused=False)
+    assert not rec._fused_ok()
+    assert [rec._next_sample_epoch() for _ in range(3)] == [0, 1, 2]      # keeps counting across train() calls
+
+
+def test_unique_ids_like_reference_round_trips_through_float32():
+    from arlib_b200.encoder import unique_ids_like_reference
+    ids = [5, 3, 5, 2 ** 24 + 1, 3]
+    want = torch.unique(torch.Tensor(ids).type(torch.long))          # recommender/SimGCL.py:213
+    assert torch.equal(unique_ids_like_reference(ids, "cpu"), want)
+    assert torch.equal(unique_ids_like_reference(torch.tensor(ids), "cpu"), want)
+    assert int(want[-1]) == 2 ** 24                                    # the reference's float32 rounding is kept
