@@ -87,7 +87,13 @@ __device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ m, int k) {
   return (__ldg(m + (k >> 5)) >> (k & 31)) & 1u;
 }
 
-constexpr int default_lpr(int d) { return d / 4 < 32 ? d / 4 : 32; }   // one float4 per lane up to d = 128
+// lanes per row: one float4 per lane up to d = 64.  d = 128 rows are held by 16 lanes x 2 float4 (AGCF_SPMM_LPR128, tuning
+// builds override it): a warp per row meant 2.5x the work items per non-zero of the d = 64 mapping and their fixed costs --
+// measured on B200, Amazon-book shape: 315 us (32 lanes, 3 CTAs / SM) -> 249 us (16 lanes, 3 CTAs) -> 215 us (16 lanes, 4 CTAs)
+#ifndef AGCF_SPMM_LPR128
+#define AGCF_SPMM_LPR128 16
+#endif
+constexpr int default_lpr(int d) { return d == 128 ? AGCF_SPMM_LPR128 : (d / 4 < 32 ? d / 4 : 32); }
 
 template <int D, int LPR_ = default_lpr(D)>
 struct RowCfg {
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(256, MINB) spmm_colmask_kernel(const SpmmParam
 
 // resident CTAs per SM the register allocation is held to: 4 (<= 64 registers) measured best at d <= 64
 #ifndef AGCF_SPMM_MINB
-#define AGCF_SPMM_MINB(D) ((D) <= 64 ? 4 : ((D) == 128 ? 3 : 2))
+#define AGCF_SPMM_MINB(D) ((D) <= 128 ? 4 : 2)
 #endif
 #ifndef AGCF_SPMM_CM_MINB
 #define AGCF_SPMM_CM_MINB(D) ((D) < 64 ? 4 : ((D) == 64 ? 5 : ((D) == 128 ? 4 : 3)))
