@@ -308,7 +308,7 @@ static int nce_tile(int d) { return d <= 64 ? 64 : 32; }
 
 static int nce_split(int n, int d) {
   const int nt = (n + nce_tile(d) - 1) / nce_tile(d);
-  int s = (2 * kSMs + nt - 1) / nt;                          // ~2 CTAs per SM in flight
+  int s = (2 * kSMs + nt - 1) / nt;                          // ~2 CTAs per SM per launch; the user and item sides run concurrently
   s = s < 1 ? 1 : s;
   s = s > nt ? nt : s;
   return s > 16 ? 16 : s;

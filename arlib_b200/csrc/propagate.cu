@@ -93,7 +93,10 @@ __device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ m, int k) {
 #ifndef AGCF_SPMM_LPR128
 #define AGCF_SPMM_LPR128 16
 #endif
-constexpr int default_lpr(int d) { return d == 128 ? AGCF_SPMM_LPR128 : (d / 4 < 32 ? d / 4 : 32); }
+#ifndef AGCF_SPMM_LPR64
+#define AGCF_SPMM_LPR64 16
+#endif
+constexpr int default_lpr(int d) { return d == 128 ? AGCF_SPMM_LPR128 : (d == 64 ? AGCF_SPMM_LPR64 : (d / 4 < 32 ? d / 4 : 32)); }
 
 template <int D, int LPR_ = default_lpr(D)>
 struct RowCfg {
