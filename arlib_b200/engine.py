@@ -510,12 +510,12 @@ class ContrastiveEngine(LightGCNEngine):
     kind "simgcl": clean pass for the rec view + two perturbed passes for the CL views."""
 
     def __init__(self, graph, table, n_users, kind, n_layers, eps, cl_rate, tau, lr, reg, batch_size, max_triples,
-                 layer_cl=1, noise_seed=0x5eed5eed, noise_tables=None):
+                 layer_cl=1, noise_seed=0x5eed5eed, noise_tables=None, betas=(0.9, 0.999), adam_eps=1e-8):
         if kind not in ("simgcl", "xsimgcl"):
             raise ValueError("kind must be 'simgcl' or 'xsimgcl'")
         if kind == "xsimgcl" and not (1 <= layer_cl < n_layers):
             raise ValueError("the fused XSimGCL step needs 1 <= layer_cl < n_layers")
-        super().__init__(graph, table, n_users, n_layers, lr, reg, batch_size, max_triples)
+        super().__init__(graph, table, n_users, n_layers, lr, reg, batch_size, max_triples, betas=betas, adam_eps=adam_eps)
         if not self.sparse_layers:
             raise ValueError("graph too large for the per-batch bitmaps of the fused contrastive step")
         dev = table.device

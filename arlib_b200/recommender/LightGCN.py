@@ -28,8 +28,10 @@ class LightGCN(GraphRecommender):
         self.bestPerformance = []
         model = self.model.cuda()
         maxEpoch = Epoch if Epoch else self.args.maxEpoch
-        if optimizer is None and not requires_adjgrad and not requires_embgrad and self._fused_ok():
-            self._train_fused(model, maxEpoch, evalNum)
+        exports = requires_adjgrad or requires_embgrad
+        adam = self._fusable_adam(optimizer, model) if optimizer is not None and not exports else None
+        if (optimizer is None or adam is not None) and not exports and self._fused_ok():
+            self._train_fused(model, maxEpoch, evalNum, optimizer, adam)
             self.user_emb, self.item_emb = self.best_user_emb, self.best_item_emb
             return None
         if optimizer is None:
@@ -61,14 +63,19 @@ class LightGCN(GraphRecommender):
         return self._train_returns(requires_adjgrad, requires_embgrad)
 
     # -------------------------------------------------------------- fused path
-    def _train_fused(self, model, maxEpoch, evalNum):
+    def _train_fused(self, model, maxEpoch, evalNum, optimizer=None, adam=None):
+        """optimizer / adam: the caller's plain torch.optim.Adam over the two embedding parameters (_fusable_adam);
+        the engine starts from its state and hands it back, so the caller can keep stepping it."""
         table = model.parameter_table()
         dev = table.device
         mode = self._sampler_mode()
         n_edges = len(self.data.training_data)
-        eng = LightGCNEngine(model._graph, table, self.data.user_num, model.layers, self.args.lRate, self.args.reg,
-                             self.args.batch_size, n_edges)
-        ts = DeviceTrainSet(self.data, dev) if mode == 'device' else None
+        adam = adam or {"lr": self.args.lRate, "betas": (0.9, 0.999), "eps": 1e-8}
+        eng = LightGCNEngine(model._graph, table, self.data.user_num, model.layers, adam["lr"], self.args.reg,
+                             self.args.batch_size, n_edges, betas=adam["betas"], adam_eps=adam["eps"])
+        if optimizer is not None:
+            self._adam_state_to_engine(optimizer, model, eng, self.data.user_num)
+        ts = self._device_train_set(dev) if mode == 'device' else None
         seed = int(getattr(self.args, 'seed', 0) or 0)
         for epoch in range(maxEpoch):
             if mode == 'device':
@@ -78,7 +85,7 @@ class LightGCN(GraphRecommender):
                 for u, i, j in next_batch_pairwise(self.data, self.args.batch_size):
                     us += u; is_ += i; js += j
                 eng.set_triples(us, is_, js)
-            losses = eng.run_steps(0)
+            losses = eng.run_steps(0, use_graph=self._graph_pays_off(maxEpoch))
             host = losses[::1000, 0].cpu().tolist()
             for k, v in enumerate(host):
                 print('training:', epoch + 1, 'batch', k * 1000, 'batch_loss:', v)
@@ -89,3 +96,5 @@ class LightGCN(GraphRecommender):
             if epoch % evalNum == 0:
                 self.evaluate(epoch)
         self.last_train_losses = eng.out4[:eng.n_batches].clone()
+        if optimizer is not None:
+            self._adam_state_from_engine(optimizer, model, eng, self.data.user_num)

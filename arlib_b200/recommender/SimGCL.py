@@ -25,8 +25,10 @@ class SimGCL(GraphRecommender):
         self.bestPerformance = []
         model = self.model.cuda()
         maxEpoch = Epoch if Epoch else self.args.maxEpoch
-        if optimizer is None and not requires_adjgrad and not requires_embgrad and self._fused_ok():
-            self._train_fused_contrastive(model, maxEpoch, evalNum, "simgcl")
+        exports = requires_adjgrad or requires_embgrad
+        adam = self._fusable_adam(optimizer, model) if optimizer is not None and not exports else None
+        if (optimizer is None or adam is not None) and not exports and self._fused_ok():
+            self._train_fused_contrastive(model, maxEpoch, evalNum, "simgcl", optimizer=optimizer, adam=adam)
             self.user_emb, self.item_emb = self.best_user_emb, self.best_item_emb
             return None
         if optimizer is None:

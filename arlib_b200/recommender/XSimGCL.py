@@ -33,9 +33,11 @@ class XSimGCL(GraphRecommender):
         self.bestPerformance = []
         model = self.model.cuda()
         maxEpoch = Epoch if Epoch else self.args.maxEpoch
-        if optimizer is None and not requires_adjgrad and not requires_embgrad and self._fused_ok() \
+        exports = requires_adjgrad or requires_embgrad
+        adam = self._fusable_adam(optimizer, model) if optimizer is not None and not exports else None
+        if (optimizer is None or adam is not None) and not exports and self._fused_ok() \
                 and 1 <= self.layer_cl < self.n_layers:
-            self._train_fused_contrastive(model, maxEpoch, evalNum, "xsimgcl", self.layer_cl)
+            self._train_fused_contrastive(model, maxEpoch, evalNum, "xsimgcl", self.layer_cl, optimizer=optimizer, adam=adam)
             self.user_emb, self.item_emb = self.best_user_emb, self.best_item_emb
             return None
         if optimizer is None:

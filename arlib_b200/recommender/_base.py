@@ -63,6 +63,64 @@ class GraphRecommender(object):
         on = getattr(self.args, 'fused', os.environ.get('ARLIB_B200_FUSED', '1'))
         return str(on).lower() not in ('0', 'false') and 3 * self.args.batch_size <= 16384
 
+    # --------------------------------------------------- caller's torch.optim.Adam on the fused engines
+    @staticmethod
+    def _fusable_adam(optimizer, model):
+        """The attacks hand ``train()`` their own optimizer (18 call sites, e.g. attack/White/CLeaR.py:145-146), nearly
+        always ``torch.optim.Adam(model.parameters(), lr)``.  If it is exactly that -- plain Adam (no amsgrad / weight
+        decay / maximize), ONE param group whose tensors ARE the model's two embedding parameters -- the fused engine
+        can stand in for ``optimizer.step()``: it starts from the optimizer's state and writes it back.  Anything
+        else (another optimizer class, stale parameters built before a re-``__init__`` -- a reference quirk callers
+        rely on) returns None and takes the reference-shaped loop."""
+        if type(optimizer) is not torch.optim.Adam or len(optimizer.param_groups) != 1:
+            return None
+        g = optimizer.param_groups[0]
+        want = [model.embedding_dict['user_emb'], model.embedding_dict['item_emb']]
+        params = list(g['params'])
+        if len(params) != 2 or {id(a) for a in params} != {id(b) for b in want} or len(list(model.parameters())) != 2:
+            return None
+        if g.get('amsgrad') or g.get('weight_decay', 0) != 0 or g.get('maximize') or g.get('differentiable'):
+            return None
+        if torch.is_tensor(g['lr']) or g.get('decoupled_weight_decay'):
+            return None
+        steps = [float(optimizer.state[p]['step']) for p in params if len(optimizer.state.get(p, {}))]
+        if len(steps) == 1 or (len(steps) == 2 and steps[0] != steps[1]):
+            return None
+        return {"lr": float(g['lr']), "betas": (float(g['betas'][0]), float(g['betas'][1])), "eps": float(g['eps'])}
+
+    @staticmethod
+    def _adam_state_to_engine(optimizer, model, eng, n_users):
+        pu, pi = model.embedding_dict['user_emb'], model.embedding_dict['item_emb']
+        su, si = optimizer.state.get(pu, {}), optimizer.state.get(pi, {})
+        if len(su) and len(si):
+            eng.m[:n_users].copy_(su['exp_avg']); eng.m[n_users:].copy_(si['exp_avg'])
+            eng.v[:n_users].copy_(su['exp_avg_sq']); eng.v[n_users:].copy_(si['exp_avg_sq'])
+            eng.step_dev.fill_(int(float(su['step'])))
+            eng._refresh_adam_coefs()
+
+    @staticmethod
+    def _adam_state_from_engine(optimizer, model, eng, n_users):
+        g = optimizer.param_groups[0]
+        steps = int(eng.step_dev.item())
+        for p, lo, hi in ((model.embedding_dict['user_emb'], 0, n_users), (model.embedding_dict['item_emb'], n_users, None)):
+            st = optimizer.state[p]
+            if len(st) == 0:                                  # what torch.optim.Adam._init_group creates lazily
+                on_dev = bool(g.get('capturable') or g.get('fused'))
+                st['step'] = torch.zeros((), dtype=torch.float32, device=p.device) if on_dev else torch.tensor(0.0)
+                st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st['exp_avg'].copy_(eng.m[lo:hi]); st['exp_avg_sq'].copy_(eng.v[lo:hi])
+            st['step'].fill_(float(steps))
+
+    @staticmethod
+    def _graph_pays_off(max_epoch):
+        """Capturing + instantiating the CUDA graph of an epoch costs ~0.3 s (torch empties its cache, thousands of
+        kernel nodes); the eager launch sequence is GPU-bound at the named shapes (7 launches, ~60 us of CPU, per
+        >= 150 us step).  The graph is worth it when it is replayed for several epochs -- not for the 1-2 epoch
+        re-entries of the attack loops (measured at ml-1M shape, 490 batches: 0.133 s with a captured graph, 0.086 s eager
+        per train(Epoch=1) call)."""
+        return max_epoch >= 5
+
     def _next_sample_epoch(self):
         """Philox stream id of the next sampled epoch: keeps counting across train() calls on one instance (an
         attack that retrains the same recommender must not see the same triples again, like the reference's
@@ -70,6 +128,18 @@ class GraphRecommender(object):
         k = getattr(self, '_epochs_sampled', 0)
         self._epochs_sampled = k + 1
         return k
+
+    def _device_train_set(self, dev):
+        """Device mirror of data.training_data / training_set_u for the Philox sampler, rebuilt only when the data
+        object changed (attacks append fake users' rows and re-enter train() many times; the O(E) Python pass over
+        the rows would otherwise dominate a fused epoch)."""
+        from ..engine import DeviceTrainSet
+        key = (id(self.data), len(self.data.training_data), self.data.user_num, self.data.item_num, str(dev))
+        cached = getattr(self, '_train_set', None)
+        if cached is None or cached[0] != key:
+            cached = (key, DeviceTrainSet(self.data, dev))
+            self._train_set = cached
+        return cached[1]
 
     def _epoch_batches(self, dev):
         """The batches of one epoch for the reference-shaped training loops (caller's optimizer, gradient export,
@@ -82,12 +152,7 @@ class GraphRecommender(object):
         if self._sampler_mode() != 'device':
             yield from next_batch_pairwise(self.data, B)
             return
-        key = (id(self.data), len(self.data.training_data), self.data.user_num, self.data.item_num)
-        cached = getattr(self, '_train_set', None)
-        if cached is None or cached[0] != key:
-            cached = (key, DeviceTrainSet(self.data, dev))
-            self._train_set = cached
-        ts = cached[1]
+        ts = self._device_train_set(dev)
         n = ts.n_edges
         u, i, j = (torch.empty(max(n, 1), dtype=torch.int32, device=dev) for _ in range(3))
         seed = int(getattr(self.args, 'seed', 0) or 0)
@@ -161,7 +226,7 @@ class GraphRecommender(object):
         return rec_list, measure
 
     # ------------------------------------------------------------------ training
-    def _train_fused_contrastive(self, model, maxEpoch, evalNum, kind, layer_cl=1):
+    def _train_fused_contrastive(self, model, maxEpoch, evalNum, kind, layer_cl=1, optimizer=None, adam=None):
         """SimGCL / XSimGCL training when the recommender owns the optimizer and no gradient is exported: the fused
         engine (arlib_b200.engine.ContrastiveEngine) -- device sampling (or the host sampler for seed parity), one
         CUDA-graph replay per epoch, Adam state owned by the engine.  Same mathematics as the reference loop
@@ -173,11 +238,15 @@ class GraphRecommender(object):
         dev = table.device
         seed = int(getattr(self.args, 'seed', 0) or 0)
         tau = self.temp if kind == "xsimgcl" else 0.2
+        adam = adam or {"lr": self.args.lRate, "betas": (0.9, 0.999), "eps": 1e-8}
         eng = ContrastiveEngine(model._graph, table, self.data.user_num, kind, self.n_layers, self.eps, self.cl_rate, tau,
-                                self.args.lRate, self.args.reg, self.args.batch_size, len(self.data.training_data),
-                                layer_cl=layer_cl, noise_seed=(seed * 2654435761 + 12345) & 0xffffffffffff or 1)
+                                adam["lr"], self.args.reg, self.args.batch_size, len(self.data.training_data),
+                                layer_cl=layer_cl, noise_seed=(seed * 2654435761 + 12345) & 0xffffffffffff or 1,
+                                betas=adam["betas"], adam_eps=adam["eps"])
+        if optimizer is not None:
+            self._adam_state_to_engine(optimizer, model, eng, self.data.user_num)
         mode = self._sampler_mode()
-        ts = DeviceTrainSet(self.data, dev) if mode == 'device' else None
+        ts = self._device_train_set(dev) if mode == 'device' else None
         for epoch in range(maxEpoch):
             if mode == 'device':
                 eng.sample_epoch(ts, seed, self._next_sample_epoch())
@@ -186,7 +255,7 @@ class GraphRecommender(object):
                 for u, i, j in next_batch_pairwise(self.data, self.args.batch_size):
                     us += u; is_ += i; js += j
                 eng.set_triples(us, is_, js)
-            eng.run_steps(0)
+            eng.run_steps(0, use_graph=self._graph_pays_off(maxEpoch))
             rec, cl = eng.losses()
             rec, cl = rec[::100].cpu().tolist(), cl[::100].cpu().tolist()
             for k, (r, c) in enumerate(zip(rec, cl)):
@@ -198,6 +267,8 @@ class GraphRecommender(object):
             if epoch % evalNum == 0:
                 self.evaluate(epoch)
         self.last_train_losses = torch.stack(eng.losses(), 1).clone()
+        if optimizer is not None:
+            self._adam_state_from_engine(optimizer, model, eng, self.data.user_num)
 
     def _grad_buffers(self, requires_adjgrad, requires_embgrad, model):
         """recommender/LightGCN.py:36-43.  The reference allocates a DENSE N x N Matgrad

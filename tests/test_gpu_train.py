@@ -119,6 +119,7 @@ def test_dropin_general_path_external_optimizer_and_grad_export(golden_rows):
     a = LightGCN(_args(), data)
     b = copy.deepcopy(a)
     random.seed(5); a.train()
+    b.args = _args(fused=False)                           # the reference-shaped loop on autograd
     opt = torch.optim.Adam(b.model.parameters(), lr=0.005)
     random.seed(5); b.train(optimizer=opt)
     assert _rel(b.model.embedding_dict["user_emb"].detach(), a.model.embedding_dict["user_emb"].detach()) < 1e-4
@@ -153,3 +154,46 @@ def test_other_graph_recommenders_train_and_eval(name, sampler, golden_rows):
     assert recall > 0.05, measure                      # random top-50 of ~1200 items would give ~0.04 at best
     out = rec.train(requires_embgrad=True, Epoch=1)
     assert len(out) == 4
+
+
+def test_callers_plain_adam_runs_on_the_fused_engine_with_state_handover(golden_rows, monkeypatch):
+    """attack/White/CLeaR.py:145-146 -- ``recommender.train(Epoch=innerEpoch, optimizer=optimizer)`` with the attacker's
+    ``torch.optim.Adam(model.parameters())``: the fused engine stands in for optimizer.step(), starts from the optimizer's
+    state and writes it back, so repeated calls continue the same Adam trajectory as the autograd loop with torch's own
+    optimizer.  A stale optimizer (built on other tensors -- a quirk callers rely on) keeps the reference-shaped loop."""
+    import copy
+    from arlib_b200.recommender.LightGCN import LightGCN
+    from arlib_b200.util.DataLoader import DataLoader
+    train, test = golden_rows
+    data = DataLoader.from_rows([list(r) for r in train[:6000]], (), test)
+    torch.manual_seed(2)
+    ref = LightGCN(_args(fused=False), data)
+    fus = copy.deepcopy(ref)
+    fus.args = _args()
+    opt_ref = torch.optim.Adam(ref.model.parameters(), lr=0.003, betas=(0.8, 0.99), eps=1e-7)
+    opt_fus = torch.optim.Adam(fus.model.parameters(), lr=0.003, betas=(0.8, 0.99), eps=1e-7)
+    calls = []
+    orig = LightGCN._train_fused
+    monkeypatch.setattr(LightGCN, "_train_fused", lambda self, *a, **k: (calls.append(self), orig(self, *a, **k))[1])
+    for rnd in range(2):                                   # two calls: the second starts from the handed-back state
+        random.seed(7 + rnd); ref.train(Epoch=1, optimizer=opt_ref)
+        random.seed(7 + rnd); fus.train(Epoch=1, optimizer=opt_fus)
+    assert calls == [fus, fus]
+    n_steps = 2 * ((len(data.training_data) + 2047) // 2048)
+    for name in ("user_emb", "item_emb"):
+        pr, pf = ref.model.embedding_dict[name], fus.model.embedding_dict[name]
+        assert _rel(pf.detach(), pr.detach()) < 1e-4
+        sr, sf = opt_ref.state[pr], opt_fus.state[pf]
+        assert float(sf["step"]) == float(sr["step"]) == n_steps
+        assert _rel(sf["exp_avg"], sr["exp_avg"]) < 1e-3 and _rel(sf["exp_avg_sq"], sr["exp_avg_sq"]) < 1e-3
+    # the caller can keep using its optimizer afterwards
+    fu, fi = fus.model()
+    opt_fus.zero_grad(); (fu.sum() + fi.sum()).backward(); opt_fus.step()
+    assert float(opt_fus.state[fus.model.embedding_dict["user_emb"]]["step"]) == n_steps + 1
+    # stale optimizer: built on tensors that are not the model's parameters
+    stale = torch.optim.Adam([torch.nn.Parameter(torch.zeros(3, 64, device=DEV)), torch.nn.Parameter(torch.zeros(3, 64, device=DEV))])
+    n_before = len(calls)
+    random.seed(1); fus.train(Epoch=1, optimizer=stale)
+    assert len(calls) == n_before
+    assert LightGCN._fusable_adam(torch.optim.SGD(fus.model.parameters(), lr=0.1), fus.model) is None
+    assert LightGCN._fusable_adam(torch.optim.Adam(fus.model.parameters(), lr=0.1, amsgrad=True), fus.model) is None

@@ -1,3 +1,5 @@
 #!/bin/bash
-echo default; timeout 300 python tools/spmm_variants.py 2>&1 | tail -1
-for v in d64l8m4 d64l8m5 d64l8m3; do echo $v; ARLIB_B200_LIB=$PWD/arlib_b200/csrc/build/libagcf_$v.so timeout 300 python tools/spmm_variants.py 2>&1 | tail -1; done
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_train.py tests/test_gpu_contrast_engine.py -q > gpurun_out/pytest_s43.log 2>&1
+tail -2 gpurun_out/pytest_s43.log | cut -c1-300
+timeout 600 python tools/whitebox_bench.py ml-1m 2>/dev/null | tail -1
