@@ -9,11 +9,12 @@ by arlib_b200.graph / arlib_b200.engine and never stored here, which keeps the
 object picklable and deep-copyable (ARLib.py:128,241).
 """
 from collections import defaultdict
+from itertools import islice
 
 import numpy as np
 import scipy.sparse as sp
 
-from .FileIO import FileIO
+from .FileIO import FileIO, no_gc, rows_from_columns
 
 
 class DataLoader(object):
@@ -34,9 +35,13 @@ class DataLoader(object):
     @classmethod
     def from_arrays(cls, train_u, train_i, test_u=(), test_i=(), name="synthetic"):
         """Integer (user, item) arrays -> rows with string names str(id)."""
-        tr = [[str(int(u)), str(int(i)), 1.0] for u, i in zip(train_u, train_i)]
-        te = [[str(int(u)), str(int(i)), 1.0] for u, i in zip(test_u, test_i)]
-        return cls.from_rows(tr, te[:1000], te, name)
+        def rows(u, i):
+            names = lambda a: np.asarray(a, dtype=np.int64).astype(str).astype(object)
+            return rows_from_columns(names(u), names(i), np.ones(len(u), dtype=np.float64))
+        tr, te = rows(train_u, train_i), rows(test_u, test_i)
+        self = cls.__new__(cls)
+        self._setup(tr, te[:1000], te, name)
+        return self
 
     # ------------------------------------------------------------------ build
     def _setup(self, training_data, val_data, test_data, name):
@@ -52,7 +57,13 @@ class DataLoader(object):
         self.val_set_item = set()
         self.test_set = defaultdict(dict)
         self.test_set_item = set()
-        self._index_interactions()
+        self._edges = None
+        cols = getattr(training_data, 'parsed_columns', lambda: None)()
+        with no_gc():
+            if cols is not None:
+                self._index_interactions_columns(cols)
+            else:
+                self._index_interactions()
         self.user_num = len(self.training_set_u)
         self.item_num = len(self.training_set_i)
         self.ui_adj = self._bipartite_adjacency()
@@ -80,9 +91,59 @@ class DataLoader(object):
                     bucket[row[0]][row[1]] = row[2]
                     seen.add(row[1])
 
+    @staticmethod
+    def _grouped_dicts(codes, n_keys, key_names, inner_names, weights):
+        """{key_names[k]: {inner: weight, ...}} with the insertion orders of the row-by-row loop: outer keys by first
+        appearance (= code order), inner keys by first appearance inside the group, later duplicates overwrite the
+        value -- built from one stable sort and one dict(zip(...)) per group instead of one dict update per row."""
+        order = np.argsort(codes, kind='stable')
+        bounds = np.searchsorted(codes[order], np.arange(n_keys + 1))
+        inner = iter(inner_names[order].tolist())
+        w = iter(weights[order].tolist())
+        out = defaultdict(dict)
+        for name, cnt in zip(key_names, np.diff(bounds).tolist()):
+            out[name] = dict(zip(islice(inner, cnt), islice(w, cnt)))
+        return out
+
+    def _index_interactions_columns(self, cols):
+        """Same result as _index_interactions (asserted attribute by attribute in tests/test_dataloader_fast.py), from
+        the parsed columns of the training rows: ids with pandas.factorize (first appearance, exactly the reference's
+        numbering util/DataLoader.py:32-40), the dict-of-dicts group-wise."""
+        import pandas as pd
+        users, items, weights = cols
+        ucode, unames = pd.factorize(users)
+        icode, inames = pd.factorize(items)
+        unames, inames = unames.tolist(), inames.tolist()
+        self.user.update(zip(unames, range(len(unames))))
+        self.item.update(zip(inames, range(len(inames))))
+        self.id2user.update(enumerate(unames))
+        self.id2item.update(enumerate(inames))
+        self.training_set_u = self._grouped_dicts(ucode, len(unames), unames, items, weights)
+        self.training_set_i = self._grouped_dicts(icode, len(inames), inames, users, weights)
+        self._edges = (len(self.training_data), len(unames), len(inames), ucode.astype(np.int64), icode.astype(np.int64))
+        user = self.user
+        for rows, bucket, seen in ((self.val_data, self.val_set, self.val_set_item),
+                                   (self.test_data, self.test_set, self.test_set_item)):
+            c = getattr(rows, 'parsed_columns', lambda: None)()
+            if c is None:
+                for row in rows:
+                    if row[0] in user:
+                        bucket[row[0]][row[1]] = row[2]
+                        seen.add(row[1])
+                continue
+            keep = np.fromiter((u in user for u in c[0].tolist()), dtype=bool, count=len(c[0]))
+            ku, ki, kw = c[0][keep], c[1][keep], c[2][keep]
+            code, names = pd.factorize(ku)
+            bucket.update(self._grouped_dicts(code, len(names), names.tolist(), ki, kw))
+            seen.update(ki.tolist())
+
     def edge_arrays(self):
-        """(user ids, item ids) of training_data as int64 arrays, in list order."""
+        """(user ids, item ids) of training_data as int64 arrays, in list order (cached from the vectorised build for
+        as long as nobody resized training_data; an in-place shuffle permutes rows, which no consumer depends on)."""
         n = len(self.training_data)
+        e = getattr(self, '_edges', None)
+        if e is not None and e[:3] == (n, len(self.user), len(self.item)):
+            return e[3], e[4]
         u = np.fromiter((self.user[r[0]] for r in self.training_data), dtype=np.int64, count=n)
         i = np.fromiter((self.item[r[1]] for r in self.training_data), dtype=np.int64, count=n)
         return u, i
