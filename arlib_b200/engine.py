@@ -36,6 +36,11 @@ class DeviceTrainSet:
     injected fake users, SURVEY.md App. B -- reject nothing)."""
 
     def __init__(self, data, device):
+        edges = getattr(data, 'pristine_edges', lambda: None)()
+        if edges is not None:              # untouched since the vectorised load: the dicts ARE these edges
+            other = DeviceTrainSet.from_arrays(edges[0], edges[1], data.user_num, data.item_num, device)
+            self.__dict__.update(other.__dict__)
+            return
         n = len(data.training_data)
         user, item = data.user, data.item
         eu = np.fromiter((user[r[0]] for r in data.training_data), dtype=np.int32, count=n)

@@ -44,12 +44,28 @@ class FullRankEvaluator:
         uid = np.array([data.user[u] for u in self.users], dtype=np.int32)
         # mask CSR indexed by GLOBAL user id: sorted train item ids (data.user_rated, LightGCN.py:151-153)
         n_users = max(data.user_num, int(uid.max()) + 1 if len(uid) else 0)
-        mask_lists = [()] * n_users
-        for u in self.users:
-            ids = np.fromiter((item[i] for i in data.training_set_u[u]), dtype=np.int32)
-            ids.sort()
-            mask_lists[data.user[u]] = ids
-        mrp, mit = _csr_from_lists(mask_lists)
+        edges = getattr(data, 'pristine_edges', lambda: None)()
+        if edges is not None:
+            # untouched since the vectorised load: training_set_u is exactly these edges -- sorted unique item ids
+            # of the TEST users' rows with array operations instead of a per-user dict walk
+            eu, ei = edges
+            is_test = np.zeros(n_users, dtype=bool)
+            is_test[uid] = True
+            keep = is_test[eu]
+            key = np.sort(eu[keep].astype(np.int64) * data.item_num + ei[keep])
+            if key.size:
+                key = key[np.concatenate(([True], key[1:] != key[:-1]))]
+            ku, ki = key // data.item_num, key % data.item_num
+            mrp = np.zeros(n_users + 1, dtype=np.int64)
+            np.cumsum(np.bincount(ku, minlength=n_users), out=mrp[1:])
+            mrp, mit = mrp.astype(np.int32), (ki.astype(np.int32) if ki.size else np.zeros(1, np.int32))
+        else:
+            mask_lists = [()] * n_users
+            for u in self.users:
+                ids = np.fromiter((item[i] for i in data.training_set_u[u]), dtype=np.int32)
+                ids.sort()
+                mask_lists[data.user[u]] = ids
+            mrp, mit = _csr_from_lists(mask_lists)
         # test CSR indexed by test-user POSITION: sorted ids of test items that exist in train
         t_lists, totals = [], []
         for u in self.users:

@@ -148,6 +148,17 @@ class DataLoader(object):
         i = np.fromiter((self.item[r[1]] for r in self.training_data), dtype=np.int64, count=n)
         return u, i
 
+    def pristine_edges(self):
+        """(user ids, item ids) from the vectorised build if training_data / user / item still have the sizes they
+        were built with -- i.e. training_set_u is still exactly the set of these edges -- else None.  Lets the
+        device mirrors (sampler rejection lists, evaluation masks) be derived with array operations; after an
+        attack appended rows they go back to reading the dicts (whose staleness is a quirk callers rely on)."""
+        e = getattr(self, '_edges', None)
+        if e is not None and e[:3] == (len(self.training_data), len(self.user), len(self.item)) \
+                and len(self.training_set_u) == len(self.user):
+            return e[3], e[4]
+        return None
+
     def _bipartite_adjacency(self, self_connection=False):
         """util/DataLoader.py:57-71 -- [[0,R],[R^T,0]] with fp32 ones."""
         n = self.user_num + self.item_num

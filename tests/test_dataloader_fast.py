@@ -90,3 +90,33 @@ def test_from_arrays_is_the_same_object_as_from_rows():
     _same_nested(a.test_set, b.test_set)
     assert a.training_data == b.training_data
     assert (a.interaction_mat != b.interaction_mat).nnz == 0
+
+
+def test_device_mirrors_from_pristine_edges_equal_the_dict_walk():
+    """The sampler's rejection lists and the evaluation masks are derived from the cached edge arrays while the data
+    object is untouched, and from the (possibly stale -- SURVEY.md App. B) dicts once an attack resized it."""
+    import torch
+    from arlib_b200.engine import DeviceTrainSet
+    from arlib_b200.evaluator import FullRankEvaluator
+    from arlib_b200.util.DataLoader import DataLoader
+    rng = np.random.default_rng(5)
+    tu, ti = rng.integers(0, 200, 6000), rng.integers(0, 300, 6000)          # with duplicate pairs
+    su, si = rng.integers(0, 220, 800), rng.integers(0, 320, 800)
+    data = DataLoader.from_arrays(tu, ti, su, si)
+    assert data.pristine_edges() is not None
+    fast_ts, fast_ev = DeviceTrainSet(data, "cpu"), FullRankEvaluator(data, "cpu")
+    edges = data._edges
+    data._edges = None                                                        # force the dict-walking constructors
+    slow_ts, slow_ev = DeviceTrainSet(data, "cpu"), FullRankEvaluator(data, "cpu")
+    for k in ("e_user", "e_item", "rej_rowptr", "rej_items"):
+        assert torch.equal(getattr(fast_ts, k), getattr(slow_ts, k)), k
+    for k in ("user_rows", "mask_rowptr", "mask_items", "t_rowptr", "t_items", "test_total"):
+        assert torch.equal(getattr(fast_ev, k), getattr(slow_ev, k)), k
+    # fake-user injection (attack/White/CLeaR.py:179-197): rows + a user appended, training_set_u left stale
+    data._edges = edges
+    data.training_data.append(["fake", data.id2item[0], 1.0])
+    data.user["fake"] = len(data.user)
+    data.user_num += 1
+    assert data.pristine_edges() is None
+    ts = DeviceTrainSet(data, "cpu")
+    assert ts.n_edges == len(data.training_data) and int(ts.rej_rowptr[-1]) == int(slow_ts.rej_rowptr[-1])   # fake user rejects nothing
