@@ -412,7 +412,7 @@ __device__ __forceinline__ void spmm_block(const SpmmParams& p, const int n_v, c
   float4 acc[C::VPL];
 #pragma unroll
   for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long slot = ((long long)blk * (C::THREADS / 32) + warp) * C::RPW + grp;
+  const long long slot = ((long long)blk * (blockDim.x >> 5) + warp) * C::RPW + grp;   // block size is a launch parameter
   bool valid = slot < n_v;
   int4 vr = make_int4(0, 0, 0, 1 << 16);
   if (valid) vr = __ldg(p.vrows + slot);                  // one 16-byte load: start, len, row, segment id
@@ -490,7 +490,8 @@ __device__ __forceinline__ void spmm_grid(const SpmmParams& p) {
     return;
   }
   __shared__ int s_next[2];
-  const int n_blocks = (n_v + C::RPB - 1) / C::RPB;
+  const int rpb = (int)(blockDim.x >> 5) * C::RPW;
+  const int n_blocks = (n_v + rpb - 1) / rpb;
   int blk = (int)blockIdx.x;
   for (int it = 0; blk < n_blocks; ++it) {
     int nxt = 0;
@@ -511,9 +512,12 @@ __global__ void __launch_bounds__(256, MINB) spmm_csr_kernel(const SpmmParams p)
   spmm_grid<D, LPR, NOISE, false>(p);
 }
 
-// first backward layer: gathers only the rows in col_mask (spmm_accumulate_masked); twice the resident warps
+// first backward layer: gathers only the rows in col_mask (spmm_accumulate_masked)
+#ifndef AGCF_SPMM_CM_THREADS
+#define AGCF_SPMM_CM_THREADS 256
+#endif
 template <int D, int LPR, int MINB>
-__global__ void __launch_bounds__(256, MINB) spmm_colmask_kernel(const SpmmParams p) {
+__global__ void __launch_bounds__(AGCF_SPMM_CM_THREADS, MINB) spmm_colmask_kernel(const SpmmParams p) {
   spmm_grid<D, LPR, false, true>(p);
 }
 
@@ -540,7 +544,10 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
     blocks = blocks < resident ? blocks : resident;
   }
   if (cmask) {
-    spmm_colmask_kernel<D, LPR, AGCF_SPMM_CM_MINB(D)><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+    const long long rpb = (AGCF_SPMM_CM_THREADS / 32) * C::RPW;
+    long long cb = ((long long)p.n_v + rpb - 1) / rpb;
+    if (p.sched != nullptr) cb = cb < blocks ? cb : blocks;
+    spmm_colmask_kernel<D, LPR, AGCF_SPMM_CM_MINB(D)><<<(unsigned)cb, AGCF_SPMM_CM_THREADS, 0, st>>>(p);
     AGCF_LAUNCH_OK();
     return AGCF_OK;
   }
