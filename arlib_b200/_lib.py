@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_uint64, c_void_p
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # ARLIB_B200_LIB selects another BUILD of the same library (kernel tuning experiments); never a fallback

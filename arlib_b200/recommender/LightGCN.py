@@ -11,7 +11,7 @@
 import torch
 
 from ..encoder import LGCN_Encoder, TorchGraphInterface  # noqa: F401  (re-exported like the reference module)
-from ..engine import DeviceTrainSet, LightGCNEngine
+from ..engine import LightGCNEngine
 from ..util.loss import bpr_loss, l2_reg_loss
 from ..util.sampler import next_batch_pairwise
 from ._base import GraphRecommender

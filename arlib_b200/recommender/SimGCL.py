@@ -7,7 +7,6 @@ import torch
 
 from ..encoder import SimGCL_Encoder, TorchGraphInterface  # noqa: F401
 from ..util.loss import bpr_loss, l2_reg_loss
-from ..util.sampler import next_batch_pairwise
 from ._base import GraphRecommender
 
 

@@ -6,7 +6,6 @@ import torch
 
 from ..encoder import TorchGraphInterface, XSimGCL_Encoder, unique_ids_like_reference  # noqa: F401
 from ..util.loss import InfoNCE, bpr_loss, l2_reg_loss
-from ..util.sampler import next_batch_pairwise
 from ._base import GraphRecommender
 
 

@@ -146,7 +146,6 @@ class GraphRecommender(object):
         NGCF / SimGCL / XSimGCL): ``(user_idx, pos_idx, neg_idx)`` as device LongTensors drawn by the on-device
         Philox sampler (agcf_bpr_sample_epoch, util/sampler.py:4-30), or -- sampler mode 'host' -- the reference's
         Python lists from util.sampler.next_batch_pairwise (same RNG consumption, in-place shuffle)."""
-        from ..engine import DeviceTrainSet
         from ..util.sampler import next_batch_pairwise
         B = self.args.batch_size
         if self._sampler_mode() != 'device':
@@ -232,7 +231,7 @@ class GraphRecommender(object):
         CUDA-graph replay per epoch, Adam state owned by the engine.  Same mathematics as the reference loop
         (recommender/SimGCL.py:36-85, XSimGCL.py:46-95); the perturbation noise comes from Philox in the SpMM
         epilogue instead of torch.rand_like."""
-        from ..engine import ContrastiveEngine, DeviceTrainSet
+        from ..engine import ContrastiveEngine
         from ..util.sampler import next_batch_pairwise
         table = model.parameter_table()
         dev = table.device
