@@ -28,7 +28,12 @@ constexpr int kTileM = 128;            // users per tile (UMMA M)
 constexpr int kKBlock = 32;            // fp32 elements per 128-byte swizzle atom row
 constexpr int kUmmaK = 8;              // K per tcgen05.mma for tf32 (32 bytes)
 constexpr int kStages = 2;
-constexpr int kThreads = 192;          // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+#ifndef AGCF_TC_EPI_WG
+#define AGCF_TC_EPI_WG 4
+#endif
+constexpr int kEpiWG = AGCF_TC_EPI_WG;  // epilogue warpgroups: each covers all 128 rows and 1/kEpiWG of a tile's columns
+constexpr int kEpiWarps = 4 * kEpiWG;
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0: TMA, warp 1: MMA + TMEM alloc, then the epilogue warps
 constexpr uint32_t kTmemCols = 512;    // two fp32 accumulators of kTileN columns (all of TMEM: 1 CTA / SM)
 constexpr float kMaskedScore = -1.0e9f;
 
@@ -147,7 +152,7 @@ group_max_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_con
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, 1);
     for (int s = 0; s < kStages; ++s) { mbar_init(&bars->b_full[s], 1); mbar_init(&bars->b_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->acc_full[a], 1); mbar_init(&bars->acc_empty[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_u)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_i)) : "memory");
@@ -215,8 +220,13 @@ group_max_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_con
       }
     }
   } else {
-    // ================================ epilogue (4 warps) ===========================
+    // ================================ epilogue (kEpiWarps warps) ===================
+    // The epilogue (TMEM -> registers, mask, max over 32 columns, one float per group) takes longer than the 8 MMAs of
+    // a K = 64 tile: with 4 warps the tensor pipe idled 74 % of the time (ncu: 26 % active, 35 % with 8 warps).  kEpiWG
+    // warpgroups split the tile's columns; a warp may only read the TMEM lanes 32 (id % 4) .. +32, so every group of
+    // four consecutive warps covers all 128 rows.
     const int quarter = warp & 3;                                  // TMEM lanes [32q, 32q+32) belong to warp (id % 4) == q
+    const int half = (warp - 2) >> 2;                              // which half of the tile's groups this warpgroup takes
     const int row_in_tile = quarter * 32 + lane;
     uint32_t acc = 0, acc_phase = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -226,33 +236,36 @@ group_max_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_con
       const int r = ut * kTileM + row_in_tile;
       const bool row_ok = r < n_u;
       // rows of bits / gmax are `pitch` words apart (multiple of 8 = 32 B), a tile covers GPT consecutive
-      // groups: one aligned 16/32-byte vector per thread per tile for the mask words and for the maxima
+      // groups, a thread GH of them: one aligned 8/16-byte vector per thread per tile for the mask words and the maxima
       constexpr int GPT = kTileN / 32;                               // groups per tile: 8 (or 4 for d = 128)
-      const uint32_t* brow = bits + (size_t)(row_ok ? r : 0) * pitch;
-      float* grow = gmax + (size_t)(row_ok ? r : 0) * pitch;
-      uint32_t w[GPT], wn[GPT];
-#pragma unroll
-      for (int q = 0; q < GPT; q += 4) {
-        const uint4 x = row_ok ? __ldg(reinterpret_cast<const uint4*>(brow + t0 * GPT + q)) : make_uint4(0u, 0u, 0u, 0u);
-        w[q] = x.x; w[q + 1] = x.y; w[q + 2] = x.z; w[q + 3] = x.w;
-      }
-      for (int t = t0; t < t1; ++t) {
-        if (t + 1 < t1) {                                            // mask words of the next tile: in flight during this one
-#pragma unroll
-          for (int q = 0; q < GPT; q += 4) {
-            const uint4 x = row_ok ? __ldg(reinterpret_cast<const uint4*>(brow + (t + 1) * GPT + q)) : make_uint4(0u, 0u, 0u, 0u);
-            wn[q] = x.x; wn[q + 1] = x.y; wn[q + 2] = x.z; wn[q + 3] = x.w;
-          }
+      constexpr int GH = GPT / kEpiWG;                               // groups per thread and tile
+      static_assert(GH == 1 || GH == 2 || GH == 4, "epilogue split");
+      const uint32_t* brow = bits + (size_t)(row_ok ? r : 0) * pitch + half * GH;
+      float* grow = gmax + (size_t)(row_ok ? r : 0) * pitch + half * GH;
+      uint32_t w[GH], wn[GH];
+      auto load_words = [&](int t, uint32_t (&dst)[GH]) {
+        if constexpr (GH == 4) {
+          const uint4 x = row_ok ? __ldg(reinterpret_cast<const uint4*>(brow + t * GPT)) : make_uint4(0u, 0u, 0u, 0u);
+          dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w;
+        } else if constexpr (GH == 2) {
+          const uint2 x = row_ok ? __ldg(reinterpret_cast<const uint2*>(brow + t * GPT)) : make_uint2(0u, 0u);
+          dst[0] = x.x; dst[1] = x.y;
+        } else {
+          dst[0] = row_ok ? __ldg(brow + t * GPT) : 0u;
         }
+      };
+      load_words(t0, w);
+      for (int t = t0; t < t1; ++t) {
+        if (t + 1 < t1) load_words(t + 1, wn);                       // mask words of the next tile: in flight during this one
         mbar_wait(&bars->acc_full[acc], acc_phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kTileN;
-        float mx[GPT];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kTileN + half * GH * 32;
+        float mx[GH];
 #pragma unroll
-        for (int q = 0; q < GPT; ++q) {
+        for (int q = 0; q < GH; ++q) {
           uint32_t v[32];
           tmem_ld32(taddr + q * 32, v);
-          const int g = t * GPT + q;
+          const int g = t * GPT + half * GH + q;
           const int valid = n_items - g * 32;                        // < 32 only in the table's last group; <= 0 past it
           float m = -FLT_MAX;
           if (w[q] == 0u && valid >= 32) {
@@ -270,12 +283,12 @@ group_max_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_con
           mx[q] = m;
         }
         if (row_ok) {
-#pragma unroll
-          for (int q = 0; q < GPT; q += 4)
-            *reinterpret_cast<float4*>(grow + t * GPT + q) = make_float4(mx[q], mx[q + 1], mx[q + 2], mx[q + 3]);
+          if constexpr (GH == 4) *reinterpret_cast<float4*>(grow + t * GPT) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+          else if constexpr (GH == 2) *reinterpret_cast<float2*>(grow + t * GPT) = make_float2(mx[0], mx[1]);
+          else grow[t * GPT] = mx[0];
         }
 #pragma unroll
-        for (int q = 0; q < GPT; ++q) w[q] = wn[q];
+        for (int q = 0; q < GH; ++q) w[q] = wn[q];
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);

@@ -1,17 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_s50.log 2>&1
-tail -3 gpurun_out/pytest_s50.log | cut -c1-200
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 900 python bench.py > gpurun_out/bench_s50_n1.json 2> gpurun_out/bench_s50_n1.err
-timeout 900 python bench.py --impl reference > gpurun_out/bench_s50_ref.json 2> gpurun_out/bench_s50_ref.err
-python - <<PY
-import json
-for f in ("gpurun_out/bench_s50_n1.json", "gpurun_out/bench_s50_ref.json"):
-    try:
-        l=json.loads(open(f).read().strip().splitlines()[-1])
-        r=l.get("roofline") or {}
-        print(f, "value %.4g"%l["value"], "ms/step %.4f"%l["ms_per_step"], "e2e", l.get("e2e",{}).get("value"), "frac", r.get("frac"), "full_ms", r.get("avg_launch_ms"), "eval", (l.get("eval") or {}).get("users_per_s"), "launches", l.get("gpu_launches"), "clocks", l.get("clocks"))
-    except Exception as e:
-        print(f, "failed", e)
-PY
+timeout 300 python -m pytest tests/test_gpu_topk.py -x -q > gpurun_out/pytest_s54.log 2>&1; echo "pytest rc=$?"
+tail -2 gpurun_out/pytest_s54.log | cut -c1-300
+timeout 200 python tools/eval_bench.py 2>&1 | sed -n 1,1p
+timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --csv -k regex:group_max_tc -s 2 -c 2 python tools/eval_bench.py 2>/dev/null | grep "group_max_tc" | awk -F'","' '{print $(NF-2), $(NF-1), $NF}' | head -4
