@@ -295,6 +295,14 @@ struct Stage2Params {
   float* w_val;                // [warps][cmax*32]
   int32_t* overflow_list;      // [n_u]
   int32_t* overflow_count;     // zeroed by the caller
+  // group-major re-scoring (stage 2 split into candidates -> per-group pair lists -> re-score -> select)
+  int32_t* u_groups;           // [n_u][cmax] candidate groups of every user
+  int32_t* u_ncg;              // [n_u] their count, -1 = overflow (block kernel)
+  float* u_val;                // [n_u][cmax*32] exact scores of the candidates
+  int32_t* g_count;            // [n_groups] users that have the group as a candidate (zeroed by the caller)
+  int32_t* g_offset;           // [n_groups + 1]
+  int32_t* g_cursor;           // [n_groups]
+  int32_t* pairs;              // [n_u * cmax] (user << 8 | candidate slot), grouped by group
 };
 
 template <int D>
@@ -665,6 +673,240 @@ __global__ void __launch_bounds__(32 * S2W<D>::WPC) topk_select_warp_kernel(cons
   }
 }
 
+// ------------------------------------------------ stage 2, GROUP-MAJOR re-scoring
+// The warp-per-user kernel above copies every candidate group (32 item rows, 8 KB at d = 64) once per user that
+// has it: 57 groups x 8 KB = 467 KB of L2 -> SM traffic per user, 12 GB per Gowalla evaluation -- the whole cost of
+// stage 2.  A group is a candidate of ~1 200 users; here it is loaded ONCE per CTA and the users stream past it
+// (256 B each): ~0.65 GB per evaluation.  Four kernels:
+//   s2_candidates : per user (warp) the threshold and the ordered candidate groups; per group a count
+//   s2_scan       : exclusive scan of the counts (one CTA)
+//   s2_pairs      : (user, slot) pairs bucketed by group (order inside a bucket is irrelevant: each pair's scores
+//                   are computed independently and land at a fixed place)
+//   s2_rescore    : CTA per (group, slice): tile in shared memory, one warp per pair, lane l walks ITS item's row in
+//                   the reference order (k ascending, fmaf) -- the same bits as exact_dot / the warp kernel
+//   s2_select     : per user (warp) step 4 of the warp kernel on the stored scores
+// Results are bit-identical to the warp kernel (tests run both).
+template <int D>
+__global__ void __launch_bounds__(256) s2_candidates_kernel(const Stage2Params p) {
+  __shared__ unsigned int hist_all[8][256];
+  __shared__ float urow_all[8][D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned int* hist = hist_all[warp];
+  float* urow = urow_all[warp];
+  const int gw = blockIdx.x * 8 + warp, n_warps = gridDim.x * 8;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  for (int r = gw; r < p.n_u; r += n_warps) {
+    const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
+    const float* grow = p.gmax + (size_t)r * p.pitch;
+    __syncwarp();
+    for (int k = lane; k < D / 4; k += 32) reinterpret_cast<float4*>(urow)[k] = __ldg(p.Uemb + (size_t)uid * (D / 4) + k);
+    __syncwarp();
+    const unsigned int R = (unsigned int)min(p.K, p.n_groups);
+    float thr = key2f(warp_radix_select(hist, p.n_groups, R, lane, grow));
+    if (p.margin_scale > 0.f) {
+      float ss = 0.f;
+      for (int k = 0; k < D; ++k) ss = fmaf(urow[k], urow[k], ss);
+      thr -= p.margin_scale * sqrtf(ss) * __ldg(p.max_item_norm);
+    }
+    int32_t* my_groups = p.u_groups + (size_t)r * p.cmax;
+    int n_cg = 0;
+    bool overflow = false;
+    for (int base = 0; base < p.n_groups; base += 32) {
+      const int g = base + lane;
+      const bool flag = g < p.n_groups && grow[g] >= thr;
+      const unsigned int b = __ballot_sync(0xffffffffu, flag);
+      if (n_cg + __popc(b) > p.cmax) { overflow = true; break; }       // warp-uniform
+      if (flag) my_groups[n_cg + __popc(b & lt_mask)] = g;
+      n_cg += __popc(b);
+    }
+    if (overflow) {
+      if (lane == 0) { p.overflow_list[atomicAdd(p.overflow_count, 1)] = r; p.u_ncg[r] = -1; }
+      continue;
+    }
+    __syncwarp();
+    for (int c = lane; c < n_cg; c += 32) atomicAdd(p.g_count + my_groups[c], 1);
+    if (lane == 0) p.u_ncg[r] = n_cg;
+  }
+}
+
+__global__ void __launch_bounds__(1024) s2_scan_kernel(const int32_t* __restrict__ count, int n, int32_t* __restrict__ offset,
+                                                       int32_t* __restrict__ cursor) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int k = base + threadIdx.x;
+    const int v = k < n ? count[k] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = carry;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    if (k < n) { offset[k] = before + incl - v; cursor[k] = 0; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offset[n] = carry;
+}
+
+__global__ void __launch_bounds__(256) s2_pairs_kernel(const Stage2Params p) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = gw; r < p.n_u; r += n_warps) {
+    const int n_cg = p.u_ncg[r];
+    const int32_t* my_groups = p.u_groups + (size_t)r * p.cmax;
+    for (int c = lane; c < n_cg; c += 32) {
+      const int g = my_groups[c];
+      const int pos = atomicAdd(p.g_cursor + g, 1);
+      p.pairs[p.g_offset[g] + pos] = (r << 8) | c;
+    }
+  }
+}
+
+constexpr int kS2Slices = 8;               // CTAs per group in s2_rescore (popular groups have >10 000 users)
+
+template <int D>
+__global__ void __launch_bounds__(256) s2_rescore_kernel(const Stage2Params p) {
+  constexpr int LD = D + 4, V4 = D / 4;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  float* tile = reinterpret_cast<float*>(dyn);                       // [32][LD]
+  float* urow_all = tile + kGroup * LD;                              // [8][D]
+  const int g = blockIdx.x, slice = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int first = p.g_offset[g], cnt = p.g_offset[g + 1] - first;
+  if (slice * 8 >= cnt) return;                                      // nothing for this slice (uniform per CTA)
+  const int rows_here = min(kGroup, p.n_items - g * kGroup);
+  const float4* src = p.Iemb + (size_t)g * kGroup * V4;
+  for (int f = threadIdx.x; f < kGroup * V4; f += 256) {
+    const int row = f / V4, c4 = f - row * V4;
+    const float4 v = row < rows_here ? __ldg(src + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(tile + row * LD + 4 * c4) = v;
+  }
+  __syncthreads();
+  float* urow = urow_all + warp * D;
+  const float* mine_row = tile + lane * LD;
+  for (int q = slice * 8 + warp; q < cnt; q += kS2Slices * 8) {
+    const int pr = p.pairs[first + q];
+    const int r = pr >> 8, c = pr & 255;
+    const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
+    __syncwarp();
+    for (int k = lane; k < V4; k += 32) reinterpret_cast<float4*>(urow)[k] = __ldg(p.Uemb + (size_t)uid * V4 + k);
+    __syncwarp();
+    float sc = 0.f;
+#pragma unroll 4
+    for (int k4 = 0; k4 < V4; ++k4) {
+      const float4 v = *reinterpret_cast<const float4*>(mine_row + 4 * k4);
+      const float4 u = *reinterpret_cast<const float4*>(urow + 4 * k4);
+      sc = fmaf(u.x, v.x, sc);
+      sc = fmaf(u.y, v.y, sc);
+      sc = fmaf(u.z, v.z, sc);
+      sc = fmaf(u.w, v.w, sc);
+    }
+    if (lane >= rows_here) sc = -FLT_MAX;
+    else if ((__ldg(p.bits + (size_t)r * p.pitch + g) >> lane) & 1u) sc = kMasked;
+    p.u_val[((size_t)r * p.cmax + c) * kGroup + lane] = sc;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) s2_select_kernel(const Stage2Params p) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int kpow2 = 1;
+  while (kpow2 < p.K) kpow2 <<= 1;
+  const size_t per_warp = 1024 + (size_t)kpow2 * 8;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(dyn + (size_t)warp * per_warp);
+  unsigned long long* sort_keys = reinterpret_cast<unsigned long long*>(dyn + (size_t)warp * per_warp + 1024);
+  const int gw = blockIdx.x * 8 + warp, n_warps = gridDim.x * 8;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  for (int r = gw; r < p.n_u; r += n_warps) {
+    const int n_cg = p.u_ncg[r];
+    if (n_cg < 0) continue;                                          // overflow user: the block kernel writes its row
+    const int32_t* my_groups = p.u_groups + (size_t)r * p.cmax;
+    const float* my_val = p.u_val + (size_t)r * p.cmax * kGroup;
+    __syncwarp();
+    const int nc = n_cg * kGroup;
+    int n_valid = nc;
+    if (n_cg > 0 && my_groups[n_cg - 1] == p.n_groups - 1) n_valid = nc - (p.n_groups * kGroup - p.n_items);
+    const int Keff = min(p.K, n_valid);
+    // K-th largest exact score s*, then the reference heap's tie rule (see topk_select_kernel)
+    int n_sel = 0;
+    if (Keff > 0) {
+      const float sstar = key2f(warp_radix_select(hist, nc, (unsigned int)Keff, lane, my_val));
+      int run_ge = 0, run_gt = 0, gp_local = 0;
+      bool found = false;
+      for (int base = 0; base < nc; base += 32) {
+        const int k = base + lane;
+        const float v = my_val[k];
+        const bool real = k < n_valid;
+        const bool gt = real && v > sstar, ge = real && v >= sstar;
+        const unsigned int bge = __ballot_sync(0xffffffffu, ge), bgt = __ballot_sync(0xffffffffu, gt);
+        if (ge && run_ge + __popc(bge & lt_mask) + 1 == Keff) { found = true; gp_local = run_gt + __popc(bgt & lt_mask) + (gt ? 1 : 0); }
+        run_ge += __popc(bge);
+        run_gt += __popc(bgt);
+      }
+      const int m = run_gt;
+      const unsigned int fb = __ballot_sync(0xffffffffu, found);
+      const int gp = __shfl_sync(0xffffffffu, gp_local, fb != 0u ? (__ffs(fb) - 1) : 0);
+      for (int k = lane; k < kpow2; k += 32) sort_keys[k] = ~0ull;
+      __syncwarp();
+      const int tie_lo = m - gp, tie_n = Keff - m;
+      int run_eq = 0;
+      run_gt = 0;
+      for (int base = 0; base < nc; base += 32) {
+        const int k = base + lane;
+        const float v = my_val[k];
+        const bool real = k < n_valid;
+        const bool gt = real && v > sstar, eq = real && v == sstar;
+        const unsigned int beq = __ballot_sync(0xffffffffu, eq), bgt = __ballot_sync(0xffffffffu, gt);
+        const int trank = run_eq + __popc(beq & lt_mask);
+        const int gt_before = run_gt + __popc(bgt & lt_mask);
+        if (gt || (eq && trank >= tie_lo && trank < tie_lo + tie_n)) {
+          int ties_before = trank - tie_lo;
+          ties_before = ties_before < 0 ? 0 : (ties_before > tie_n ? tie_n : ties_before);
+          const int item = my_groups[k >> 5] * kGroup + (k & 31);
+          sort_keys[gt_before + ties_before] = ((unsigned long long)(~f2key(v)) << 32) | (uint32_t)item;
+        }
+        run_eq += __popc(beq);
+        run_gt += __popc(bgt);
+      }
+      n_sel = Keff;
+      __syncwarp();
+      for (int kk = 2; kk <= kpow2; kk <<= 1)
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+          for (int idx = lane; idx < (kpow2 >> 1); idx += 32) {
+            const int a = ((idx & ~(jj - 1)) << 1) | (idx & (jj - 1));
+            const int c = a | jj;
+            const bool up = (a & kk) == 0;
+            const unsigned long long ka = sort_keys[a], kc = sort_keys[c];
+            if ((ka > kc) == up) { sort_keys[a] = kc; sort_keys[c] = ka; }
+          }
+          __syncwarp();
+        }
+    }
+    for (int k = lane; k < p.K; k += 32) {
+      float v = -INFINITY;
+      int idx = -1;
+      if (k < n_sel) {
+        const unsigned long long key = sort_keys[k];
+        v = key2f(~(uint32_t)(key >> 32));
+        idx = (int)(uint32_t)key + p.item_offset;
+      }
+      p.out_val[(size_t)r * p.K + k] = v;
+      p.out_idx[(size_t)r * p.K + k] = idx;
+    }
+    if (lane == 0 && p.out_flags != nullptr) p.out_flags[r] = n_cg;
+  }
+}
+
 // --------------------------------------------------------------------- predict
 template <int D>
 __global__ void __launch_bounds__(256) score_rows_kernel(const float4* __restrict__ Uemb, const int32_t* __restrict__ user_rows,
@@ -746,11 +988,19 @@ int launch_group_max_tc(const float* Uemb, const int32_t* user_rows, int n_u, co
 
 struct WsLayout {
   size_t bits_off, gmax_off, norm_off, groups_off, cval_off, udense_off, wgroups_off, wval_off, ovf_off, total;
+  size_t ugroups_off, uncg_off, uval_off, gcount_off, goffset_off, gcursor_off, pairs_off;   // group-major stage 2
   int n_groups, pitch, grid2, grid_w, cmax, wpc;
 };
 
 constexpr int kStage2OverflowCtas = 32;      // block-kernel CTAs that mop up users with > cmax candidate groups
 constexpr int kStage2CandMax = 160;          // candidate groups a warp can hold (mean 55, max 72 seen at K = 50)
+
+// stage 2 implementation: 1 = group-major re-scoring (default), 0 = the warp-per-user kernel (re-loads every candidate
+// group per user); identical results
+static int stage2_impl() {
+  const char* e = getenv("AGCF_STAGE2_IMPL");
+  return e ? atoi(e) : 1;
+}
 
 static int stage2_ctas_per_sm() {
   static int v = 0;
@@ -790,6 +1040,13 @@ static WsLayout ws_layout(int n_u, int n_items, int d) {
   L.wgroups_off = off; off = up(off + (size_t)L.grid_w * L.wpc * L.cmax * 4);
   L.wval_off = off; off = up(off + (size_t)L.grid_w * L.wpc * L.cmax * kGroup * 4);
   L.ovf_off = off; off = up(off + ((size_t)n_u + 64) * 4);          // [0] = count, [64 ..] = list
+  L.ugroups_off = off; off = up(off + (size_t)n_u * L.cmax * 4);
+  L.uncg_off = off; off = up(off + (size_t)n_u * 4);
+  L.uval_off = off; off = up(off + (size_t)n_u * L.cmax * kGroup * 4);
+  L.gcount_off = off; off = up(off + ((size_t)L.n_groups + 1) * 4);
+  L.goffset_off = off; off = up(off + ((size_t)L.n_groups + 1) * 4);
+  L.gcursor_off = off; off = up(off + ((size_t)L.n_groups + 1) * 4);
+  L.pairs_off = off; off = up(off + (size_t)n_u * L.cmax * 4);
   L.total = off;
   return L;
 }
@@ -879,9 +1136,41 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   p.w_val = reinterpret_cast<float*>(base + L.wval_off);
   p.overflow_list = ovf + 64; p.overflow_count = ovf;
   AGCF_CUDA_OK(cudaMemsetAsync(ovf, 0, 4, st));
+  p.u_groups = reinterpret_cast<int32_t*>(base + L.ugroups_off);
+  p.u_ncg = reinterpret_cast<int32_t*>(base + L.uncg_off);
+  p.u_val = reinterpret_cast<float*>(base + L.uval_off);
+  p.g_count = reinterpret_cast<int32_t*>(base + L.gcount_off);
+  p.g_offset = reinterpret_cast<int32_t*>(base + L.goffset_off);
+  p.g_cursor = reinterpret_cast<int32_t*>(base + L.gcursor_off);
+  p.pairs = reinterpret_cast<int32_t*>(base + L.pairs_off);
   int kpow2 = 1;
   while (kpow2 < K) kpow2 <<= 1;
   const size_t dyn = (size_t)kpow2 * 8;
+  if (stage2_impl() == 1 && n_u < (1 << 23) && L.cmax <= 256) {
+    // group-major: candidates -> per-group pair lists -> re-score each group's tile once per CTA -> select
+    AGCF_CUDA_OK(cudaMemsetAsync(p.g_count, 0, ((size_t)L.n_groups + 1) * 4, st));
+    const unsigned warp_grid = (unsigned)min((n_u + 7) / 8, 8 * kSMs);
+    const size_t dyn_sel = 8 * (1024 + (size_t)kpow2 * 8);
+    if (dyn_sel > 200 * 1024) return AGCF_EUNSUPPORTED;
+#define AGCF_S2G(DD)                                                                                             \
+  {                                                                                                              \
+    const size_t dyn_r = ((size_t)kGroup * (DD + 4) + 8 * DD) * 4;                                               \
+    if (dyn_r > 48 * 1024)                                                                                       \
+      AGCF_CUDA_OK(cudaFuncSetAttribute(s2_rescore_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_r)); \
+    if (dyn_sel > 48 * 1024)                                                                                     \
+      AGCF_CUDA_OK(cudaFuncSetAttribute(s2_select_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel)); \
+    s2_candidates_kernel<DD><<<warp_grid, 256, 0, st>>>(p);                                                      \
+    s2_scan_kernel<<<1, 1024, 0, st>>>(p.g_count, L.n_groups, p.g_offset, p.g_cursor);                           \
+    s2_pairs_kernel<<<warp_grid, 256, 0, st>>>(p);                                                               \
+    s2_rescore_kernel<DD><<<dim3((unsigned)L.n_groups, kS2Slices), 256, dyn_r, st>>>(p);                         \
+    s2_select_kernel<DD><<<warp_grid, 256, dyn_sel, st>>>(p);                                                    \
+    topk_select_kernel<DD><<<(unsigned)L.grid2, 256, dyn, st>>>(p);                                              \
+  }
+    switch (d) { case 32: AGCF_S2G(32) break; case 64: AGCF_S2G(64) break; case 128: AGCF_S2G(128) break; case 256: AGCF_S2G(256) break; }
+#undef AGCF_S2G
+    AGCF_LAUNCH_OK();
+    return AGCF_OK;
+  }
   // warp per user, then the block kernel on the users the warp kernel could not hold (normally none)
 #define AGCF_S2(DD)                                                                                              \
   {                                                                                                              \

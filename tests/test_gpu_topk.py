@@ -8,6 +8,13 @@ from _util import assert_topk_matches
 from oracle import port
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["1", "0"], ids=["stage2-group-major", "stage2-warp-per-user"])
+def stage2_impl(request, monkeypatch):
+    """every test runs on both stage-2 implementations (csrc/score.cu): they must agree bit for bit"""
+    monkeypatch.setenv("AGCF_STAGE2_IMPL", request.param)
+    return request.param
 DEV = "cuda:0"
 
 
@@ -265,3 +272,22 @@ def test_masked_score_topk_equals_the_attacks_dense_topk():
     vals2, idx2 = masked_score_topk(Pu.cuda(), Pi.cuda(), K, None)
     ref_v2, _ = torch.topk(Pu.double() @ Pi.double().T, K)
     np.testing.assert_allclose(vals2.cpu().numpy(), ref_v2.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_stage2_implementations_are_bit_identical(monkeypatch):
+    from arlib_b200 import ops
+    rng = np.random.default_rng(8)
+    U, I, d, K = 3000, 9000, 64, 50
+    ue = torch.from_numpy(rng.standard_normal((U, d)).astype(np.float32)).to(DEV)
+    ie = torch.from_numpy((rng.standard_normal((I, d)) * (1 + 3 * rng.random((I, 1)) ** 4)).astype(np.float32)).to(DEV)
+    lists = [np.sort(rng.choice(I, rng.integers(0, 200), replace=False)) for _ in range(U)]
+    mrp, mit = _mask_csr(U, lists)
+    outs = {}
+    for impl2 in ("1", "0"):
+        monkeypatch.setenv("AGCF_STAGE2_IMPL", impl2)
+        for impl1 in (1, 0):
+            outs[(impl2, impl1)] = ops.score_topk(ue, ie, K, mask_rowptr=mrp, mask_items=mit, impl=impl1, return_flags=True)
+    ref = outs[("0", 0)]
+    for key, got in outs.items():
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), key
+    assert torch.equal(outs[("1", 1)][2], outs[("0", 1)][2])               # same candidate-group counts
