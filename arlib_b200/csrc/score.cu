@@ -300,9 +300,7 @@ struct Stage2Params {
   int32_t* u_ncg;              // [n_u] their count, -1 = overflow (block kernel)
   float* u_val;                // [n_u][cmax*32] exact scores of the candidates
   int32_t* g_count;            // [n_groups] users that have the group as a candidate (zeroed by the caller)
-  int32_t* g_offset;           // [n_groups + 1]
-  int32_t* g_cursor;           // [n_groups]
-  int32_t* pairs;              // [n_u * cmax] (user << 8 | candidate slot), grouped by group
+  int32_t* pairs;              // [n_groups][n_u] (user << 8 | candidate slot) of the users that have the group
 };
 
 template <int D>
@@ -677,11 +675,9 @@ __global__ void __launch_bounds__(32 * S2W<D>::WPC) topk_select_warp_kernel(cons
 // The warp-per-user kernel above copies every candidate group (32 item rows, 8 KB at d = 64) once per user that
 // has it: 57 groups x 8 KB = 467 KB of L2 -> SM traffic per user, 12 GB per Gowalla evaluation -- the whole cost of
 // stage 2.  A group is a candidate of ~1 200 users; here it is loaded ONCE per CTA and the users stream past it
-// (256 B each): ~0.65 GB per evaluation.  Four kernels:
-//   s2_candidates : per user (warp) the threshold and the ordered candidate groups; per group a count
-//   s2_scan       : exclusive scan of the counts (one CTA)
-//   s2_pairs      : (user, slot) pairs bucketed by group (order inside a bucket is irrelevant: each pair's scores
-//                   are computed independently and land at a fixed place)
+// (256 B each): ~0.65 GB per evaluation.  Three kernels:
+//   s2_candidates : per user (warp) the threshold and the ordered candidate groups; the (user, slot) pairs are
+//                   bucketed by group on the spot (every group owns n_u slots)
 //   s2_rescore    : CTA per (group, slice): tile in shared memory, one warp per pair, lane l walks ITS item's row in
 //                   the reference order (k ascending, fmaf) -- the same bits as exact_dot / the warp kernel
 //   s2_select     : per user (warp) step 4 of the warp kernel on the stored scores
@@ -724,50 +720,15 @@ __global__ void __launch_bounds__(256) s2_candidates_kernel(const Stage2Params p
       continue;
     }
     __syncwarp();
-    for (int c = lane; c < n_cg; c += 32) atomicAdd(p.g_count + my_groups[c], 1);
-    if (lane == 0) p.u_ncg[r] = n_cg;
-  }
-}
-
-__global__ void __launch_bounds__(1024) s2_scan_kernel(const int32_t* __restrict__ count, int n, int32_t* __restrict__ offset,
-                                                       int32_t* __restrict__ cursor) {
-  __shared__ int warp_tot[32];
-  __shared__ int carry;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int k = base + threadIdx.x;
-    const int v = k < n ? count[k] : 0;
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    int before = carry;
-    for (int w = 0; w < warp; ++w) before += warp_tot[w];
-    if (k < n) { offset[k] = before + incl - v; cursor[k] = 0; }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = before + incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) offset[n] = carry;
-}
-
-__global__ void __launch_bounds__(256) s2_pairs_kernel(const Stage2Params p) {
-  const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int r = gw; r < p.n_u; r += n_warps) {
-    const int n_cg = p.u_ncg[r];
-    const int32_t* my_groups = p.u_groups + (size_t)r * p.cmax;
+    // bucket the (user, slot) pairs by group: every group owns n_u slots (a group is a candidate of every user at
+    // most once), so a pair takes the next free one -- no scan, no second pass; the order inside a bucket is
+    // irrelevant (each pair's scores land at a fixed place)
     for (int c = lane; c < n_cg; c += 32) {
       const int g = my_groups[c];
-      const int pos = atomicAdd(p.g_cursor + g, 1);
-      p.pairs[p.g_offset[g] + pos] = (r << 8) | c;
+      const int pos = atomicAdd(p.g_count + g, 1);
+      p.pairs[(size_t)g * p.n_u + pos] = (r << 8) | c;
     }
+    if (lane == 0) p.u_ncg[r] = n_cg;
   }
 }
 
@@ -778,41 +739,69 @@ __global__ void __launch_bounds__(256) s2_rescore_kernel(const Stage2Params p) {
   constexpr int LD = D + 4, V4 = D / 4;
   extern __shared__ __align__(16) unsigned char dyn[];
   float* tile = reinterpret_cast<float*>(dyn);                       // [32][LD]
-  float* urow_all = tile + kGroup * LD;                              // [8][D]
+  float* urow_all = tile + kGroup * LD;                              // [8 warps][PB][D]
   const int g = blockIdx.x, slice = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int first = p.g_offset[g], cnt = p.g_offset[g + 1] - first;
+  const int cnt = p.g_count[g];
   if (slice * 8 >= cnt) return;                                      // nothing for this slice (uniform per CTA)
+  const int32_t* my_pairs = p.pairs + (size_t)g * p.n_u;
   const int rows_here = min(kGroup, p.n_items - g * kGroup);
   const float4* src = p.Iemb + (size_t)g * kGroup * V4;
+  // (lane l keeping ITS item's row in registers instead -- no tile reads, only the broadcast user row -- was measured
+  //  slower: 494 vs 308 us per chunk; 94 registers halve the resident warps and the per-lane row load is uncoalesced)
   for (int f = threadIdx.x; f < kGroup * V4; f += 256) {
     const int row = f / V4, c4 = f - row * V4;
     const float4 v = row < rows_here ? __ldg(src + f) : make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(tile + row * LD + 4 * c4) = v;
   }
   __syncthreads();
-  float* urow = urow_all + warp * D;
+  // A warp scores PB pairs per trip: the 32 lanes read 32 different tile rows (4 wavefronts per float4 step), a user
+  // row is a broadcast (1 wavefront) -- sharing every tile read between PB users cuts the shared-memory traffic per
+  // pair from 5 to (4 + PB) / PB wavefronts per step; it bounded the kernel.
+  constexpr int PB = 4;
+  float* urows = urow_all + warp * PB * D;
   const float* mine_row = tile + lane * LD;
-  for (int q = slice * 8 + warp; q < cnt; q += kS2Slices * 8) {
-    const int pr = p.pairs[first + q];
-    const int r = pr >> 8, c = pr & 255;
-    const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
+  const int stride = kS2Slices * 8;
+  for (int q0 = slice * 8 + warp; q0 < cnt; q0 += PB * stride) {
+    int pr[PB];
+    uint32_t word[PB];
     __syncwarp();
-    for (int k = lane; k < V4; k += 32) reinterpret_cast<float4*>(urow)[k] = __ldg(p.Uemb + (size_t)uid * V4 + k);
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int q = q0 + j * stride;
+      pr[j] = q < cnt ? my_pairs[q] : -1;
+      word[j] = 0u;
+      if (pr[j] >= 0) {
+        const int r = pr[j] >> 8;
+        const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
+        for (int k = lane; k < V4; k += 32) reinterpret_cast<float4*>(urows + j * D)[k] = __ldg(p.Uemb + (size_t)uid * V4 + k);
+        word[j] = __ldg(p.bits + (size_t)r * p.pitch + g);
+      }
+    }
     __syncwarp();
-    float sc = 0.f;
+    float sc[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) sc[j] = 0.f;
 #pragma unroll 4
     for (int k4 = 0; k4 < V4; ++k4) {
       const float4 v = *reinterpret_cast<const float4*>(mine_row + 4 * k4);
-      const float4 u = *reinterpret_cast<const float4*>(urow + 4 * k4);
-      sc = fmaf(u.x, v.x, sc);
-      sc = fmaf(u.y, v.y, sc);
-      sc = fmaf(u.z, v.z, sc);
-      sc = fmaf(u.w, v.w, sc);
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(urows + j * D + 4 * k4);
+        sc[j] = fmaf(w.x, v.x, sc[j]);
+        sc[j] = fmaf(w.y, v.y, sc[j]);
+        sc[j] = fmaf(w.z, v.z, sc[j]);
+        sc[j] = fmaf(w.w, v.w, sc[j]);
+      }
     }
-    if (lane >= rows_here) sc = -FLT_MAX;
-    else if ((__ldg(p.bits + (size_t)r * p.pitch + g) >> lane) & 1u) sc = kMasked;
-    p.u_val[((size_t)r * p.cmax + c) * kGroup + lane] = sc;
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      if (pr[j] < 0) continue;
+      float v = sc[j];
+      if (lane >= rows_here) v = -FLT_MAX;
+      else if ((word[j] >> lane) & 1u) v = kMasked;
+      p.u_val[((size_t)(pr[j] >> 8) * p.cmax + (pr[j] & 255)) * kGroup + lane] = v;
+    }
   }
 }
 
@@ -988,7 +977,7 @@ int launch_group_max_tc(const float* Uemb, const int32_t* user_rows, int n_u, co
 
 struct WsLayout {
   size_t bits_off, gmax_off, norm_off, groups_off, cval_off, udense_off, wgroups_off, wval_off, ovf_off, total;
-  size_t ugroups_off, uncg_off, uval_off, gcount_off, goffset_off, gcursor_off, pairs_off;   // group-major stage 2
+  size_t ugroups_off, uncg_off, uval_off, gcount_off, pairs_off;   // group-major stage 2
   int n_groups, pitch, grid2, grid_w, cmax, wpc;
 };
 
@@ -1044,9 +1033,7 @@ static WsLayout ws_layout(int n_u, int n_items, int d) {
   L.uncg_off = off; off = up(off + (size_t)n_u * 4);
   L.uval_off = off; off = up(off + (size_t)n_u * L.cmax * kGroup * 4);
   L.gcount_off = off; off = up(off + ((size_t)L.n_groups + 1) * 4);
-  L.goffset_off = off; off = up(off + ((size_t)L.n_groups + 1) * 4);
-  L.gcursor_off = off; off = up(off + ((size_t)L.n_groups + 1) * 4);
-  L.pairs_off = off; off = up(off + (size_t)n_u * L.cmax * 4);
+  L.pairs_off = off; off = up(off + (size_t)L.n_groups * n_u * 4);
   L.total = off;
   return L;
 }
@@ -1140,8 +1127,6 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   p.u_ncg = reinterpret_cast<int32_t*>(base + L.uncg_off);
   p.u_val = reinterpret_cast<float*>(base + L.uval_off);
   p.g_count = reinterpret_cast<int32_t*>(base + L.gcount_off);
-  p.g_offset = reinterpret_cast<int32_t*>(base + L.goffset_off);
-  p.g_cursor = reinterpret_cast<int32_t*>(base + L.gcursor_off);
   p.pairs = reinterpret_cast<int32_t*>(base + L.pairs_off);
   int kpow2 = 1;
   while (kpow2 < K) kpow2 <<= 1;
@@ -1154,14 +1139,12 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
     if (dyn_sel > 200 * 1024) return AGCF_EUNSUPPORTED;
 #define AGCF_S2G(DD)                                                                                             \
   {                                                                                                              \
-    const size_t dyn_r = ((size_t)kGroup * (DD + 4) + 8 * DD) * 4;                                               \
+    const size_t dyn_r = ((size_t)kGroup * (DD + 4) + 8 * 4 * DD) * 4;      /* tile + 8 warps x PB user rows */      \
     if (dyn_r > 48 * 1024)                                                                                       \
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_rescore_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_r)); \
     if (dyn_sel > 48 * 1024)                                                                                     \
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_select_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel)); \
     s2_candidates_kernel<DD><<<warp_grid, 256, 0, st>>>(p);                                                      \
-    s2_scan_kernel<<<1, 1024, 0, st>>>(p.g_count, L.n_groups, p.g_offset, p.g_cursor);                           \
-    s2_pairs_kernel<<<warp_grid, 256, 0, st>>>(p);                                                               \
     s2_rescore_kernel<DD><<<dim3((unsigned)L.n_groups, kS2Slices), 256, dyn_r, st>>>(p);                         \
     s2_select_kernel<DD><<<warp_grid, 256, dyn_sel, st>>>(p);                                                    \
     topk_select_kernel<DD><<<(unsigned)L.grid2, 256, dyn, st>>>(p);                                              \
