@@ -26,7 +26,7 @@ def _mask_csr(U, lists):
 
 
 @pytest.mark.parametrize("U,I,d,K", [(70, 1000, 64, 50), (130, 333, 32, 10), (64, 4100, 128, 50), (5, 31, 64, 3),
-                                      (33, 2049, 256, 100)])
+                                      (33, 2049, 256, 100), (40, 70000, 32, 20)])
 def test_topk_exact_scores_and_sets(U, I, d, K):
     from arlib_b200 import ops
     rng = np.random.default_rng(U + I)

@@ -1,12 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_s60.log 2>&1
-tail -3 gpurun_out/pytest_s60.log | cut -c1-200
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 900 python bench.py > gpurun_out/bench_s60_n1.json 2> gpurun_out/bench_s60_n1.err
-python - <<PY
-import json
-l=json.loads(open("gpurun_out/bench_s60_n1.json").read().strip().splitlines()[-1])
-r=l["roofline"]; e=l["eval"]
-print("value %.4g"%l["value"], "ms/step %.4f"%l["ms_per_step"], "e2e %.4g"%l["e2e"]["value"], "frac %.3f"%r["frac"], "eval %.4g users/s %.3f ms"%(e["users_per_s"], e["ms"]), "eval frac %.3f"%e["roofline"]["frac"], "e2e_eval %.4g"%e["e2e_users_per_s"], l["clocks"])
-PY
+timeout 600 python -m pytest tests/test_gpu_topk.py tests/test_gpu_fullsize.py -x -q > gpurun_out/pytest_s61.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/pytest_s61.log | cut -c1-300
+for i in 1 0; do AGCF_STAGE2_IMPL=$i timeout 200 python tools/eval_bench.py 2>&1 | sed -n '1p;3p'; done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 50 --csv --log-file gpurun_out/launches_eval_s61.csv python tools/eval_bench.py > /dev/null 2>&1
+python tools/launch_summary.py gpurun_out/launches_eval_s61.csv 2>/dev/null | head -9
