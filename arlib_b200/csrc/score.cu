@@ -732,6 +732,9 @@ __global__ void __launch_bounds__(256) s2_candidates_kernel(const Stage2Params p
   }
 }
 
+#ifndef AGCF_S2_PB
+#define AGCF_S2_PB 4            // pairs a warp scores per trip (4: 219 us per chunk)
+#endif
 constexpr int kS2Slices = 8;               // CTAs per group in s2_rescore (popular groups have >10 000 users)
 
 template <int D>
@@ -758,7 +761,7 @@ __global__ void __launch_bounds__(256) s2_rescore_kernel(const Stage2Params p) {
   // A warp scores PB pairs per trip: the 32 lanes read 32 different tile rows (4 wavefronts per float4 step), a user
   // row is a broadcast (1 wavefront) -- sharing every tile read between PB users cuts the shared-memory traffic per
   // pair from 5 to (4 + PB) / PB wavefronts per step; it bounded the kernel.
-  constexpr int PB = 4;
+  constexpr int PB = AGCF_S2_PB;
   float* urows = urow_all + warp * PB * D;
   const float* mine_row = tile + lane * LD;
   const int stride = kS2Slices * 8;
@@ -1139,7 +1142,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
     if (dyn_sel > 200 * 1024) return AGCF_EUNSUPPORTED;
 #define AGCF_S2G(DD)                                                                                             \
   {                                                                                                              \
-    const size_t dyn_r = ((size_t)kGroup * (DD + 4) + 8 * 4 * DD) * 4;      /* tile + 8 warps x PB user rows */      \
+    const size_t dyn_r = ((size_t)kGroup * (DD + 4) + 8 * AGCF_S2_PB * DD) * 4;   /* tile + 8 warps x PB user rows */ \
     if (dyn_r > 48 * 1024)                                                                                       \
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_rescore_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_r)); \
     if (dyn_sel > 48 * 1024)                                                                                     \
