@@ -151,8 +151,14 @@ class FullRankEvaluator:
         i1 = n_items * (rank + 1) // world
         block = item_emb[i0:i1].detach().contiguous()
         n = self.user_rows.numel()
-        vals, idx = ops.score_topk(user_emb.detach().contiguous(), block, K, user_rows=self.user_rows,
-                                   mask_rowptr=self.mask_rowptr, mask_items=self.mask_items, item_offset=i0, impl=impl)
+        ue = user_emb.detach().contiguous()
+        vals = torch.empty((n, K), dtype=torch.float32, device=self.device)
+        idx = torch.empty((n, K), dtype=torch.int32, device=self.device)
+        for lo in range(0, n, USER_CHUNK):                   # the stage-2 workspace grows with the users of a call
+            hi = min(n, lo + USER_CHUNK)
+            v, i = ops.score_topk(ue, block, K, user_rows=self.user_rows[lo:hi], mask_rowptr=self.mask_rowptr,
+                                  mask_items=self.mask_items, item_offset=i0, impl=impl)
+            vals[lo:hi], idx[lo:hi] = v, i
         all_v = torch.empty((world, n, K), dtype=torch.float32, device=self.device)
         all_i = torch.empty((world, n, K), dtype=torch.int32, device=self.device)
         dist.all_gather_into_tensor(all_v, vals)
