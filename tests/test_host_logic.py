@@ -75,3 +75,34 @@ def test_unique_ids_like_reference_round_trips_through_float32():
     assert torch.equal(unique_ids_like_reference(ids, "cpu"), want)
     assert torch.equal(unique_ids_like_reference(torch.tensor(ids), "cpu"), want)
     assert int(want[-1]) == 2 ** 24                                    # the reference's float32 rounding is kept
+
+
+def test_fusable_adam_recognises_exactly_the_plain_optimizer_over_the_models_parameters():
+    """attack/White/CLeaR.py:59,145-146: ``torch.optim.Adam(model.parameters(), lr)`` handed to train().  Note that
+    nn.ParameterDict sorts its keys, so model.parameters() yields item_emb BEFORE user_emb."""
+    from arlib_b200.recommender._base import GraphRecommender
+    m = torch.nn.Module()
+    m.embedding_dict = torch.nn.ParameterDict({'user_emb': torch.nn.Parameter(torch.zeros(3, 4)),
+                                               'item_emb': torch.nn.Parameter(torch.zeros(5, 4))})
+    f = GraphRecommender._fusable_adam
+    got = f(torch.optim.Adam(m.parameters(), lr=0.003, betas=(0.8, 0.99), eps=1e-7), m)
+    assert got == {"lr": 0.003, "betas": (0.8, 0.99), "eps": 1e-7}
+    assert f(torch.optim.Adam([m.embedding_dict['user_emb'], m.embedding_dict['item_emb']], lr=0.1), m) is not None
+    for bad in (torch.optim.SGD(m.parameters(), lr=0.1),
+                torch.optim.AdamW(m.parameters(), lr=0.1),
+                torch.optim.Adam(m.parameters(), lr=0.1, amsgrad=True),
+                torch.optim.Adam(m.parameters(), lr=0.1, weight_decay=1e-4),
+                torch.optim.Adam(m.parameters(), lr=0.1, maximize=True),
+                torch.optim.Adam([m.embedding_dict['user_emb']], lr=0.1),                      # not all parameters
+                torch.optim.Adam([{'params': [m.embedding_dict['user_emb']]}, {'params': [m.embedding_dict['item_emb']]}], lr=0.1),
+                torch.optim.Adam([torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5, 4))], lr=0.1)):  # stale
+        assert f(bad, m) is None, type(bad).__name__
+    # a model with extra parameters (NGCF's weight matrices) is not the two-table case
+    m2 = torch.nn.Module()
+    m2.embedding_dict = m.embedding_dict
+    m2.W = torch.nn.Parameter(torch.zeros(4, 4))
+    assert f(torch.optim.Adam([m.embedding_dict['user_emb'], m.embedding_dict['item_emb']], lr=0.1), m2) is None
+    # state handover helpers on CPU tensors: a half-initialised state (one parameter stepped) is refused
+    opt = torch.optim.Adam(m.parameters(), lr=0.1)
+    opt.state[m.embedding_dict['user_emb']] = {'step': torch.tensor(3.0), 'exp_avg': torch.zeros(3, 4), 'exp_avg_sq': torch.zeros(3, 4)}
+    assert f(opt, m) is None
