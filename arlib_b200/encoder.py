@@ -144,24 +144,38 @@ class _Propagate(torch.autograd.Function):
 
 
 class _SpMM(torch.autograd.Function):
-    """Y = A X as a differentiable op (NGCF's two propagations per layer)."""
+    """Y = A X as a differentiable op (NGCF's two propagations per layer).  ``adj`` is the encoder's sparse COO leaf
+    (or None): when it requires grad the backward also returns dL/dA on the stored pattern -- <gY[i], X[j]> per
+    non-zero (agcf_sddmm_csr_f32), what torch.sparse.mm's autograd gives attack/White/PGA.py:98,117."""
 
     @staticmethod
-    def forward(ctx, x, graph):
+    def forward(ctx, x, adj, graph):
         ctx.graph = graph
+        ctx.need_adj_grad = adj is not None and adj.requires_grad and ctx.needs_input_grad[1]
+        x = x.detach().contiguous()
+        if ctx.need_adj_grad:
+            ctx.save_for_backward(x)
         y = torch.empty_like(x)
-        ops.spmm(graph, x.detach().contiguous(), Y=y)
+        ops.spmm(graph, x, Y=y)
         return y
 
     @staticmethod
     def backward(ctx, gy):
+        g = ctx.graph
+        gy = gy.contiguous()
         gx = torch.empty_like(gy)
-        ops.spmm(ctx.graph, gy.contiguous(), Y=gx)
-        return gx, None
+        ops.spmm(g, gy, Y=gx)
+        adj_grad = None
+        if ctx.need_adj_grad:
+            (x,) = ctx.saved_tensors
+            gval = torch.empty(g.nnz, dtype=torch.float32, device=gy.device)
+            ops.sddmm(g, gy, x, gval)
+            adj_grad = torch.sparse_coo_tensor(g.coo_indices(), gval, (g.n_rows, g.n_rows), is_coalesced=True)
+        return gx, adj_grad, None
 
 
-def spmm_autograd(graph, x):
-    return _SpMM.apply(x, graph)
+def spmm_autograd(graph, x, adj=None):
+    return _SpMM.apply(x, adj, graph)
 
 
 # --------------------------------------------------------------------- modules
@@ -363,11 +377,12 @@ class NGCF_Encoder(GraphEncoderBase):
         import torch.nn.functional as F
         pu, pi = self.embedding_dict['user_emb'], self.embedding_dict['item_emb']
         ego = torch.cat([pu, pi], 0)
+        adj = self._adj_for_autograd()
         layers = [ego]
         for k in range(self.layers):
             t = torch.mm(ego, self.W['w1_' + str(k)])
-            ego = F.leaky_relu(spmm_autograd(self._graph, t) + t +
-                               torch.mm(spmm_autograd(self._graph, ego) * ego, self.W['w2_' + str(k)]))
+            ego = F.leaky_relu(spmm_autograd(self._graph, t, adj) + t +
+                               torch.mm(spmm_autograd(self._graph, ego, adj) * ego, self.W['w2_' + str(k)]))
             layers.append(ego)
         out = torch.mean(torch.stack(layers, dim=1), dim=1)
         return out[:self.data.user_num], out[self.data.user_num:]

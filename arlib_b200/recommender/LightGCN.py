@@ -12,7 +12,7 @@ import torch
 
 from ..encoder import LGCN_Encoder, TorchGraphInterface  # noqa: F401  (re-exported like the reference module)
 from ..engine import LightGCNEngine
-from ..util.loss import bpr_loss, l2_reg_loss
+from ..util.loss import bpr_l2_fused, bpr_loss, l2_reg_loss  # noqa: F401
 from ..util.sampler import next_batch_pairwise
 from ._base import GraphRecommender
 
@@ -42,12 +42,11 @@ class LightGCN(GraphRecommender):
         dev = model.embedding_dict['user_emb'].device
         for epoch in range(maxEpoch):
             for n, batch in enumerate(self._epoch_batches(dev)):
-                user_idx, pos_idx, neg_idx = (torch.as_tensor(x, dtype=torch.long, device=dev) for x in batch)
+                user_idx, pos_idx, neg_idx = batch
                 model.train()
                 rec_user_emb, rec_item_emb = model()
-                user_emb, pos_item_emb, neg_item_emb = rec_user_emb[user_idx], rec_item_emb[pos_idx], rec_item_emb[neg_idx]
-                batch_loss = bpr_loss(user_emb, pos_item_emb, neg_item_emb) + l2_reg_loss(self.args.reg, user_emb,
-                                                                                          pos_item_emb)
+                # the three gathers + bpr_loss + l2_reg_loss(reg, user_emb, pos_item_emb) of the reference, one fused op
+                batch_loss = bpr_l2_fused(rec_user_emb, rec_item_emb, user_idx, pos_idx, neg_idx, self.args.reg)
                 self.optimizer.zero_grad()
                 batch_loss.backward()
                 self._accumulate_grads(requires_adjgrad, requires_embgrad, maxEpoch, epoch, gradIterationNum)

@@ -6,7 +6,7 @@ into the epilogue."""
 import torch
 
 from ..encoder import SimGCL_Encoder, TorchGraphInterface  # noqa: F401
-from ..util.loss import bpr_loss, l2_reg_loss
+from ..util.loss import bpr_l2_fused, bpr_loss, l2_reg_loss  # noqa: F401
 from ._base import GraphRecommender
 
 
@@ -38,13 +38,13 @@ class SimGCL(GraphRecommender):
         for epoch in range(maxEpoch):
             for n, batch in enumerate(self._epoch_batches(dev)):
                 user_idx, pos_idx, neg_idx = batch
-                ut, pt, nt = (torch.as_tensor(x, dtype=torch.long, device=dev) for x in batch)
                 model.train()
                 rec_user_emb, rec_item_emb = model()
-                user_emb, pos_item_emb, neg_item_emb = rec_user_emb[ut], rec_item_emb[pt], rec_item_emb[nt]
-                rec_loss = bpr_loss(user_emb, pos_item_emb, neg_item_emb)
+                rec_l2, parts = bpr_l2_fused(rec_user_emb, rec_item_emb, user_idx, pos_idx, neg_idx, self.args.reg,
+                                             return_parts=True)
+                rec_loss = parts[1]
                 cl_loss = self.cl_rate * model.cal_cl_loss([user_idx, pos_idx])
-                batch_loss = rec_loss + l2_reg_loss(self.args.reg, user_emb, pos_item_emb) + cl_loss
+                batch_loss = rec_l2 + cl_loss
                 optimizer.zero_grad()
                 batch_loss.backward()
                 self._accumulate_grads(requires_adjgrad, requires_embgrad, maxEpoch, epoch, gradIterationNum)

@@ -30,7 +30,13 @@ class GraphRecommender(object):
         self.recOutput = []
         self.topN = [int(num) for num in self.args.topK.split(',')]
         self.max_N = max(self.topN)
+        # the row kernels hold a row as d/4 float4 lanes and are compiled for these widths only (csrc/common.cuh);
+        # there is no fallback path by design, so say so here instead of failing inside the first propagation
+        if int(self.args.emb_size) not in (32, 64, 128, 256):
+            raise ValueError("arlib_b200: emb_size must be one of 32, 64, 128, 256 (got %r); the sm_100a row kernels "
+                             "are compiled for these widths and there is no CPU / generic fallback" % (self.args.emb_size,))
         self._evaluator = None
+        self._train_set = None                # device mirrors are derived from ``data``: a re-__init__ drops both
         self.model = self._build_model()
 
     def _build_model(self):
@@ -128,6 +134,15 @@ class GraphRecommender(object):
         k = getattr(self, '_epochs_sampled', 0)
         self._epochs_sampled = k + 1
         return k
+
+    def _next_noise_seed(self, seed):
+        """Philox key of the perturbation noise of ONE train() call.  The engine's counter is (key, step, stream, row)
+        and its step restarts at 0 with every engine, so the key mixes in a per-instance call counter: an attack that
+        re-enters train(Epoch=1) must not replay the same perturbations per step index (the reference's
+        torch.rand_like stream simply keeps advancing, recommender/SimGCL.py:204)."""
+        k = getattr(self, '_noise_calls', 0)
+        self._noise_calls = k + 1
+        return ((seed * 2654435761 + 12345) ^ (k * 0x9E3779B97F4A7C15)) & 0xffffffffffffffff or 1
 
     def _device_train_set(self, dev):
         """Device mirror of data.training_data / training_set_u for the Philox sampler, rebuilt only when the data
@@ -240,7 +255,7 @@ class GraphRecommender(object):
         adam = adam or {"lr": self.args.lRate, "betas": (0.9, 0.999), "eps": 1e-8}
         eng = ContrastiveEngine(model._graph, table, self.data.user_num, kind, self.n_layers, self.eps, self.cl_rate, tau,
                                 adam["lr"], self.args.reg, self.args.batch_size, len(self.data.training_data),
-                                layer_cl=layer_cl, noise_seed=(seed * 2654435761 + 12345) & 0xffffffffffff or 1,
+                                layer_cl=layer_cl, noise_seed=self._next_noise_seed(seed),
                                 betas=adam["betas"], adam_eps=adam["eps"])
         if optimizer is not None:
             self._adam_state_to_engine(optimizer, model, eng, self.data.user_num)

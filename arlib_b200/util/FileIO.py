@@ -62,7 +62,8 @@ class FileIO(object):
             import pandas as pd
             df = pd.read_csv(file, sep=' ', header=None, usecols=[0, 1, 2], dtype={0: str, 1: str, 2: np.float64},
                              engine='c', keep_default_na=False, na_filter=False, skip_blank_lines=False,
-                             quoting=3, skipinitialspace=False)
+                             quoting=3, skipinitialspace=False,
+                             float_precision='round_trip')      # == float(text) of the reference, to the last ulp
             return rows_from_columns(df[0].to_numpy(dtype=object), df[1].to_numpy(dtype=object),
                                      df[2].to_numpy(dtype=np.float64))
         except Exception:

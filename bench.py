@@ -123,11 +123,94 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------- CPU baseline leg
-def cpu_train_baseline(D, n_steps, n_warm):
-    """The oracle port of the reference's CPU torch path (oracle/ is used here ONLY as
-    the timed baseline): body of recommender/LightGCN.py:47-64 incl. the Python sampler
-    cost model (per-triple rejection sampling against the train set)."""
+# ------------------------------------------------------------------- baseline legs
+def host_threads():
+    """all host cores for the CPU legs: torchrun exports OMP_NUM_THREADS=1 to every rank, which would make the
+    reference arm single-threaded at N > 1 -- the arm runs on rank 0 alone and may use the whole host"""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
+def write_reference_dataset(D, name, max_test_users):
+    """the synthetic graph in the reference's text format ("<user> <item> 1" per line, util/FileIO.py:22-31) under
+    /tmp/arlib_b200_ref/data/clean/<name>/; the test file keeps the pairs of the first ``max_test_users`` test users
+    (the bounded evaluation sample)"""
+    root = "/tmp/arlib_b200_ref"
+    d = os.path.join(root, "data", "clean", name)
+    os.makedirs(d, exist_ok=True)
+    users = np.unique(D["su"])[:max_test_users]
+    keep = np.isin(D["su"], users)
+
+    def dump(path, u, i):
+        with open(path, "w") as fh:
+            fh.write("".join("%d %d 1\n" % (a, b) for a, b in zip(u.tolist(), i.tolist())))
+    dump(os.path.join(d, "train.txt"), D["tu"], D["ti"])
+    dump(os.path.join(d, "test.txt"), D["su"][keep], D["si"][keep])
+    dump(os.path.join(d, "val.txt"), D["su"][keep][:1000], D["si"][keep][:1000])
+    return root, int(users.shape[0])
+
+
+def reference_leg(D, name, n_steps, n_warm, cuda, eval_users=2000):
+    """The UNMODIFIED reference (oracle/_ref, staged by oracle/make_ref.py) through its own public API:
+    ``DataLoader(args)``, ``LightGCN(args, data)``, ``train(Epoch=1)`` and ``test()`` (recommender/LightGCN.py:29-80,
+    137-161).  The only interception is the sampler generator, wrapped to stop after n_warm + n_steps batches and to
+    take the timestamps -- so a timed step is exactly the reference's: Python rejection sampler (util/sampler.py:4-30),
+    model(), gathers, bpr_loss + l2_reg_loss, backward, Adam.  ``cuda=False``: the reference's CPU torch path (its
+    ``.cuda()`` calls made identities); ``cuda=True``: its own eager PyTorch + cuSPARSE path on this GPU.
+    -> dict(triples_per_s, s_per_step, users_per_s, n_eval_users)"""
+    import contextlib
+    import io
+    from oracle import ref_loader
+    root, n_eval = write_reference_dataset(D, name, eval_users)
+    stamps = []
+    old = os.getcwd()
+    os.chdir(root)
+    try:
+        with ref_loader.reference_modules(cuda=cuda) as ref, contextlib.redirect_stdout(io.StringIO()):
+            args = ref_loader.make_args(ref, dataset=name, data_path="data/clean/", model_name="LightGCN", maxEpoch=1,
+                                        n_layers=D["L"], emb_size=D["d"], batch_size=D["B"], lRate=LR, reg=REG,
+                                        topK=str(TOPK))
+            ref.tool.seedSet(2018)
+            data = ref.DataLoader(args)
+            rec = ref.LightGCN.LightGCN(args, data)
+            real = ref.LightGCN.next_batch_pairwise
+
+            def sync():
+                if cuda:
+                    torch.cuda.synchronize()
+
+            def truncated(d_, bs):
+                for k, b in enumerate(real(d_, bs)):
+                    if k >= n_warm + n_steps:
+                        break
+                    if k == n_warm:
+                        sync(); stamps.append(time.perf_counter())
+                    yield b
+                sync(); stamps.append(time.perf_counter())
+            ref.LightGCN.next_batch_pairwise = truncated
+            ref.algorithm.find_k_largest(TOPK, np.random.rand(D["I"]).astype(np.float32))      # numba JIT warm-up
+            try:
+                rec.train(Epoch=1)               # the truncated epoch, then the reference's own evaluate() (untimed here)
+            finally:
+                ref.LightGCN.next_batch_pairwise = real
+            sync(); t0 = time.perf_counter()
+            rec.test()
+            sync(); t_eval = time.perf_counter() - t0
+    finally:
+        os.chdir(old)
+    dt = stamps[1] - stamps[0]
+    return {"triples_per_s": n_steps * D["B"] / dt, "s_per_step": dt / n_steps, "users_per_s": n_eval / t_eval,
+            "n_eval_users": n_eval}
+
+
+def port_leg(D, n_steps, n_warm, eval_users=300):
+    """fallback when no reference copy is staged: oracle/port.py's restatement of the same loop body (torch CPU),
+    incl. the reference's Python rejection sampler on an array-backed data shim"""
     from oracle import port
     U, I, L, d, B = D["U"], D["I"], D["L"], D["d"], D["B"]
     adj = port.bipartite_adjacency(D["tu"], D["ti"], U, I)
@@ -135,13 +218,20 @@ def cpu_train_baseline(D, n_steps, n_warm):
     ue, ie = xavier_tables(U, I, d)
     tr = port.LightGCNTrainer(norm, ue, ie, L, LR, REG)
     rng = np.random.default_rng(1)
-    train_sets = None
+    train_of = {}
+    for u, i in zip(D["tu"].tolist(), D["ti"].tolist()):
+        train_of.setdefault(u, set()).add(i)
 
     def batch(k):
-        sl = slice((k * B) % (D["E"] - B), (k * B) % (D["E"] - B) + B)
-        u, i = D["tu"][sl], D["ti"][sl]
-        j = rng.integers(0, I, B)
-        return u.tolist(), i.tolist(), j.tolist()
+        lo = (k * B) % (D["E"] - B)
+        u, i = D["tu"][lo:lo + B].tolist(), D["ti"][lo:lo + B].tolist()
+        j = []
+        for uu in u:                                   # util/sampler.py:23-29: rejection sampling per triple
+            neg = int(rng.integers(0, I))
+            while neg in train_of[uu]:
+                neg = int(rng.integers(0, I))
+            j.append(neg)
+        return u, i, j
 
     for k in range(n_warm):
         tr.step(*batch(k))
@@ -149,44 +239,52 @@ def cpu_train_baseline(D, n_steps, n_warm):
     for k in range(n_steps):
         tr.step(*batch(n_warm + k))
     dt = time.perf_counter() - t0
-    return n_steps * B / dt, dt / n_steps
-
-
-def cpu_eval_baseline(D, n_users=300):
-    from oracle import port
-    U, I, d = D["U"], D["I"], D["d"]
-    ue, ie = xavier_tables(U, I, d)
-    users = np.unique(D["su"])[:n_users]
+    users = np.unique(D["su"])[:eval_users]
     data = port.ArrayEvalData(U, I, D["tu"], D["ti"], D["su"], D["si"], users)
     port.find_k_largest(TOPK, np.random.rand(I).astype(np.float32))       # numba JIT warm-up
     names = [str(int(u)) for u in users]
-    t0 = time.perf_counter()
+    t1 = time.perf_counter()
     port.full_rank_test(data, ue, ie, TOPK, [TOPK], users=names)
-    return len(names) / (time.perf_counter() - t0)
+    return {"triples_per_s": n_steps * B / dt, "s_per_step": dt / n_steps,
+            "users_per_s": len(names) / (time.perf_counter() - t1), "n_eval_users": len(names)}
+
+
+def cpu_leg(D, name, n_steps, n_warm):
+    """-> (result dict, kind, sample description)"""
+    from oracle import ref_loader
+    cores = host_threads()
+    if ref_loader.available():
+        r = reference_leg(D, name, n_steps, n_warm, cuda=False)
+        kind = "reference"
+        what = ("%d warm-up + %d timed steps of the UNMODIFIED reference's LightGCN.train() loop (oracle/_ref; Python "
+                "rejection sampler + model() + loss + backward + Adam, %d triples per step, torch CPU, %d threads) and its "
+                "test() over %d test users" % (n_warm, n_steps, D["B"], cores, r["n_eval_users"]))
+    else:
+        r = port_leg(D, n_steps, n_warm)
+        kind = "port"
+        what = ("%d warm-up + %d timed steps of oracle/port.py's restatement of LightGCN.train() (sampler included, torch "
+                "CPU, %d threads) and a %d-user full-rank eval" % (n_warm, n_steps, cores, r["n_eval_users"]))
+    return r, kind, what, cores
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation (oracle port; the Python
-    reference cannot travel to the GPU box) on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores (rank 0 alone)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     D = make_data(args.workload, args.alpha)
     cap = max(1, min(args.steps, 40))
     warm = max(1, min(args.warmup, 2))
-    tps, s_per_step = cpu_train_baseline(D, cap, warm)
-    ups = cpu_eval_baseline(D)
-    cores = torch.get_num_threads()
+    r, kind, what, cores = cpu_leg(D, args.workload, cap, warm)
+    tps = r["triples_per_s"]
     line = {
         "impl": "reference", "metric": "LightGCN train triples/s", "value": tps, "unit": "triples/s",
-        "n_gpus": args.gpus, "steps": cap, "warmup": warm, "ms_per_step": s_per_step * 1e3,
+        "n_gpus": args.gpus, "steps": cap, "warmup": warm, "ms_per_step": r["s_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_of(args, D),
-        "cpu_baseline": {"value": tps, "unit": "triples/s", "cores": cores, "kind": "port",
-                         "sample": "%d full-graph training steps of %d triples (oracle/port.py LightGCNTrainer, torch CPU, "
-                                   "%d threads); eval %d users" % (cap, D["B"], cores, 300)},
+        "cpu_baseline": {"value": tps, "unit": "triples/s", "cores": cores, "kind": kind, "sample": what},
         "e2e": {"value": tps, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "eval": {"users_per_s": ups, "unit": "users/s"},
+        "eval": {"users_per_s": r["users_per_s"], "unit": "users/s", "n_users": r["n_eval_users"]},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -445,13 +543,24 @@ def run_ours(args):
         "gpu_launches": K * eng.launches_per_step, "last_loss": loss_last,
     }
     if rank == 0 and not args.no_cpu_baseline:
-        cores = torch.get_num_threads()
-        tps, _ = cpu_train_baseline(D, 8, 2)
-        ups = cpu_eval_baseline(D)
-        line["cpu_baseline"] = {"value": tps, "unit": "triples/s", "cores": cores, "kind": "port",
-                                "eval_users_per_s": ups,
-                                "sample": "2 warm-up + 8 timed full-graph training steps of %d triples and a 300-user "
-                                          "full-rank eval with oracle/port.py (torch CPU, %d threads)" % (B, cores)}
+        r, kind, what, cores = cpu_leg(D, args.workload, 8, 2)
+        line["cpu_baseline"] = {"value": r["triples_per_s"], "unit": "triples/s", "cores": cores, "kind": kind,
+                                "eval_users_per_s": r["users_per_s"], "sample": what}
+        # the honest prior-art bar: the reference's OWN GPU path -- eager PyTorch,
+        # uncoalesced COO torch.sparse.mm (cuSPARSE), Python sampler, per-user GEMV + D2H -- on this same B200
+        from oracle import ref_loader
+        if ref_loader.available() and world == 1:
+            try:
+                g_ = reference_leg(D, args.workload, 20, 3, cuda=True)
+                line["gpu_eager_baseline"] = {
+                    "value": g_["triples_per_s"], "unit": "triples/s", "ms_per_step": g_["s_per_step"] * 1e3,
+                    "eval_users_per_s": g_["users_per_s"], "n_eval_users": g_["n_eval_users"],
+                    "what": "the UNMODIFIED reference (oracle/_ref) on this GPU: LightGCN.train() loop, 3 warm-up + 20 timed "
+                            "steps incl. its Python sampler, and test() over %d users" % g_["n_eval_users"],
+                    "speedup_e2e": e2e["value"] / g_["triples_per_s"],
+                    "speedup_eval_e2e": evald["e2e_users_per_s"] / g_["users_per_s"]}
+            except Exception as ex:          # the baseline must never take the bench line down with it
+                line["gpu_eager_baseline"] = {"unavailable": repr(ex)[:300]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

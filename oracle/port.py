@@ -397,6 +397,111 @@ class LightGCNTrainer:
         return float(loss.item())
 
 
+class _BprTrainerBase:
+    """Shared skeleton of the four train() bodies (recommender/LightGCN.py:46-64, NGCF.py:48-66, SimGCL.py:46-69,
+    XSimGCL.py:56-80): forward, three row gathers, bpr_loss (+ l2_reg_loss(reg, user_emb, pos_item_emb)) (+ cl term),
+    zero_grad, backward, Adam.step (torch defaults, lr = args.lRate) over ``model.parameters()`` in registration
+    order.  Returns python floats like the reference prints them."""
+
+    def _params(self):
+        return [self.user_emb, self.item_emb]
+
+    def _finish(self, loss):
+        self.opt.zero_grad()
+        loss.backward()
+        self.opt.step()
+
+
+class NGCFTrainer(_BprTrainerBase):
+    """recommender/NGCF.py:31-66 with NGCF_Encoder.forward (:197-212).  ``w1`` / ``w2``: lists of the d x d layer
+    weights (xavier_uniform, drawn w1_k then w2_k per layer after the two embedding tables, :176-183).  Adam is
+    element-wise, so the registration order of ``model.parameters()`` does not enter the result."""
+
+    def __init__(self, norm_adj, user_emb, item_emb, w1, w2, lr, reg):
+        self.adj = to_torch_coo(norm_adj)
+        self.user_emb = torch.nn.Parameter(user_emb.clone())
+        self.item_emb = torch.nn.Parameter(item_emb.clone())
+        self.w1 = [torch.nn.Parameter(w.clone()) for w in w1]
+        self.w2 = [torch.nn.Parameter(w.clone()) for w in w2]
+        self.reg = reg
+        params = [self.user_emb, self.item_emb]
+        for a, b in zip(self.w1, self.w2):
+            params += [a, b]
+        self.opt = torch.optim.Adam(params, lr=lr)
+
+    def forward(self):
+        return ngcf_forward(self.adj, self.user_emb, self.item_emb, self.w1, self.w2)
+
+    def step(self, u_idx, i_idx, j_idx):
+        ru, ri = self.forward()
+        ue, pe, ne = ru[u_idx], ri[i_idx], ri[j_idx]
+        loss = bpr_loss(ue, pe, ne) + l2_reg_loss(self.reg, ue, pe)
+        self._finish(loss)
+        return float(loss.item())
+
+
+def unique_ids_f32(ids):
+    """``torch.unique(torch.Tensor(ids).type(torch.long))`` -- recommender/SimGCL.py:213-214, XSimGCL.py:40-41: the ids
+    pass through float32."""
+    return torch.unique(torch.Tensor(ids).type(torch.long))
+
+
+class SimGCLTrainer(_BprTrainerBase):
+    """recommender/SimGCL.py:36-69 with SimGCL_Encoder.forward / cal_cl_loss (:198-219): one clean pass for the rec
+    loss, two perturbed passes for the contrastive views, InfoNCE(tau = 0.2) over the unique batch users and unique
+    positive items.  ``noise()`` returns the next U[0,1) tensor [N, d] (the reference calls torch.rand_like once per
+    perturbed layer, pass 1 layers 1..L then pass 2 layers 1..L)."""
+
+    def __init__(self, norm_adj, user_emb, item_emb, n_layers, eps, cl_rate, lr, reg, noise, tau=0.2):
+        self.adj = to_torch_coo(norm_adj)
+        self.user_emb = torch.nn.Parameter(user_emb.clone())
+        self.item_emb = torch.nn.Parameter(item_emb.clone())
+        self.n_layers, self.eps, self.cl_rate, self.reg, self.tau = n_layers, eps, cl_rate, reg, tau
+        self.noise = noise
+        self.opt = torch.optim.Adam([self.user_emb, self.item_emb], lr=lr)
+
+    def forward(self, perturbed=False):
+        noises = [self.noise() for _ in range(self.n_layers)] if perturbed else None
+        return simgcl_forward(self.adj, self.user_emb, self.item_emb, self.n_layers, self.eps, noises)
+
+    def step(self, u_idx, i_idx, j_idx):
+        ru, ri = self.forward()
+        ue, pe, ne = ru[u_idx], ri[i_idx], ri[j_idx]
+        rec_loss = bpr_loss(ue, pe, ne)
+        uu, ii = unique_ids_f32(u_idx), unique_ids_f32(i_idx)
+        u1, i1 = self.forward(True)
+        u2, i2 = self.forward(True)
+        cl_loss = self.cl_rate * (infonce(u1[uu], u2[uu], self.tau) + infonce(i1[ii], i2[ii], self.tau))
+        self._finish(rec_loss + l2_reg_loss(self.reg, ue, pe) + cl_loss)
+        return float(rec_loss.item()), float(cl_loss.item())
+
+
+class XSimGCLTrainer(_BprTrainerBase):
+    """recommender/XSimGCL.py:46-80 with XSimGCL_Encoder.forward (:205-223) and cal_cl_loss (:39-44): ONE perturbed
+    pass gives the rec view and the layer_cl view; InfoNCE(tau = 0.1)."""
+
+    def __init__(self, norm_adj, user_emb, item_emb, n_layers, eps, cl_rate, layer_cl, lr, reg, noise, tau=0.1):
+        self.adj = to_torch_coo(norm_adj)
+        self.user_emb = torch.nn.Parameter(user_emb.clone())
+        self.item_emb = torch.nn.Parameter(item_emb.clone())
+        self.n_layers, self.eps, self.cl_rate, self.layer_cl = n_layers, eps, cl_rate, layer_cl
+        self.reg, self.tau, self.noise = reg, tau, noise
+        self.opt = torch.optim.Adam([self.user_emb, self.item_emb], lr=lr)
+
+    def forward(self, perturbed=False):
+        noises = [self.noise() for _ in range(self.n_layers)] if perturbed else None
+        return xsimgcl_forward(self.adj, self.user_emb, self.item_emb, self.n_layers, self.eps, self.layer_cl, noises)
+
+    def step(self, u_idx, i_idx, j_idx):
+        ru, ri, cu, ci = self.forward(True)
+        ue, pe, ne = ru[u_idx], ri[i_idx], ri[j_idx]
+        rec_loss = bpr_loss(ue, pe, ne)
+        uu, ii = unique_ids_f32(u_idx), unique_ids_f32(i_idx)
+        cl_loss = self.cl_rate * (infonce(ru[uu], cu[uu], self.tau) + infonce(ri[ii], ci[ii], self.tau))
+        self._finish(rec_loss + l2_reg_loss(self.reg, ue, pe) + cl_loss)
+        return float(rec_loss.item()), float(cl_loss.item())
+
+
 def adjacency_value_grad(norm_adj, user_emb, item_emb, n_layers, loss_fn):
     """attack/White/PGA.py:97-117 -- d loss / d (values of sparse_norm_adj),
     restricted to the stored pattern (torch returns a sparse COO gradient with

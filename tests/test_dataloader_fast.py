@@ -120,3 +120,16 @@ def test_device_mirrors_from_pristine_edges_equal_the_dict_walk():
     assert data.pristine_edges() is None
     ts = DeviceTrainSet(data, "cpu")
     assert ts.n_edges == len(data.training_data) and int(ts.rej_rowptr[-1]) == int(slow_ts.rej_rowptr[-1])   # fake user rejects nothing
+
+
+def test_long_mantissa_weights_parse_like_float(tmp_path):
+    """pandas' default fast float parser is not bit-identical to the reference's ``float(weight)``
+    (util/FileIO.py:28); the loader asks for the round-trip parser."""
+    import random as _r
+    from arlib_b200.util.FileIO import FileIO
+    rng = _r.Random(5)
+    weights = [repr(rng.random() * 10 ** rng.randint(-8, 8)) for _ in range(20000)] + ["1", "0.1", "1e-7", "3.0000000000000004"]
+    path = tmp_path / "w.txt"
+    path.write_text("".join("u%d i%d %s\n" % (k % 97, k % 89, w) for k, w in enumerate(weights)))
+    rows = FileIO.load_data_set(str(path))
+    assert [r[2] for r in rows] == [float(w) for w in weights]

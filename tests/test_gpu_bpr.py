@@ -158,3 +158,27 @@ def test_adam_matches_torch_optim():
             ops.increment(step_dev)
         torch.testing.assert_close(p.cpu(), p_ref.detach(), rtol=2e-6, atol=1e-7)
     assert int(step_dev) == 5
+
+
+@pytest.mark.parametrize("d,nb", [(64, 2048), (32, 77), (128, 1), (64, 5461)])
+def test_bpr_l2_fused_autograd_op_matches_the_reference_expressions(d, nb):
+    """util/loss.py:5-9,25-29 behind ONE autograd function (the loss line of the reference-shaped loops,
+    recommender/LightGCN.py:51-54): value, both table gradients, and the upstream gradient scale."""
+    from arlib_b200.util.loss import bpr_l2_fused
+    U, I, reg = 300, 500, 1e-3
+    gen = torch.Generator().manual_seed(nb)
+    table = ((torch.rand(U + I, d, generator=gen) - 0.5) * 0.6).to("cuda:0")
+    u = torch.randint(0, U, (nb,), generator=gen)
+    i = torch.randint(0, I, (nb,), generator=gen)
+    j = torch.randint(0, I, (nb,), generator=gen)
+    ref_t = table.double().cpu().requires_grad_(True)
+    ue, pe, ne = ref_t[:U][u], ref_t[U:][i], ref_t[U:][j]
+    ref = port.bpr_loss(ue, pe, ne) + port.l2_reg_loss(reg, ue, pe)
+    (ref * 1.7).backward()
+    t = table.clone().requires_grad_(True)
+    got, parts = bpr_l2_fused(t[:U], t[U:], u.tolist(), i.to("cuda:0"), j.tolist(), reg, return_parts=True)
+    (got * 1.7).backward()
+    assert abs(float(got) - float(ref)) <= 2e-6 * abs(float(ref))
+    assert abs(float(parts[1]) - float(port.bpr_loss(ue, pe, ne))) <= 2e-6 * abs(float(ref))
+    err = float((t.grad.double().cpu() - ref_t.grad).abs().max() / ref_t.grad.abs().max())
+    assert err < 2e-6, err

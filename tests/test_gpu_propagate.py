@@ -238,3 +238,28 @@ def test_spmm_row_and_column_masks(d):
     out = out.cpu()
     torch.testing.assert_close(out[torch.from_numpy(live)], ref_full[torch.from_numpy(live)], rtol=1e-5, atol=1e-6)
     assert bool((out[~torch.from_numpy(live)] == 7.0).all())
+
+
+def test_ngcf_adjacency_gradient_matches_sparse_mm_autograd():
+    """with NGCF as the victim, attack/White/PGA.py:98,117 sets
+    ``model.sparse_norm_adj.requires_grad = True`` and calls ``torch.autograd.grad(Loss, model.sparse_norm_adj)``; the
+    reference gets that through torch.sparse.mm (recommender/NGCF.py:197-212, two products per layer)."""
+    from arlib_b200.encoder import NGCF_Encoder
+    U, I, d = 100, 140, 64
+    u, i = _rand_graph(U, I, 2000, 7)
+    data = _Data(U, I, u, i)
+    torch.manual_seed(2)
+    enc = NGCF_Encoder(data, d, 2)
+    ue = enc.embedding_dict['user_emb'].detach().cpu().clone().requires_grad_(True)
+    ie = enc.embedding_dict['item_emb'].detach().cpu().clone().requires_grad_(True)
+    w1 = [enc.W['w1_%d' % k].detach().cpu().clone() for k in range(2)]
+    w2 = [enc.W['w2_%d' % k].detach().cpu().clone() for k in range(2)]
+    adj = port.to_torch_coo(data.norm_adj).coalesce().requires_grad_(True)
+    gr = torch.autograd.grad(_loss(*port.ngcf_forward(adj, ue, ie, w1, w2)), adj)[0].coalesce()
+    enc.sparse_norm_adj.requires_grad = True
+    ga = torch.autograd.grad(_loss(*enc()), enc.sparse_norm_adj)[0].coalesce()
+    assert torch.equal(ga.indices().cpu(), gr.indices())
+    torch.testing.assert_close(ga.values().cpu(), gr.values(), rtol=1e-3, atol=1e-4)
+    # .backward() fills .grad like LightGCN's (recommender/NGCF.py:41-43,59-60: Matgrad += sparse_norm_adj.grad)
+    _loss(*enc()).backward()
+    torch.testing.assert_close(enc.sparse_norm_adj.grad.coalesce().values().cpu(), gr.values(), rtol=1e-3, atol=1e-4)
