@@ -41,6 +41,7 @@ class SpmmArgs(ctypes.Structure):
         ("sched", P),
         ("d", I32),
         ("flags", I32),
+        ("mask_bits", I32),
     ]
 
 

@@ -275,14 +275,42 @@ __global__ void __launch_bounds__(256) bpr_forward_kernel(const float4* __restri
 
 // ===================================================== d-sharded forward (multi-GPU)
 // Every rank holds a column slice [N, d/P] of the tables.  bpr_partial computes, per triple, the slice's
-// share of the two dot products and of the two squared norms and stores the float4 into slot `rank` of the
-// exchange buffer on EVERY rank (plain NVLink P2P stores); after a barrier bpr_finish sums the P shares in
-// rank order -- identical bits on all ranks -- and does what bpr_forward does from there on.  The exchange
-// buffer is double-buffered on the parity of the device step counter, so one barrier per step suffices.
+// share of the two dot products and of the two squared norms and stores it into slot `rank` of the exchange
+// buffer on EVERY rank (NVLink P2P stores); bpr_finish sums the P shares in rank order -- identical bits on all
+// ranks -- and does what bpr_forward does from there on.
+//
+// The exchange carries its own synchronisation (the "LL" idea of collective libraries): every value travels as ONE
+// naturally aligned 64-bit word {stamp : 32 | float bits : 32}, stamp = step + 1.  A 64-bit scalar store is
+// single-copy atomic, so a reader that sees the stamp of the current step has the value that was written with it:
+// no fence, no flag, NO BARRIER LAUNCH (the torch symmetric-memory barrier this replaces cost 41.5 us per step and
+// was the largest single item of the 8-GPU step, profiles/r1_summary.md section 4).  bpr_finish spins on the words
+// it needs (ld.relaxed.sys, L1 bypassed) -- it waits exactly as long as the slowest rank is behind, per triple.
+// The buffer is double-buffered on the parity of the step: a writer can reach step s + 2 (the next use of the same
+// half) only after its own finish(s + 1), which needed every reader's partial(s + 1), which that reader launched
+// after its finish(s) had read the half.
 struct XchgPeers {
   int n;
-  float4* p[AGCF_MAX_PEERS];
+  unsigned long long* p[AGCF_MAX_PEERS];
 };
+
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long ll_pack(float v, uint32_t stamp) {
+  return ((unsigned long long)stamp << 32) | (unsigned long long)__float_as_uint(v);
+}
+// a rank that never shows up must not hang the GPU: after this long the reader gives up and poisons the loss
+constexpr unsigned long long kXchgTimeoutNs = 4000000000ull;
 
 template <int D>
 __global__ void __launch_bounds__(256) bpr_partial_kernel(const float4* __restrict__ F, const int32_t* __restrict__ u,
@@ -312,27 +340,46 @@ __global__ void __launch_bounds__(256) bpr_partial_kernel(const float4* __restri
   dneg = group_sum<C::LPR>(dneg);
   su = group_sum<C::LPR>(su);
   si = group_sum<C::LPR>(si);
-  if (valid && gl == 0) {
-    const int parity = step_dev != nullptr ? (__ldg(step_dev) & 1) : 0;
-    const size_t off = ((size_t)parity * AGCF_MAX_PEERS + rank) * cap + t;
-    const float4 out = make_float4(dpos, dneg, su, si);
-    for (int q = 0; q < x.n; ++q) x.p[q][off] = out;
+  if (valid && gl < 4) {                                     // LPR >= 2 everywhere: 2 or 4 lanes share the stores
+    const uint32_t step = step_dev != nullptr ? (uint32_t)__ldg(step_dev) : 0u;
+    const size_t off = ((((size_t)(step & 1u) * AGCF_MAX_PEERS + rank) * cap + t) << 2);
+    constexpr int STRIDE = C::LPR < 4 ? C::LPR : 4;
+#pragma unroll
+    for (int k = 0; k < 4 / STRIDE; ++k) {
+      const int c = gl + k * STRIDE;
+      const unsigned long long w = ll_pack(c == 0 ? dpos : (c == 1 ? dneg : (c == 2 ? su : si)), step + 1u);
+#pragma unroll
+      for (int q = 0; q < AGCF_MAX_PEERS; ++q)
+        if (q < x.n) st_relaxed_sys_u64(x.p[q] + off + c, w);
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) bpr_finish_kernel(const float4* __restrict__ xchg, int world, int cap, int nb,
+__global__ void __launch_bounds__(256) bpr_finish_kernel(const unsigned long long* __restrict__ xchg, int world, int cap, int nb,
                                                          float reg, const int32_t* __restrict__ step_dev,
                                                          float* __restrict__ out4, float* __restrict__ coef,
                                                          BprWs* __restrict__ ws) {
   __shared__ float red[3][256];
   const int t = blockIdx.x * 256 + threadIdx.x;
-  const int parity = step_dev != nullptr ? (__ldg(step_dev) & 1) : 0;
+  const uint32_t step = step_dev != nullptr ? (uint32_t)__ldg(step_dev) : 0u;
   float l = 0.f, su = 0.f, si = 0.f;
   if (t < nb) {
     float dpos = 0.f, dneg = 0.f;
+    const unsigned long long t_start = global_ns();
     for (int r = 0; r < world; ++r) {                       // rank order: the same bits on every rank
-      const float4 v = xchg[((size_t)parity * AGCF_MAX_PEERS + r) * cap + t];
-      dpos += v.x; dneg += v.y; su += v.z; si += v.w;
+      const unsigned long long* src = xchg + ((((size_t)(step & 1u) * AGCF_MAX_PEERS + r) * cap + t) << 2);
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        unsigned long long w = ld_relaxed_sys_u64(src + c);
+        while ((uint32_t)(w >> 32) != step + 1u) {          // rank r's share of this triple has not landed yet
+          if (global_ns() - t_start > kXchgTimeoutNs) { w = 0x7fc00000ull; break; }      // give up: NaN
+          __nanosleep(40);
+          w = ld_relaxed_sys_u64(src + c);
+        }
+        v[c] = __uint_as_float((uint32_t)w);
+      }
+      dpos += v[0]; dneg += v[1]; su += v[2]; si += v[3];
     }
     const float x = dpos - dneg;
     const float s = 1.f / (1.f + expf(-x));
@@ -636,7 +683,7 @@ extern "C" int agcf_bpr_forward(const float* F, const int32_t* u, const int32_t*
 
 extern "C" int64_t agcf_bpr_xchg_bytes(int32_t cap) {
   if (cap < 0) return AGCF_EINVAL;
-  return 2ll * AGCF_MAX_PEERS * (long long)cap * 16;
+  return 2ll * AGCF_MAX_PEERS * (long long)cap * 32;       // 2 halves x ranks x cap x 4 words {stamp | value}
 }
 
 extern "C" int agcf_bpr_partial(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
@@ -650,7 +697,7 @@ extern "C" int agcf_bpr_partial(const float* F, const int32_t* u, const int32_t*
   XchgPeers x;
   x.n = world;
   for (int q = 0; q < AGCF_MAX_PEERS; ++q) {
-    x.p[q] = q < world ? reinterpret_cast<float4*>(xchg_all_host[q]) : nullptr;
+    x.p[q] = q < world ? reinterpret_cast<unsigned long long*>(xchg_all_host[q]) : nullptr;
     if (q < world && (x.p[q] == nullptr || !aligned16(x.p[q]))) return AGCF_EINVAL;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -678,7 +725,7 @@ extern "C" int agcf_bpr_finish(const void* xchg, int32_t world, int32_t cap, int
   if (!xchg || !out4 || !coef || !ws || nb <= 0 || nb > cap || world < 1 || world > AGCF_MAX_PEERS) return AGCF_EINVAL;
   if (!aligned16(xchg) || !aligned16(ws)) return AGCF_EINVAL;
   const unsigned blocks = (unsigned)((nb + 255) / 256);
-  bpr_finish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(xchg), world, cap, nb, reg,
+  bpr_finish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(xchg), world, cap, nb, reg,
                                                               step_dev, out4, coef, reinterpret_cast<BprWs*>(ws));
   AGCF_LAUNCH_OK();
   return AGCF_OK;

@@ -8,7 +8,7 @@ thread_local const char* g_last_cuda_file = "";
 thread_local int g_last_cuda_line = 0;
 }
 
-extern "C" int agcf_abi_version(void) { return 3; }
+extern "C" int agcf_abi_version(void) { return 4; }
 
 extern "C" const char* agcf_strerror(int code) {
   switch (code) {

@@ -64,6 +64,7 @@ struct SpmmParams {
   uint32_t aux_stream[2];
   const uint32_t* row_mask;   // nullable bitmap over rows: only rows with their bit set are computed / written
   const uint32_t* col_mask;   // nullable bitmap over columns: rows of X outside it are known to be zero (skipped)
+  int mask_bits;              // bits in the bitmaps (0 = unknown)
   // fused all-gather: the same rows are also stored into the peer GPUs' copies of Y / acc_out
   // (NVLink P2P stores straight from the epilogue; peers see them after the next barrier)
   int n_peers;
@@ -398,6 +399,45 @@ __device__ __forceinline__ void spmm_accumulate_masked(const SpmmParams& p, int 
   }
 }
 
+// the end of a work item, shared by the two accumulation schemes below: rows cut into several segments combine
+// through the partial-sum scratch (every segment stores its partial sum, the one that arrives last -- a ticket per
+// row -- adds them in segment order: deterministic, no floating-point atomics), then the fused epilogue
+template <typename C, bool NOISE>
+__device__ __forceinline__ void spmm_finish_item(const SpmmParams& p, bool valid, int row, int k, int nseg, long long slot,
+                                                 float4 (&acc)[C::VPL], int gl, const float4* pre) {
+  const bool multi = valid && nseg > 1;
+  bool do_epilogue = valid;
+  if (__any_sync(0xffffffffu, multi)) {
+    int pb = 0;
+    if (multi) {
+      pb = __ldg(p.vpart + slot);
+      float4* mine = p.partial + ((size_t)pb + k) * C::V4;
+#pragma unroll
+      for (int v = 0; v < C::VPL; ++v) mine[v * C::LPR + gl] = acc[v];
+      __threadfence();                                     // partial visible before the ticket is taken
+    }
+    __syncwarp();
+    int old = 0;
+    if (multi && gl == 0) old = atomicAdd(p.tickets + pb, 1);
+    old = __shfl_sync(0xffffffffu, old, 0, C::LPR);
+    if (multi) {
+      do_epilogue = old == nseg - 1;                       // the last segment to arrive finishes the row
+      if (do_epilogue) {
+        __threadfence();
+#pragma unroll
+        for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kk = 0; kk < nseg; ++kk) {                // segment order: deterministic
+          const float4* part = p.partial + ((size_t)pb + kk) * C::V4;
+#pragma unroll
+          for (int v = 0; v < C::VPL; ++v) acc[v] = add4(acc[v], __ldcg(part + v * C::LPR + gl));
+        }
+        if (gl == 0) p.tickets[pb] = 0;                    // ready for the next launch
+      }
+    }
+  }
+  spmm_epilogue<C, NOISE>(p, row, do_epilogue, acc, gl, pre);
+}
+
 // one block of RPB work items (one lane group each)
 template <int D, int LPR, bool NOISE, bool CMASK>
 __device__ __forceinline__ void spmm_block(const SpmmParams& p, const int n_v, const int blk) {
@@ -439,38 +479,157 @@ __device__ __forceinline__ void spmm_block(const SpmmParams& p, const int n_v, c
     spmm_accumulate_chunks<C, true>(p, s, len, 0, C::CH, iters, gl, acc);
   }
   AGCF_TRACE_AFTER(2, __float_as_int(acc[0].x));
-  // ---- rows cut into several segments: combine through the partial-sum scratch -----------------
-  const bool multi = valid && nseg > 1;
-  bool do_epilogue = valid;
-  if (__any_sync(0xffffffffu, multi)) {
-    int pb = 0;
-    if (multi) {
-      pb = __ldg(p.vpart + slot);
-      float4* mine = p.partial + ((size_t)pb + k) * C::V4;
+  spmm_finish_item<C, NOISE>(p, valid, row, k, nseg, slot, acc, gl, (CMASK && p.addend != nullptr) ? pre : nullptr);
+}
+
+// ------------------------------------------------------------------ narrow rows (column-sharded tables)
+// d = 8 / 16 column slices (the d-sharded multi-GPU layout): a row is 32 / 64 bytes, LPR = 2 / 4 lanes.  With one work
+// item per lane group (spmm_block) the 16 / 8 groups of a warp walk 16 / 8 DIFFERENT items, so every index load of a warp
+// touches 16 different cache lines and is replayed as 16 L1 wavefronts, and every (col, val) pair is broadcast by two
+// shuffles inside a 2-lane group -- the LSU data pipe, which has to serve one wavefront per gathered row anyway (a 32-byte
+// row is one sector of its own line), carried ~4 wavefronts per non-zero; that, not bytes, bounded the kernel
+// (26.5 us per launch at d = 8 for 82 MB of L2 traffic, profiles/r1_summary.md section 3).
+// Here the WARP walks its G = 32 / LPR items one after the other: the item's indices are read with coalesced loads (lane l
+// holds entries l and l + 32 of a 64-entry block), every gather instruction fetches G different entries of the SAME item
+// (one per lane group, two shuffles for all of them), and the G partial sums are combined by a halving butterfly that ends
+// with one value per lane, transposed so that lane group i receives item i's row -- from there on the groups own one item
+// each, exactly like spmm_block (segment combine, epilogue).  Per non-zero: 1 gather wavefront + ~0.4 others.
+// Summation order: entries j * G + grp of a block are summed per group in j order, groups by the fixed butterfly:
+// deterministic, run-to-run identical, not the entry order of spmm_block (parity bars are tolerances).
+template <typename C>
+__device__ __forceinline__ float4 coop_reduce_transpose(float4 acc, int lane, int gl) {
+  constexpr unsigned FULL = 0xffffffffu;
+  // halving over lane bit 4 (keep x,y or z,w) and bit 3 (keep one of the two): 3 shuffles, 4 -> 1 value per lane
+  const bool up = (lane & 16) != 0;
+  const float r0 = __shfl_xor_sync(FULL, up ? acc.x : acc.z, 16);
+  const float r1 = __shfl_xor_sync(FULL, up ? acc.y : acc.w, 16);
+  const float a = (up ? acc.z : acc.x) + r0;
+  const float b = (up ? acc.w : acc.y) + r1;
+  const bool up2 = (lane & 8) != 0;
+  const float r2 = __shfl_xor_sync(FULL, up2 ? a : b, 8);
+  float t = (up2 ? b : a) + r2;                      // column gl * 4 + (bit4 ? 2 : 0) + (bit3 ? 1 : 0)
 #pragma unroll
-      for (int v = 0; v < C::VPL; ++v) mine[v * C::LPR + gl] = acc[v];
-      __threadfence();                                     // partial visible before the ticket is taken
+  for (int m = 4; m >= C::LPR; m >>= 1) t += __shfl_xor_sync(FULL, t, m);      // the remaining group bits
+  // every lane fetches the float4 of ITS gl (lanes gl | 8 c0 | 16 c1 hold column 4 gl + c0 + 2 c1)
+  float4 o;
+  o.x = __shfl_sync(FULL, t, gl);
+  o.y = __shfl_sync(FULL, t, gl | 8);
+  o.z = __shfl_sync(FULL, t, gl | 16);
+  o.w = __shfl_sync(FULL, t, gl | 24);
+  return o;
+}
+
+template <int D, int LPR, bool NOISE, bool CMASK>
+__device__ __forceinline__ void spmm_block_coop(const SpmmParams& p, const int n_v, const int blk,
+                                                const uint32_t* __restrict__ cmask, int2* __restrict__ stage) {
+  using C = RowCfg<D, LPR>;
+  static_assert(C::VPL == 1 && LPR <= 4, "cooperative scheme: rows of at most 4 lanes");
+  constexpr int G = C::RPW;                                // lane groups per warp = items per warp = entries per gather
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gl = lane & (C::LPR - 1);
+  const int grp = lane / C::LPR;
+  const long long slot = ((long long)blk * (blockDim.x >> 5) + warp) * G + grp;
+  bool valid = slot < n_v;
+  int4 vr = make_int4(0, 0, 0, 1 << 16);
+  if (valid) vr = __ldg(p.vrows + slot);
+  const int s_mine = vr.x, row = vr.z, k = vr.w & 0xffff, nseg = vr.w >> 16;
+  int len_mine = vr.y;
+  if (valid && p.row_mask != nullptr && !bit_set(p.row_mask, row)) { valid = false; len_mine = 0; }
+  if (!valid) len_mine = 0;
+  float4 pre[1];
+  if constexpr (CMASK) {
+    const bool has_add = p.addend != nullptr && valid;
+    pre[0] = has_add ? ld_stream_f4(p.addend + (size_t)row * C::V4 + gl) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
+  // entries [base, base + 64) of an item: lane l holds entries base + l and base + l + 32 (coalesced, streamed)
+  auto load_block = [&](int s, int len, int base, int& c0, float& v0, int& c1, float& v1) {
+    c0 = -1; c1 = -1; v0 = 0.f; v1 = 0.f;
+    const int e0 = base + lane, e1 = base + lane + 32;
+    if (e0 < len) { c0 = ld_stream_i32(p.col + s + e0); v0 = ld_stream_f32(p.val + s + e0); }
+    if (e1 < len) { c1 = ld_stream_i32(p.col + s + e1); v1 = ld_stream_f32(p.val + s + e1); }
+  };
+  int s_i = __shfl_sync(FULL, s_mine, 0), len_i = __shfl_sync(FULL, len_mine, 0);
+  int c0, c1; float v0, v1;
+  load_block(s_i, len_i, 0, c0, v0, c1, v1);
+  for (int i = 0; i < G; ++i) {
+    int s_n = 0, len_n = 0, nc0 = -1, nc1 = -1; float nv0 = 0.f, nv1 = 0.f;
+    if (i + 1 < G) {                                       // next item's first block: in flight during these gathers
+      s_n = __shfl_sync(FULL, s_mine, (i + 1) * C::LPR);
+      len_n = __shfl_sync(FULL, len_mine, (i + 1) * C::LPR);
+      load_block(s_n, len_n, 0, nc0, nv0, nc1, nv1);
     }
-    __syncwarp();
-    int old = 0;
-    if (multi && gl == 0) old = atomicAdd(p.tickets + pb, 1);
-    old = __shfl_sync(0xffffffffu, old, 0, C::LPR);
-    if (multi) {
-      do_epilogue = old == nseg - 1;                       // the last segment to arrive finishes the row
-      if (do_epilogue) {
-        __threadfence();
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = 0; base < len_i; base += 64) {         // warp-uniform
+      if (base > 0) load_block(s_i, len_i, base, c0, v0, c1, v1);
+      int n_here = len_i - base < 64 ? len_i - base : 64;
+      if constexpr (CMASK) {
+        // only entries whose column carries a non-zero row of X are gathered (~13 % at the benchmark shape): compact
+        // them through a 64-slot staging row of this warp, in entry order
+        const bool l0 = c0 >= 0 && ((cmask[c0 >> 5] >> (c0 & 31)) & 1u);
+        const bool l1 = c1 >= 0 && ((cmask[c1 >> 5] >> (c1 & 31)) & 1u);
+        const unsigned b0 = __ballot_sync(FULL, l0), b1 = __ballot_sync(FULL, l1);
+        const unsigned lt = (1u << lane) - 1u;
+        __syncwarp();
+        if (l0) stage[__popc(b0 & lt)] = make_int2(c0, __float_as_int(v0));
+        if (l1) stage[__popc(b0) + __popc(b1 & lt)] = make_int2(c1, __float_as_int(v1));
+        __syncwarp();
+        n_here = __popc(b0) + __popc(b1);
 #pragma unroll
-        for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int kk = 0; kk < nseg; ++kk) {                // segment order: deterministic
-          const float4* part = p.partial + ((size_t)pb + kk) * C::V4;
-#pragma unroll
-          for (int v = 0; v < C::VPL; ++v) acc[v] = add4(acc[v], __ldcg(part + v * C::LPR + gl));
+        for (int j = 0; j < 64 / G; ++j) {
+          if (j * G >= n_here) break;
+          const int e = j * G + grp;
+          if (e < n_here) {
+            const int2 cv = stage[e];
+            fma4_packed(acc, __int_as_float(cv.y), ld_gather_f4(p.X + (size_t)cv.x * C::V4 + gl));
+          }
         }
-        if (gl == 0) p.tickets[pb] = 0;                    // ready for the next launch
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64 / G; ++j) {
+          if (j * G >= n_here) break;                      // warp-uniform
+          const int e = j * G + grp;                       // this group's entry of the step
+          const int cc = __shfl_sync(FULL, (j * G) < 32 ? c0 : c1, e & 31);
+          const float vv = __shfl_sync(FULL, (j * G) < 32 ? v0 : v1, e & 31);
+          if (cc >= 0) fma4_packed(acc, vv, ld_gather_f4(p.X + (size_t)cc * C::V4 + gl));
+        }
       }
     }
+    if (len_i > 0) {                                       // warp-uniform
+      const float4 o = coop_reduce_transpose<C>(acc, lane, gl);
+      if (grp == i) res = o;
+    }
+    s_i = s_n; len_i = len_n; c0 = nc0; c1 = nc1; v0 = nv0; v1 = nv1;
   }
-  spmm_epilogue<C, NOISE>(p, row, do_epilogue, acc, gl, (CMASK && p.addend != nullptr) ? pre : nullptr);
+  float4 accv[1] = {res};
+  spmm_finish_item<C, NOISE>(p, valid, row, k, nseg, slot, accv, gl, (CMASK && p.addend != nullptr) ? pre : nullptr);
+}
+
+// the column bitmap of the first backward layer lives in shared memory while it fits (N <= 32 * kCoopMaskWords nodes)
+constexpr int kCoopMaskWords = 8192;
+
+template <int D, int LPR, int MINB, bool NOISE, bool CMASK>
+__global__ void __launch_bounds__(256, MINB) spmm_coop_kernel(const SpmmParams p, int mask_words) {
+  extern __shared__ __align__(16) unsigned char coop_smem[];
+  int n_v = p.n_v;
+  if (p.n_v_dev != nullptr) {
+    const int n_dev = __ldg(p.n_v_dev);
+    n_v = n_dev < n_v ? n_dev : n_v;
+  }
+  const uint32_t* cmask = p.col_mask;
+  int2* stage = nullptr;
+  if constexpr (CMASK) {
+    stage = reinterpret_cast<int2*>(coop_smem) + (threadIdx.x >> 5) * 64;
+    if (mask_words > 0) {                                  // bitmap copy: one coalesced pass per CTA, then LDS lookups
+      uint32_t* sm = reinterpret_cast<uint32_t*>(coop_smem + 8 * 64 * sizeof(int2));
+      for (int w = threadIdx.x; w < mask_words; w += 256) sm[w] = __ldg(p.col_mask + w);
+      __syncthreads();
+      cmask = sm;
+    }
+  }
+  spmm_block_coop<D, LPR, NOISE, CMASK>(p, n_v, (int)blockIdx.x, cmask, stage);
 }
 
 // Grid: one CTA per block of RPB items (sched == nullptr), or PERSISTENT CTAs (148 x MINB of them) that take their
@@ -539,6 +698,27 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   if (blocks <= 0) return AGCF_OK;
   if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
   const bool cmask = p.col_mask != nullptr && p.noise == nullptr && !p.noise_main && p.aux_Y[0] == nullptr && p.aux_Y[1] == nullptr;
+  if constexpr (D <= 16) {
+    // narrow column slices: the warp-cooperative scheme (AGCF_SPMM_COOP=0 keeps the lane-group kernel for A/B runs)
+    static const bool coop = [] { const char* e = getenv("AGCF_SPMM_COOP"); return e == nullptr || atoi(e) != 0; }();
+    if (coop && p.sched == nullptr && (p.col_mask == nullptr || cmask)) {
+      const bool noise = p.noise != nullptr || p.noise_main || p.aux_Y[0] != nullptr || p.aux_Y[1] != nullptr;
+      if (cmask) {
+        const int words = (p.mask_bits + 31) / 32;
+        const int mw = (p.mask_bits > 0 && words <= kCoopMaskWords) ? words : 0;
+        const size_t smem = 8 * 64 * sizeof(int2) + (size_t)mw * 4;
+        auto kern = spmm_coop_kernel<D, LPR, AGCF_SPMM_MINB(D), false, true>;
+        if (smem > 48 * 1024) AGCF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)blocks, C::THREADS, smem, st>>>(p, mw);
+      } else if (noise) {
+        spmm_coop_kernel<D, LPR, AGCF_SPMM_MINB(D), true, false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p, 0);
+      } else {
+        spmm_coop_kernel<D, LPR, AGCF_SPMM_MINB(D), false, false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p, 0);
+      }
+      AGCF_LAUNCH_OK();
+      return AGCF_OK;
+    }
+  }
   if (p.sched != nullptr) {                                  // persistent: every CTA resident at once
     const long long resident = (long long)kSMs * (cmask ? AGCF_SPMM_CM_MINB(D) : AGCF_SPMM_MINB(D));
     blocks = blocks < resident ? blocks : resident;
@@ -759,7 +939,7 @@ extern "C" int agcf_spmm_csr_f32_ex(const agcf_spmm_args* a, agcf_stream_t strea
     if (!aligned16(a->aux_Y[q]) || !aligned16(a->aux_noise[q]) || (a->aux_Y[q] != nullptr && a->aux_Y[q] == a->X)) return AGCF_EINVAL;
     if (a->aux_Y[q] != nullptr && a->aux_noise[q] == nullptr && a->noise_seed == 0ull) return AGCF_EINVAL;
   }
-  p.row_mask = a->row_mask; p.col_mask = a->col_mask;
+  p.row_mask = a->row_mask; p.col_mask = a->col_mask; p.mask_bits = a->mask_bits > 0 ? a->mask_bits : 0;
   p.mc_Y = a->Y != nullptr ? reinterpret_cast<float4*>(a->mc_Y) : nullptr;
   p.mc_acc = a->acc_out != nullptr ? reinterpret_cast<float4*>(a->mc_acc) : nullptr;
   p.n_peers = a->n_peers;

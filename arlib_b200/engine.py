@@ -94,8 +94,9 @@ class LightGCNEngine:
                   epilogue (P2P stores) and closed by a barrier: 2L + 1 exchanges per step;
       "dshard" -- the graph is replicated and every table is COLUMN-sharded (rank r owns columns
                   [r*d/P, (r+1)*d/P)): propagation, backward and Adam need no communication at all, the
-                  only exchange of a step is 16 bytes per triple per peer (the partial scores) and one
-                  barrier.  Needs d/P in {8, 16, 32, ...} and the graph to fit on one GPU."""
+                  only exchange of a step is 32 bytes per triple per peer (the partial scores, each value
+                  stamped with the step so that the consumer needs no barrier).  Needs d/P in {8, 16, 32, ...}
+                  and the graph to fit on one GPU."""
 
     def __init__(self, graph: DeviceGraph, table: torch.Tensor, n_users: int, n_layers: int,
                  lr: float, reg: float, batch_size: int, max_triples: int,
@@ -200,7 +201,7 @@ class LightGCNEngine:
         self._ext = None
         self._loss_eager = None
         self.dist_graphs = _os.environ.get("ARLIB_B200_DIST_GRAPHS", "1") == "1"
-        self.launches_per_step = {"single": 2 * self.L + 5, "rows": 4 * self.L + 5, "dshard": 2 * self.L + 7}[self.mode]
+        self.launches_per_step = {"single": 2 * self.L + 5, "rows": 4 * self.L + 5, "dshard": 2 * self.L + 6}[self.mode]
         if self.fuse_adam:       # no adam kernel; no zero_rows kernel either when the last backward layer re-zeroes G
             self.launches_per_step -= 2 if self.L > 1 else 1
         self._refresh_adam_coefs()
@@ -330,8 +331,9 @@ class LightGCNEngine:
         mask = self.node_mask[b * self.mask_words:] if self.sparse_layers else None
         F = self.forward_table(row_mask=mask, worklist=self._worklist(b) if mask is not None else None)
         if self.mode == "dshard":
+            # the step's only exchange: 32 B per triple to every peer, stamped with the step -- bpr_finish spins on
+            # the words it needs, no barrier launch (csrc/bpr.cu)
             ops.bpr_partial(F, u, i, j, nb, self.U, self.comm.rank, self.B, self.step_dev, self._xchg_all)
-            self.comm.barrier()                  # the step's only exchange: 16 B per triple to every peer
             ops.bpr_finish(self.xchg, self.comm.world, self.B, nb, self.reg, self.step_dev, out4, self.coef, self.ws)
         else:
             ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)

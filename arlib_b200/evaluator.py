@@ -165,6 +165,41 @@ class FullRankEvaluator:
         dist.all_gather_into_tensor(all_i, idx)
         return ops.topk_merge(all_v, all_i)
 
+    def topk_user_sharded(self, user_emb, item_emb, K, rank, world, impl=None, gather=True):
+        """User-sharded evaluation (multi-GPU default when the item table fits one GPU, which it does at every named
+        shape): rank r scores test users [r n/P, (r+1) n/P) against ALL items with the fused top-K -- every per-user
+        cost (mask bits, GEMM rows, candidate selection, exact re-scoring, selection) divides by P and nothing is
+        exchanged until the P blocks of [n/P, K] results are all-gathered (NCCL, ``gather=False`` keeps them local:
+        the ranking metrics are per-user sums).  Item sharding (topk_sharded) replicates the per-user work on every
+        rank and only pays when the item table itself must be split."""
+        import torch.distributed as dist
+        impl = DEFAULT_IMPL if impl is None else impl
+        if item_emb.shape[1] > 128:
+            impl = 0
+        n = self.user_rows.numel()
+        per = (n + world - 1) // world
+        lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+        ue, ie = user_emb.detach().contiguous(), item_emb.detach().contiguous()
+        vals = torch.full((per, K), float("-inf"), dtype=torch.float32, device=self.device)
+        idx = torch.full((per, K), -1, dtype=torch.int32, device=self.device)
+        for a in range(lo, hi, USER_CHUNK):
+            b = min(hi, a + USER_CHUNK)
+            need = ops._lib.load().agcf_score_topk_ws_bytes(b - a, ie.shape[0], ie.shape[1], K)
+            if need < 0:
+                ops._lib.check(int(need), "agcf_score_topk_ws_bytes")
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+            v, i = ops.score_topk(ue, ie, K, user_rows=self.user_rows[a:b], mask_rowptr=self.mask_rowptr,
+                                  mask_items=self.mask_items, impl=impl, ws=self._ws)
+            vals[a - lo:b - lo], idx[a - lo:b - lo] = v, i
+        if not gather:
+            return vals[:hi - lo], idx[:hi - lo], (lo, hi)
+        all_v = torch.empty((world * per, K), dtype=torch.float32, device=self.device)
+        all_i = torch.empty((world * per, K), dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(all_v, vals)
+        dist.all_gather_into_tensor(all_i, idx)
+        return all_v[:n], all_i[:n]
+
     def per_user_metrics(self, idx, cutoffs):
         """[n_users, n_cutoffs, 3] float64 (hits, dcg, idcg) on device."""
         K = idx.shape[1]

@@ -85,6 +85,7 @@ def spmm(g: DeviceGraph, X, Y=None, addend=None, acc_in=None, acc_out=None, acc_
             raise ValueError("aux operand shape mismatch")
         a.aux_Y[q], a.aux_noise[q], a.aux_stream[q] = y_q.data_ptr(), _p(tab_q), int(stream_q or 0)
     a.row_mask, a.col_mask = _p(row_mask), _p(col_mask)
+    a.mask_bits = g.n_rows
     a.peer_Y_host = ctypes.cast(py, ctypes.c_void_p) if py is not None else None
     a.peer_acc_host = ctypes.cast(pa, ctypes.c_void_p) if pa is not None else None
     a.n_peers = max(n1, n2)

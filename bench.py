@@ -496,8 +496,14 @@ def run_ours(args):
     ev = FullRankEvaluator.from_arrays(U, I, D["tu"], D["ti"], D["su"], D["si"], dev)
     F = eng.full_table(eng.forward_table()).clone()
     n_test = ev.user_rows.numel()
+    eval_shard = os.environ.get("ARLIB_B200_EVAL_SHARD", "users")
     if world > 1:
-        ev.topk = lambda ue_, ie_, k_, impl=None: ev.topk_sharded(ue_, ie_, k_, rank, world, impl)
+        # users: every per-user cost divides by P, one all-gather of the [n/P, K] result blocks; items: the layout for
+        # item tables that do not fit one GPU (per-user work replicated, top-K merge)
+        if eval_shard == "users":
+            ev.topk = lambda ue_, ie_, k_, impl=None: ev.topk_user_sharded(ue_, ie_, k_, rank, world, impl)
+        else:
+            ev.topk = lambda ue_, ie_, k_, impl=None: ev.topk_sharded(ue_, ie_, k_, rank, world, impl)
     for _ in range(2):
         vals, idx = ev.topk(F[:U], F[U:], TOPK)
     barrier()
@@ -527,7 +533,9 @@ def run_ours(args):
              "roofline": {"bound": "tensor", "achieved": flops / (ev_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                           "frac": flops / (ev_ms * 1e-3) / 1e12 / tpeak, "traffic": None,
                           "note": "whole eval pipeline (mask bits + group-max GEMM + select/rescore + metrics)"},
-             "candidate_groups_mean": cand_groups, "measure": [m.strip() for m in measure]}
+             "candidate_groups_mean": cand_groups, "measure": [m.strip() for m in measure],
+             "sharding": "single GPU" if world == 1 else ("user-sharded x%d, results all-gathered" % world
+                                                          if eval_shard == "users" else "item-sharded x%d + top-K merge" % world)}
 
     line = {
         "metric": "LightGCN train triples/s", "value": value, "unit": "triples/s", "n_gpus": world, "steps": K,
@@ -538,8 +546,8 @@ def run_ours(args):
                         "rows": "row-partitioned x%d: per-layer all-gather fused into the SpMM epilogue (NVLink P2P "
                                 "stores), item-sharded eval" % world,
                         "dshard": "column-sharded x%d: every table split [N, d/%d], graph replicated, propagation / "
-                                  "backward / Adam communication-free, one P2P exchange of the partial scores (16 B per "
-                                  "triple per peer) + one barrier per step; item-sharded eval" % (world, world)}[eng.mode],
+                                  "backward / Adam communication-free, one P2P exchange of the partial scores (32 B per "
+                                  "triple per peer): the consumer spins on step-stamped words, no barrier launch; user-sharded eval" % (world, world)}[eng.mode],
         "gpu_launches": K * eng.launches_per_step, "last_loss": loss_last,
     }
     if rank == 0 and not args.no_cpu_baseline:

@@ -122,7 +122,9 @@ int agcf_spmm_csr_f32(const int32_t* vrows, const int32_t* vpart, int32_t n_vrow
  *                 (148 x resident CTAs per SM) that take blocks of work items from this counter in plan order instead
  *                 of one CTA per block -- no CTA turnover gaps and no tail of idle SMs; launches sharing it must be
  *                 stream-ordered;
- *   flags         reserved, must be 0.
+ *   flags         reserved, must be 0;
+ *   mask_bits     number of bits of row_mask / col_mask (= rows of X), or 0 if unknown: the narrow-row (d <= 16) variant
+ *                 of the column-masked launch copies the bitmap into shared memory when it is given and fits.
  * A launch with col_mask (and no noise) runs the sparse variant (ballot over the live entries of a chunk, only
  * those are gathered): identical results. */
 typedef struct agcf_spmm_args {
@@ -142,6 +144,7 @@ typedef struct agcf_spmm_args {
   int32_t* sched;
   int32_t d;
   int32_t flags;
+  int32_t mask_bits;
 } agcf_spmm_args;
 int agcf_spmm_csr_f32_ex(const agcf_spmm_args* args, agcf_stream_t stream);
 
@@ -216,10 +219,14 @@ int agcf_bpr_forward(const float* F, const int32_t* u, const int32_t* i, const i
  * width): agcf_bpr_partial computes each triple's share {<u,i>, <u,j>, |u|^2, |i|^2} on this rank's
  * slice and stores it into slot `rank` of the exchange buffer of EVERY rank (xchg_all_host: HOST array
  * of `world` device pointers, own buffer included, peer-mapped over NVLink; agcf_bpr_xchg_bytes(cap)
- * bytes each, cap >= nb).  After a cross-rank barrier agcf_bpr_finish sums the shares in rank order --
- * the same bits on every rank -- and produces out4 / coef exactly like agcf_bpr_forward.  The buffer
- * is double-buffered on the parity of *step_dev (device step counter, nullable), so one barrier per
- * step is enough.  This is the ONLY exchange of a d-sharded training step: 16*nb bytes per peer. */
+ * bytes each, cap >= nb, ZERO before the first use).  agcf_bpr_finish sums the shares in rank order --
+ * the same bits on every rank -- and produces out4 / coef exactly like agcf_bpr_forward.
+ * No barrier between the two calls: every value travels as one 64-bit word {step + 1 : 32 | float : 32}
+ * (a single-copy-atomic store), and agcf_bpr_finish spins until the words it needs carry the current
+ * step's stamp (it gives up with a NaN loss after 4 s if a rank never shows up).  The buffer is
+ * double-buffered on the parity of *step_dev (device step counter; every rank must advance it once per
+ * step; NULL = a single use of a zeroed buffer).  This is the ONLY exchange of a d-sharded training
+ * step: 32*nb bytes per peer. */
 int64_t agcf_bpr_xchg_bytes(int32_t cap);
 int agcf_bpr_partial(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
                      int32_t nb, int32_t n_users, int32_t d, int32_t rank, int32_t cap,

@@ -58,7 +58,7 @@ def main():
     assert shard.d == d // world
     shard.sample_epoch(ts, 7, 0)
     shard.run_steps(0, 3, use_graph=False)
-    shard.run_steps(3, 2, use_graph=True)                  # graph capture incl. the barrier and the parity buffers
+    shard.run_steps(3, 2, use_graph=True)                  # graph capture incl. the stamped exchange and its parity halves
     torch.cuda.synchronize(); dist.barrier()
     full = shard.full_table(shard.E0)
     derr = float((full - single.E0).abs().max())
@@ -77,6 +77,18 @@ def main():
     v1, i1 = ev.topk(Fs[:U], Fs[U:], 50)
     v2, i2 = ev.topk_sharded(Fs[:U], Fs[U:], 50, rank, world)
     assert torch.equal(i1, i2) and torch.equal(v1, v2)
+    # user-sharded evaluation (the default multi-GPU layout of the bench) == unsharded, on every rank
+    v3, i3 = ev.topk_user_sharded(Fs[:U], Fs[U:], 50, rank, world)
+    assert torch.equal(i1, i3) and torch.equal(v1, v3)
+    # many d-sharded steps back to back through a captured graph: the stamped exchange must stay in step without
+    # any barrier (both halves of the double buffer are re-used hundreds of times)
+    shard.run_steps(0, 40, use_graph=True)
+    for _ in range(4):
+        shard.run_steps(0, 40, use_graph=True)
+    torch.cuda.synchronize(); dist.barrier()
+    rows = [torch.empty_like(shard.out4[:40]) for _ in range(world)]
+    dist.all_gather(rows, shard.out4[:40].contiguous())
+    assert all(torch.equal(rows[0], r) for r in rows) and bool(torch.isfinite(rows[0]).all())
     dist.barrier()
     if rank == 0:
         print("DIST_CHECK_OK world=%d table_err=%.2e dshard_err=%.2e" % (world, err, derr))

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_strings():
     lib = _lib.load()
-    assert lib.agcf_abi_version() == 3
+    assert lib.agcf_abi_version() == 4
     assert lib.agcf_strerror(0) == b"ok"
     assert b"invalid" in lib.agcf_strerror(-1)
     # argument validation happens before any CUDA call, so it is checkable without a GPU

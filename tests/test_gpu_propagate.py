@@ -208,7 +208,7 @@ def test_simgcl_xsimgcl_ngcf_encoders_match_oracle():
     torch.testing.assert_close(enc.W['w2_1'].grad.cpu(), w2[1].grad, rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("d", [8, 16, 64, 128])
 def test_spmm_row_and_column_masks(d):
     """Batch-sparse layers: row_mask = only those rows are computed/written; col_mask =
     rows of X outside it are zero and are skipped (same result as the dense product)."""
@@ -263,3 +263,52 @@ def test_ngcf_adjacency_gradient_matches_sparse_mm_autograd():
     # .backward() fills .grad like LightGCN's (recommender/NGCF.py:41-43,59-60: Matgrad += sparse_norm_adj.grad)
     _loss(*enc()).backward()
     torch.testing.assert_close(enc.sparse_norm_adj.grad.coalesce().values().cpu(), gr.values(), rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("segment", [64, 256])
+@pytest.mark.parametrize("d", [8, 16])
+def test_narrow_rows_cooperative_kernel(d, segment):
+    """Column slices of the d-sharded tables (d = 8 / 16) run the warp-cooperative kernel (csrc/propagate.cu
+    spmm_block_coop): items longer than one 64-entry index block, hub rows cut into many segments, the fused epilogue,
+    the column-masked variant (bitmap in shared memory), per-batch work lists and run-to-run determinism."""
+    from arlib_b200 import ops
+    from arlib_b200.graph import DeviceGraph
+    U, I = 1300, 1700
+    u, i = _rand_graph(U, I, 40000, 12, 900)
+    adj = port.bipartite_adjacency(u, i, U, I)
+    norm = port.to_torch_coo(port.normalize_graph_mat(adj))
+    g = DeviceGraph.from_dataloader_adj(adj, _dev()).replan(segment, segment)
+    assert g.segment == segment and g.max_segments >= 3
+    n = U + I
+    X = torch.randn(n, d)
+    ref = torch.sparse.mm(norm, X)
+    Xd = X.to(_dev())
+    Y = torch.empty_like(Xd)
+    ops.spmm(g, Xd, Y=Y)
+    torch.testing.assert_close(Y.cpu(), ref, rtol=1e-5, atol=2e-6)
+    Y2 = torch.empty_like(Xd)
+    ops.spmm(g, Xd, Y=Y2)
+    assert torch.equal(Y, Y2)                                   # fixed summation order
+    add, acc = torch.randn(n, d), torch.randn(n, d)
+    accd = acc.to(_dev())
+    ops.spmm(g, Xd, Y=Y2, addend=add.to(_dev()), acc_in=accd, acc_out=accd, acc_div=4.0)
+    torch.testing.assert_close(Y2.cpu(), ref + add, rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(accd.cpu(), (acc + ref + add) / 4.0, rtol=1e-5, atol=2e-6)
+    # column mask: X is zero outside the live rows
+    rng = np.random.default_rng(d)
+    live = rng.random(n) < 0.13
+    live[:3] = True
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    for k in np.flatnonzero(live):
+        words[k >> 5] |= np.uint32(1) << np.uint32(k & 31)
+    mask = torch.from_numpy(words.view(np.int32)).to(_dev())
+    Xz = X.clone(); Xz[~torch.from_numpy(live)] = 0
+    refz = torch.sparse.mm(norm, Xz)
+    ops.spmm(g, Xz.to(_dev()), Y=Y2, addend=add.to(_dev()), col_mask=mask)
+    torch.testing.assert_close(Y2.cpu(), refz + add, rtol=1e-5, atol=2e-6)
+    # row mask: only the live rows are written
+    out = torch.full((n, d), 7.0, device=_dev())
+    ops.spmm(g, Xd, acc_out=out, row_mask=mask)
+    out = out.cpu()
+    torch.testing.assert_close(out[torch.from_numpy(live)], ref[torch.from_numpy(live)], rtol=1e-5, atol=2e-6)
+    assert bool((out[~torch.from_numpy(live)] == 7.0).all())
