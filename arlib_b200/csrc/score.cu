@@ -301,6 +301,11 @@ struct Stage2Params {
   float* u_val;                // [n_u][cmax*32] exact scores of the candidates
   int32_t* g_count;            // [n_groups] users that have the group as a candidate (zeroed by the caller)
   int32_t* pairs;              // [n_groups][n_u] (user << 8 | candidate slot) of the users that have the group
+  // item-compacting variant of the group-major stage 2: the re-scoring keeps only the exact scores that can still matter
+  float* u_thr;                // [n_u] T_u <= s*_u (K-th largest exact score): nothing below it can be selected or tie
+  int32_t* u_cnt;              // [n_u] kept (item, score) entries (zeroed by the caller); > cap_items = overflow
+  int2* u_items;               // [n_u][cap_items] {item, score bits}, unordered
+  int cap_items;
 };
 
 template <int D>
@@ -699,11 +704,15 @@ __global__ void __launch_bounds__(256) s2_candidates_kernel(const Stage2Params p
     __syncwarp();
     const unsigned int R = (unsigned int)min(p.K, p.n_groups);
     float thr = key2f(warp_radix_select(hist, p.n_groups, R, lane, grow));
+    float keep_from = thr;                                           // tau itself when stage 1 is exact
     if (p.margin_scale > 0.f) {
       float ss = 0.f;
       for (int k = 0; k < D; ++k) ss = fmaf(urow[k], urow[k], ss);
-      thr -= p.margin_scale * sqrtf(ss) * __ldg(p.max_item_norm);
+      const float margin = p.margin_scale * sqrtf(ss) * __ldg(p.max_item_norm);      // 2 delta
+      keep_from = thr - 0.75f * margin;                              // tau - 1.5 delta  <=  tau - delta  <=  s*
+      thr -= margin;
     }
+    if (p.u_thr != nullptr && lane == 0) p.u_thr[r] = keep_from;
     int32_t* my_groups = p.u_groups + (size_t)r * p.cmax;
     int n_cg = 0;
     bool overflow = false;
@@ -899,6 +908,215 @@ __global__ void __launch_bounds__(256) s2_select_kernel(const Stage2Params p) {
   }
 }
 
+// ------------------------------------- stage 2, group-major, ITEM-compacting variant
+// s2_rescore above stores all 32 exact scores of every candidate group (57 x 32 = 1 824 per user at the Gowalla shape)
+// and s2_select radix-selects the K-th largest of them in four passes -- yet only ~60 of them can matter: with tau the
+// K-th largest stage-1 group maximum and delta the stage-1 error bound, the K-th largest EXACT score s* is >= tau - delta
+// (file header), and neither the selection nor the reference's tie rule looks at a score below s*.  s2_candidates
+// publishes T_u = tau - 1.5 delta (<= s*), the re-scoring keeps only entries with score >= T_u (a ballot + one atomic per
+// pair, {item, score} compacted per user in arrival order), and the per-user selection first orders its <= 128 entries
+// by item id (the tie rule is defined on item order) and then runs the SAME selection / tie / sort code on ~60 values
+// instead of 1 824.  Users with more than cap_items entries (heavy ties, fewer than K unmasked items) go to the block
+// kernel like the candidate-group overflows.  Bit-identical results (tests run all stage-2 variants).
+constexpr int kS2ItemCap = 128;
+
+template <int D>
+__global__ void __launch_bounds__(256) s2_rescore_items_kernel(const Stage2Params p) {
+  constexpr int LD = D + 4, V4 = D / 4;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  float* tile = reinterpret_cast<float*>(dyn);                       // [32][LD]
+  float* urow_all = tile + kGroup * LD;                              // [8 warps][PB][D]
+  const int g = blockIdx.x, slice = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cnt = p.g_count[g];
+  if (slice * 8 >= cnt) return;
+  const int32_t* my_pairs = p.pairs + (size_t)g * p.n_u;
+  const int rows_here = min(kGroup, p.n_items - g * kGroup);
+  const float4* src = p.Iemb + (size_t)g * kGroup * V4;
+  for (int f = threadIdx.x; f < kGroup * V4; f += 256) {
+    const int row = f / V4, c4 = f - row * V4;
+    const float4 v = row < rows_here ? __ldg(src + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(tile + row * LD + 4 * c4) = v;
+  }
+  __syncthreads();
+  constexpr int PB = AGCF_S2_PB;
+  float* urows = urow_all + warp * PB * D;
+  const float* mine_row = tile + lane * LD;
+  const int stride = kS2Slices * 8;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  for (int q0 = slice * 8 + warp; q0 < cnt; q0 += PB * stride) {
+    int pr[PB];
+    uint32_t word[PB];
+    float keep_from[PB];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int q = q0 + j * stride;
+      pr[j] = q < cnt ? my_pairs[q] : -1;
+      word[j] = 0u;
+      keep_from[j] = 0.f;
+      if (pr[j] >= 0) {
+        const int r = pr[j] >> 8;
+        const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
+        for (int k = lane; k < V4; k += 32) reinterpret_cast<float4*>(urows + j * D)[k] = __ldg(p.Uemb + (size_t)uid * V4 + k);
+        word[j] = __ldg(p.bits + (size_t)r * p.pitch + g);
+        keep_from[j] = __ldg(p.u_thr + r);
+      }
+    }
+    __syncwarp();
+    float sc[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) sc[j] = 0.f;
+#pragma unroll 4
+    for (int k4 = 0; k4 < V4; ++k4) {
+      const float4 v = *reinterpret_cast<const float4*>(mine_row + 4 * k4);
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(urows + j * D + 4 * k4);
+        sc[j] = fmaf(w.x, v.x, sc[j]);
+        sc[j] = fmaf(w.y, v.y, sc[j]);
+        sc[j] = fmaf(w.z, v.z, sc[j]);
+        sc[j] = fmaf(w.w, v.w, sc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      if (pr[j] < 0) continue;                                       // warp-uniform
+      float v = sc[j];
+      if ((word[j] >> lane) & 1u) v = kMasked;
+      const bool keep = lane < rows_here && v >= keep_from[j];
+      const unsigned int b = __ballot_sync(0xffffffffu, keep);
+      if (b == 0u) continue;
+      const int r = pr[j] >> 8;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(p.u_cnt + r, __popc(b));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) {
+        const int pos = base + __popc(b & lt_mask);
+        if (pos < p.cap_items) p.u_items[(size_t)r * p.cap_items + pos] = make_int2(g * kGroup + lane, __float_as_int(v));
+      }
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) s2_select_items_kernel(const Stage2Params p) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int kpow2 = 1;
+  while (kpow2 < p.K) kpow2 <<= 1;
+  // per warp: histogram (1 KB), K sort keys, the entries as 64-bit keys / as (score, item) arrays
+  const size_t per_warp = 1024 + (size_t)kpow2 * 8 + (size_t)kS2ItemCap * 16;
+  unsigned char* mine = dyn + (size_t)warp * per_warp;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(mine);
+  unsigned long long* sort_keys = reinterpret_cast<unsigned long long*>(mine + 1024);
+  unsigned long long* ekeys = reinterpret_cast<unsigned long long*>(mine + 1024 + (size_t)kpow2 * 8);
+  float* my_val = reinterpret_cast<float*>(ekeys + kS2ItemCap);
+  int* my_item = reinterpret_cast<int*>(my_val + kS2ItemCap);
+  const int gw = blockIdx.x * 8 + warp, n_warps = gridDim.x * 8;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  for (int r = gw; r < p.n_u; r += n_warps) {
+    const int n_cg = p.u_ncg[r];
+    if (n_cg < 0) continue;                                          // candidate-group overflow: already on the list
+    const int n = p.u_cnt[r];
+    const int Keff = min(p.K, p.n_items);
+    if (n > p.cap_items || n < Keff) {                               // too many survivors (ties / few unmasked items)
+      if (lane == 0) p.overflow_list[atomicAdd(p.overflow_count, 1)] = r;
+      continue;
+    }
+    __syncwarp();
+    // order the entries by item id: the tie rule of the reference's heap is defined on item order
+    for (int k = lane; k < kS2ItemCap; k += 32) {
+      unsigned long long key = ~0ull;
+      if (k < n) {
+        const int2 e = p.u_items[(size_t)r * p.cap_items + k];
+        key = ((unsigned long long)(uint32_t)e.x << 32) | (uint32_t)e.y;
+      }
+      ekeys[k] = key;
+    }
+    __syncwarp();
+    for (int kk = 2; kk <= kS2ItemCap; kk <<= 1)
+      for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+        for (int idx = lane; idx < (kS2ItemCap >> 1); idx += 32) {
+          const int a = ((idx & ~(jj - 1)) << 1) | (idx & (jj - 1));
+          const int c = a | jj;
+          const bool up = (a & kk) == 0;
+          const unsigned long long ka = ekeys[a], kc = ekeys[c];
+          if ((ka > kc) == up) { ekeys[a] = kc; ekeys[c] = ka; }
+        }
+        __syncwarp();
+      }
+    for (int k = lane; k < n; k += 32) {
+      const unsigned long long key = ekeys[k];
+      my_item[k] = (int)(uint32_t)(key >> 32);
+      my_val[k] = __uint_as_float((uint32_t)key);
+    }
+    __syncwarp();
+    // K-th largest exact score s*, then the reference heap's tie rule (see topk_select_kernel) -- on n entries
+    const float sstar = key2f(warp_radix_select(hist, n, (unsigned int)Keff, lane, my_val));
+    int run_ge = 0, run_gt = 0, gp_local = 0;
+    bool found = false;
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      const bool real = k < n;
+      const float v = real ? my_val[k] : 0.f;
+      const bool gt = real && v > sstar, ge = real && v >= sstar;
+      const unsigned int bge = __ballot_sync(0xffffffffu, ge), bgt = __ballot_sync(0xffffffffu, gt);
+      if (ge && run_ge + __popc(bge & lt_mask) + 1 == Keff) { found = true; gp_local = run_gt + __popc(bgt & lt_mask) + (gt ? 1 : 0); }
+      run_ge += __popc(bge);
+      run_gt += __popc(bgt);
+    }
+    const int m = run_gt;
+    const unsigned int fb = __ballot_sync(0xffffffffu, found);
+    const int gp = __shfl_sync(0xffffffffu, gp_local, fb != 0u ? (__ffs(fb) - 1) : 0);
+    for (int k = lane; k < kpow2; k += 32) sort_keys[k] = ~0ull;
+    __syncwarp();
+    const int tie_lo = m - gp, tie_n = Keff - m;
+    int run_eq = 0;
+    run_gt = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      const bool real = k < n;
+      const float v = real ? my_val[k] : 0.f;
+      const bool gt = real && v > sstar, eq = real && v == sstar;
+      const unsigned int beq = __ballot_sync(0xffffffffu, eq), bgt = __ballot_sync(0xffffffffu, gt);
+      const int trank = run_eq + __popc(beq & lt_mask);
+      const int gt_before = run_gt + __popc(bgt & lt_mask);
+      if (gt || (eq && trank >= tie_lo && trank < tie_lo + tie_n)) {
+        int ties_before = trank - tie_lo;
+        ties_before = ties_before < 0 ? 0 : (ties_before > tie_n ? tie_n : ties_before);
+        sort_keys[gt_before + ties_before] = ((unsigned long long)(~f2key(v)) << 32) | (uint32_t)my_item[k];
+      }
+      run_eq += __popc(beq);
+      run_gt += __popc(bgt);
+    }
+    __syncwarp();
+    for (int kk = 2; kk <= kpow2; kk <<= 1)
+      for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+        for (int idx = lane; idx < (kpow2 >> 1); idx += 32) {
+          const int a = ((idx & ~(jj - 1)) << 1) | (idx & (jj - 1));
+          const int c = a | jj;
+          const bool up = (a & kk) == 0;
+          const unsigned long long ka = sort_keys[a], kc = sort_keys[c];
+          if ((ka > kc) == up) { sort_keys[a] = kc; sort_keys[c] = ka; }
+        }
+        __syncwarp();
+      }
+    for (int k = lane; k < p.K; k += 32) {
+      float v = -INFINITY;
+      int idx = -1;
+      if (k < Keff) {
+        const unsigned long long key = sort_keys[k];
+        v = key2f(~(uint32_t)(key >> 32));
+        idx = (int)(uint32_t)key + p.item_offset;
+      }
+      p.out_val[(size_t)r * p.K + k] = v;
+      p.out_idx[(size_t)r * p.K + k] = idx;
+    }
+    if (lane == 0 && p.out_flags != nullptr) p.out_flags[r] = n_cg;
+  }
+}
+
 // --------------------------------------------------------------------- predict
 template <int D>
 __global__ void __launch_bounds__(256) score_rows_kernel(const float4* __restrict__ Uemb, const int32_t* __restrict__ user_rows,
@@ -981,17 +1199,19 @@ int launch_group_max_tc(const float* Uemb, const int32_t* user_rows, int n_u, co
 struct WsLayout {
   size_t bits_off, gmax_off, norm_off, groups_off, cval_off, udense_off, wgroups_off, wval_off, ovf_off, total;
   size_t ugroups_off, uncg_off, uval_off, gcount_off, pairs_off;   // group-major stage 2
+  size_t uthr_off, ucnt_off, uitems_off;                            // its item-compacting variant
   int n_groups, pitch, grid2, grid_w, cmax, wpc;
 };
 
 constexpr int kStage2OverflowCtas = 32;      // block-kernel CTAs that mop up users with > cmax candidate groups
 constexpr int kStage2CandMax = 160;          // candidate groups a warp can hold (mean 55, max 72 seen at K = 50)
 
-// stage 2 implementation: 1 = group-major re-scoring (default), 0 = the warp-per-user kernel (re-loads every candidate
-// group per user); identical results
+// stage 2 implementation: 2 = group-major re-scoring that keeps only the entries >= T_u (default), 1 = group-major, all 32
+// scores of every candidate group stored and selected from, 0 = the warp-per-user kernel (re-loads every candidate group
+// per user); identical results
 static int stage2_impl() {
   const char* e = getenv("AGCF_STAGE2_IMPL");
-  return e ? atoi(e) : 1;
+  return e ? atoi(e) : 2;
 }
 
 static int stage2_ctas_per_sm() {
@@ -1037,6 +1257,9 @@ static WsLayout ws_layout(int n_u, int n_items, int d) {
   L.uval_off = off; off = up(off + (size_t)n_u * L.cmax * kGroup * 4);
   L.gcount_off = off; off = up(off + ((size_t)L.n_groups + 1) * 4);
   L.pairs_off = off; off = up(off + (size_t)L.n_groups * n_u * 4);
+  L.uthr_off = off; off = up(off + (size_t)n_u * 4);
+  L.ucnt_off = off; off = up(off + (size_t)n_u * 4);
+  L.uitems_off = off; off = up(off + (size_t)n_u * kS2ItemCap * 8);
   L.total = off;
   return L;
 }
@@ -1131,15 +1354,26 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   p.u_val = reinterpret_cast<float*>(base + L.uval_off);
   p.g_count = reinterpret_cast<int32_t*>(base + L.gcount_off);
   p.pairs = reinterpret_cast<int32_t*>(base + L.pairs_off);
+  p.u_thr = nullptr; p.u_cnt = nullptr; p.u_items = nullptr; p.cap_items = kS2ItemCap;
   int kpow2 = 1;
   while (kpow2 < K) kpow2 <<= 1;
   const size_t dyn = (size_t)kpow2 * 8;
-  if (stage2_impl() == 1 && n_u < (1 << 23) && L.cmax <= 256) {
+  if (stage2_impl() >= 1 && n_u < (1 << 23) && L.cmax <= 256) {
+    // the item-compacting variant needs T_u <= s*, which the file header proves for K <= n_groups; with few groups (tiny
+    // item tables) nearly every item is wanted anyway and the plain group-major kernels run
+    const bool items = stage2_impl() == 2 && L.n_groups >= 2 * K;
+    if (items) {
+      p.u_thr = reinterpret_cast<float*>(base + L.uthr_off);
+      p.u_cnt = reinterpret_cast<int32_t*>(base + L.ucnt_off);
+      p.u_items = reinterpret_cast<int2*>(base + L.uitems_off);
+      AGCF_CUDA_OK(cudaMemsetAsync(p.u_cnt, 0, (size_t)n_u * 4, st));
+    }
     // group-major: candidates -> per-group pair lists -> re-score each group's tile once per CTA -> select
     AGCF_CUDA_OK(cudaMemsetAsync(p.g_count, 0, ((size_t)L.n_groups + 1) * 4, st));
     const unsigned warp_grid = (unsigned)min((n_u + 7) / 8, 8 * kSMs);
     const size_t dyn_sel = 8 * (1024 + (size_t)kpow2 * 8);
-    if (dyn_sel > 200 * 1024) return AGCF_EUNSUPPORTED;
+    const size_t dyn_sel_items = 8 * (1024 + (size_t)kpow2 * 8 + (size_t)kS2ItemCap * 16);
+    if (dyn_sel_items > 200 * 1024) return AGCF_EUNSUPPORTED;
 #define AGCF_S2G(DD)                                                                                             \
   {                                                                                                              \
     const size_t dyn_r = ((size_t)kGroup * (DD + 4) + 8 * AGCF_S2_PB * DD) * 4;   /* tile + 8 warps x PB user rows */ \
@@ -1148,8 +1382,17 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
     if (dyn_sel > 48 * 1024)                                                                                     \
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_select_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel)); \
     s2_candidates_kernel<DD><<<warp_grid, 256, 0, st>>>(p);                                                      \
-    s2_rescore_kernel<DD><<<dim3((unsigned)L.n_groups, kS2Slices), 256, dyn_r, st>>>(p);                         \
-    s2_select_kernel<DD><<<warp_grid, 256, dyn_sel, st>>>(p);                                                    \
+    if (items) {                                                                                                 \
+      if (dyn_r > 48 * 1024)                                                                                     \
+        AGCF_CUDA_OK(cudaFuncSetAttribute(s2_rescore_items_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_r)); \
+      if (dyn_sel_items > 48 * 1024)                                                                             \
+        AGCF_CUDA_OK(cudaFuncSetAttribute(s2_select_items_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel_items)); \
+      s2_rescore_items_kernel<DD><<<dim3((unsigned)L.n_groups, kS2Slices), 256, dyn_r, st>>>(p);                 \
+      s2_select_items_kernel<DD><<<warp_grid, 256, dyn_sel_items, st>>>(p);                                      \
+    } else {                                                                                                     \
+      s2_rescore_kernel<DD><<<dim3((unsigned)L.n_groups, kS2Slices), 256, dyn_r, st>>>(p);                       \
+      s2_select_kernel<DD><<<warp_grid, 256, dyn_sel, st>>>(p);                                                  \
+    }                                                                                                            \
     topk_select_kernel<DD><<<(unsigned)L.grid2, 256, dyn, st>>>(p);                                              \
   }
     switch (d) { case 32: AGCF_S2G(32) break; case 64: AGCF_S2G(64) break; case 128: AGCF_S2G(128) break; case 256: AGCF_S2G(256) break; }

@@ -88,6 +88,32 @@ class DeviceTrainSet:
         return self
 
 
+    @classmethod
+    def from_graph(cls, graph, n_users, n_items, epoch_edges=None, seed=0):
+        """From the device adjacency itself (no host pass over the edges; the 10 M x 1 M scale-stress shape): the
+        rejection lists ARE the user rows of the canonical CSR (sorted item columns minus the user offset); the
+        positives of an "epoch" are all user -> item non-zeros, or a uniform sample of ``epoch_edges`` of them (a full
+        epoch of a 200 M-edge graph is 97 657 full-graph steps -- SURVEY.md 8d reports per-step numbers there)."""
+        self = cls.__new__(cls)
+        dev = graph.rowptr.device
+        U = int(n_users)
+        n_ui = int(graph.rowptr[U])                                  # non-zeros of the user rows = E
+        rowptr_u = graph.rowptr[:U + 1].contiguous()
+        items = (graph.col[:n_ui] - U).contiguous()
+        if epoch_edges is None or epoch_edges >= n_ui:
+            pos = torch.arange(n_ui, device=dev)
+        else:
+            g = torch.Generator(device=dev).manual_seed(seed)
+            pos = torch.randint(0, n_ui, (int(epoch_edges),), generator=g, device=dev)
+        e_user = (torch.searchsorted(rowptr_u.long(), pos, right=True) - 1).to(torch.int32)
+        self.n_edges, self.n_users, self.n_items = int(pos.numel()), U, int(n_items)
+        self.e_user = e_user.contiguous()
+        self.e_item = items[pos].contiguous()
+        self.rej_rowptr = rowptr_u
+        self.rej_items = items if items.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
+        return self
+
+
 class LightGCNEngine:
     """``mode`` (multi-GPU only):
       "rows"   -- node rows and adjacency rows partitioned; every layer's rows are all-gathered by the SpMM

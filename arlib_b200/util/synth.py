@@ -53,3 +53,47 @@ def synth_edges(user_num, item_num, n_edges, alpha_u=0.5, alpha_i=0.5, seed=0, t
     test = rest[n_train_rest:n_train_rest + n_test]
     train = train[rng.permutation(train.shape[0])]
     return train // item_num, train % item_num, test // item_num, test % item_num
+
+
+def synth_edges_device(user_num, item_num, n_edges, alpha_u=0.5, alpha_i=0.5, seed=0, device="cuda", chunk=1 << 26):
+    """The same power-law model drawn ON THE DEVICE (torch), for graphs the host generator and the reference's
+    dict-of-dicts loader cannot hold (BASELINE.json configs[4]: 10 M users x 1 M items; SURVEY.md 8 fixes E = 200 M):
+    user activity ~ rank^-alpha_u and item popularity ~ rank^-alpha_i over randomly permuted ranks, pairs drawn
+    independently by inverse-CDF search and de-duplicated, one coverage edge per user and per item.  Returns int64
+    device tensors (u, i) of ~n_edges UNIQUE pairs (exactly n_edges when enough distinct pairs were drawn; the pairs
+    are sorted by user, then item)."""
+    import torch
+    gen = torch.Generator(device=device).manual_seed(seed)
+    dev = torch.device(device)
+
+    def cdf(n, alpha):
+        p = torch.arange(1, n + 1, dtype=torch.float64, device=dev) ** (-alpha)
+        p = p[torch.randperm(n, generator=gen, device=dev)]
+        return torch.cumsum(p / p.sum(), 0)
+
+    cu, ci = cdf(user_num, alpha_u), cdf(item_num, alpha_i)
+
+    def draw(c, n, m):
+        r = torch.rand(m, dtype=torch.float64, device=dev, generator=gen)
+        return torch.searchsorted(c, r).clamp_(max=n - 1)
+
+    cov = torch.cat([torch.arange(user_num, device=dev) * item_num + draw(ci, item_num, user_num),
+                     draw(cu, user_num, item_num) * item_num + torch.arange(item_num, device=dev)])
+    keys = torch.unique(cov)
+    while keys.numel() < n_edges:
+        need = n_edges - keys.numel()
+        parts = [keys]
+        m = int(need * 1.15) + 1024
+        for lo in range(0, m, chunk):
+            k = min(chunk, m - lo)
+            parts.append(draw(cu, user_num, k) * item_num + draw(ci, item_num, k))
+        keys = torch.unique(torch.cat(parts))
+        del parts
+    if keys.numel() > n_edges:                      # drop a random surplus, never a coverage edge
+        is_cov = torch.isin(keys, cov)
+        extra = torch.nonzero(~is_cov).flatten()
+        drop = extra[torch.randperm(extra.numel(), generator=gen, device=dev)[:keys.numel() - n_edges]]
+        keep = torch.ones(keys.numel(), dtype=torch.bool, device=dev)
+        keep[drop] = False
+        keys = keys[keep]
+    return keys // item_num, keys % item_num

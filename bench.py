@@ -550,6 +550,33 @@ def run_ours(args):
                                   "triple per peer): the consumer spins on step-stamped words, no barrier launch; user-sharded eval" % (world, world)}[eng.mode],
         "gpu_launches": K * eng.launches_per_step, "last_loss": loss_last,
     }
+    # ---- the recommender-level number (north_star: "trains one epoch plus full-rank eval"): wall clock of the drop-in
+    # class's own public calls, LightGCN(args, data).train() with maxEpoch = 1 (DeviceTrainSet, Philox sampling of the
+    # epoch, all ceil(E/B) steps, end-of-epoch forward, evaluate() incl. best-epoch bookkeeping) and test()
+    if rank == 0 and world == 1 and not args.no_epoch_e2e:
+        import contextlib, io, types
+        from arlib_b200.recommender.LightGCN import LightGCN
+        from arlib_b200.util.DataLoader import DataLoader
+        t0 = time.perf_counter()
+        data = DataLoader.from_arrays(D["tu"], D["ti"], D["su"], D["si"])
+        t_data = time.perf_counter() - t0
+        rargs = types.SimpleNamespace(topK=str(TOPK), emb_size=d, n_layers=L, batch_size=B, lRate=LR, reg=REG, maxEpoch=1,
+                                      seed=2018, model_name="LightGCN")
+        runs = []
+        with contextlib.redirect_stdout(io.StringIO()):
+            torch.manual_seed(2018)
+            rec = LightGCN(rargs, data)
+            for _ in range(2):                         # first call builds the device mirrors, the second re-uses them
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                rec.train()
+                torch.cuda.synchronize(); t1 = time.perf_counter()
+                _, measure_e = rec.test()
+                torch.cuda.synchronize(); t2 = time.perf_counter()
+                runs.append((t1 - t0, t2 - t1))
+        line["epoch_e2e"] = {"api": "LightGCN(args, data).train() [maxEpoch=1: %d steps + evaluate()] ; test()" % nb_epoch,
+                             "train_epoch_s": [r[0] for r in runs], "test_s": [r[1] for r in runs],
+                             "triples_per_s": E / runs[-1][0], "test_users_per_s": n_test / runs[-1][1],
+                             "data_object_build_s": t_data, "recall_after_2_epochs": measure_e[3].strip()}
     if rank == 0 and not args.no_cpu_baseline:
         r, kind, what, cores = cpu_leg(D, args.workload, 8, 2)
         line["cpu_baseline"] = {"value": r["triples_per_s"], "unit": "triples/s", "cores": cores, "kind": kind,
@@ -576,6 +603,168 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
+# ------------------------------------------------------------------ scale stress (configs[4], second half)
+SCALE_SHAPES = {
+    # BASELINE.json configs[4]: "a 10M-user x 1M-item power-law graph row-partitioned across 2/4/8 B200"; the edge count is
+    # SURVEY.md 8's choice (average user degree 20).  c5b-small keeps the code path testable on a short GPU slot.
+    "c5b": (10_000_000, 1_000_000, 200_000_000, 3, 128, 2048),
+    "c5b-small": (1_000_000, 100_000, 20_000_000, 3, 128, 2048),
+}
+
+
+def run_scale_stress(args):
+    """LightGCN d = 128 on a graph built ON THE DEVICE (generator -> canonical CSR -> normalization -> work plan -> train
+    set; nothing of it exists on the host, the reference's dict-of-dicts loader cannot hold it: no CPU arm).  A full
+    epoch would be E / B = 97 657 full-graph steps, so -- as SURVEY.md 8d prescribes -- the line reports per-step and
+    per-SpMM numbers over K steps on a 64-batch sample of the epoch."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from arlib_b200 import ops
+    from arlib_b200.engine import DeviceTrainSet, LightGCNEngine
+    from arlib_b200.graph import DeviceGraph
+    from arlib_b200.util.synth import synth_edges_device
+    U, I, E, L, d, B = SCALE_SHAPES[args.workload]
+    N = U + I
+    t0 = time.perf_counter()
+    eu, ei = synth_edges_device(U, I, E, args.alpha, args.alpha, seed=0, device=dev)
+    E = int(eu.numel())
+    g = DeviceGraph.from_device_edges(eu, ei, U, I)
+    del eu, ei
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    ts = DeviceTrainSet.from_graph(g, U, I, epoch_edges=64 * B, seed=1)
+    gen = torch.Generator(device=dev).manual_seed(2018)
+    table = torch.empty((N, d), dtype=torch.float32, device=dev)
+    for lo, hi in ((0, U), (U, N)):                      # xavier_uniform per table: U(-a, a), a = sqrt(6 / (rows + d))
+        a = (6.0 / ((hi - lo) + d)) ** 0.5
+        table[lo:hi] = (torch.rand((hi - lo, d), generator=gen, device=dev) * 2 - 1) * a
+    comm = None
+    mode = os.environ.get("ARLIB_B200_DIST", "rows")      # north_star's layout is the default here
+    if world > 1:
+        from arlib_b200.dist import DistContext
+        comm = DistContext(dev)
+    eng = LightGCNEngine(g, table, U, L, LR, REG, B, ts.n_edges, comm=comm, mode=mode)
+    if eng.mode != "single":
+        del table
+    torch.cuda.empty_cache()
+    K, W = args.steps, max(args.warmup, 3)
+    nb = ts.n_edges // B
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    eng.sample_epoch(ts, 2018, 0)
+    for k in range(W):
+        eng.run_steps(k % nb, 1, use_graph=False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for k in range(K):
+            eng.run_steps((W + k) % nb, 1, use_graph=False)
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    # per-launch timing of the SpMMs of a step (event pairs; launch gaps are negligible next to ms-scale launches)
+    spmm_ms = []
+    orig = ops.spmm
+    import arlib_b200.engine as engmod
+
+    def timed_spmm(*a, **k):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(); orig(*a, **k); a1.record()
+        kind = ("row_masked" if (k.get("row_mask") is not None or k.get("worklist") is not None) else
+                "col_masked" if k.get("col_mask") is not None else "full_with_adam" if k.get("adam") is not None else "full")
+        spmm_ms.append((kind, a0, a1))
+    engmod.ops.spmm = timed_spmm
+    try:
+        for k in range(min(K, 5)):
+            eng.run_steps(k % nb, 1, use_graph=False)
+    finally:
+        engmod.ops.spmm = orig
+    torch.cuda.synchronize()
+    by_kind = {}
+    for kind, a, b_ in spmm_ms:
+        by_kind.setdefault(kind, []).append(a.elapsed_time(b_))
+    full_ms = max_over_ranks(float(np.mean(by_kind["full"])))
+    bar_us = None
+    if comm is not None:
+        for _ in range(5):
+            comm.barrier()
+        e0.record()
+        for _ in range(50):
+            comm.barrier()
+        e1.record()
+        torch.cuda.synchronize()
+        bar_us = e0.elapsed_time(e1) / 50 * 1e3
+    Tbytes = N * d * 4
+    ln, lr_ = eng.g.local_nnz, eng.g.n_local_rows
+    if eng.mode == "rows":
+        b_spmm = ln * 8 + (lr_ + 1) * 4 + Tbytes + lr_ * d * 4
+    elif eng.mode == "dshard":
+        b_spmm = g.nnz * 8 + (N + 1) * 4 + 2 * N * eng.d * 4
+    else:
+        b_spmm = g.nnz * 8 + (N + 1) * 4 + 2 * Tbytes
+    b_gather = ln * (8 + 4 * eng.d) + lr_ * eng.d * 4
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": "LightGCN train triples/s", "value": K * B / (ms * 1e-3), "unit": "triples/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "scale stress: LightGCN %d-layer d=%d BPR batch %d, power-law graph %d users x %d items, %d edges "
+                               "(alpha=%s), generated and indexed on the device" % (L, d, B, U, I, E, args.alpha),
+                   "lr": LR, "reg": REG, "sampler": "device-philox over a 64-batch sample of the epoch",
+                   "l2": "one table = %.1f GB >> the 126 MB L2: every launch streams from HBM" % (Tbytes / 1e9)},
+        "roofline": {"kernel": "spmm_csr_kernel<%d>" % eng.d, "bound": "hbm", "achieved": b_spmm / (full_ms * 1e-3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": b_spmm / (full_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": b_spmm, "avg_launch_ms": full_ms,
+                     "gather_model": {"bytes_per_launch": b_gather, "achieved": b_gather / (full_ms * 1e-3) / 1e9,
+                                      "frac": b_gather / (full_ms * 1e-3) / 1e9 / peak,
+                                      "note": "no-reuse model nnz*(8+4d)+T (SURVEY.md 8d): what HBM sees when the table does not "
+                                              "fit L2 -- can exceed the contract figure's fraction by the L2 hit rate"},
+                     "launch_ms": {k: float(np.mean(v)) for k, v in by_kind.items()}},
+        "clocks": clk.summary(),
+        "parallelism": eng.mode if world > 1 else "single GPU",
+        "comm": None if world == 1 else {
+            "layout": eng.mode,
+            "all_gather_bytes_received_per_layer_per_rank": int((world - 1) / world * Tbytes) if eng.mode == "rows" else 0,
+            "exchanges_per_step": 2 * L + 1 if eng.mode == "rows" else 1, "barrier_us": bar_us,
+            "transport": "NVSwitch multimem.st from the SpMM epilogue" if eng.mode == "rows" and eng._mc.get("F") else
+                         "NVLink P2P stores from the kernels"},
+        "graph_build_s": t_build, "gpu_launches": K * eng.launches_per_step,
+        "last_loss": float(eng.out4[(W + K - 1) % nb, 0]),
+        "cpu_baseline": {"unavailable": "the reference's dict-of-dicts DataLoader (util/DataLoader.py:32-55) cannot hold "
+                                        "%d edges; SURVEY.md 8d: reference not run at this shape" % E},
+        "hbm_gb_allocated": torch.cuda.max_memory_allocated() / 1e9,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def main():
     # everything (NCCL banners, library chatter) goes to stderr; the ONE JSON line goes to the real stdout
     global print
@@ -594,11 +783,18 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gowalla", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="gowalla", choices=sorted(WORKLOADS) + sorted(SCALE_SHAPES))
     ap.add_argument("--alpha", type=float, default=0.5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-epoch-e2e", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload in SCALE_SHAPES:
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference cannot load this shape (SURVEY.md 8d)"}))
+            return
+        run_scale_stress(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

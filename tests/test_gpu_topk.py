@@ -10,9 +10,9 @@ from oracle import port
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["1", "0"], ids=["stage2-group-major", "stage2-warp-per-user"])
+@pytest.fixture(autouse=True, params=["2", "1", "0"], ids=["stage2-group-major-items", "stage2-group-major", "stage2-warp-per-user"])
 def stage2_impl(request, monkeypatch):
-    """every test runs on both stage-2 implementations (csrc/score.cu): they must agree bit for bit"""
+    """every test runs on all three stage-2 implementations (csrc/score.cu): they must agree bit for bit"""
     monkeypatch.setenv("AGCF_STAGE2_IMPL", request.param)
     return request.param
 DEV = "cuda:0"
@@ -283,7 +283,7 @@ def test_stage2_implementations_are_bit_identical(monkeypatch):
     lists = [np.sort(rng.choice(I, rng.integers(0, 200), replace=False)) for _ in range(U)]
     mrp, mit = _mask_csr(U, lists)
     outs = {}
-    for impl2 in ("1", "0"):
+    for impl2 in ("2", "1", "0"):
         monkeypatch.setenv("AGCF_STAGE2_IMPL", impl2)
         for impl1 in (1, 0):
             outs[(impl2, impl1)] = ops.score_topk(ue, ie, K, mask_rowptr=mrp, mask_items=mit, impl=impl1, return_flags=True)
@@ -291,3 +291,33 @@ def test_stage2_implementations_are_bit_identical(monkeypatch):
     for key, got in outs.items():
         assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), key
     assert torch.equal(outs[("1", 1)][2], outs[("0", 1)][2])               # same candidate-group counts
+    assert torch.equal(outs[("2", 1)][2], outs[("0", 1)][2])
+
+
+def test_item_compacting_stage2_with_heavy_ties_and_few_free_items(monkeypatch):
+    """The default stage 2 keeps only the exact scores >= T_u per user (<= 128 entries); users it cannot hold -- exact
+    ties by the hundred, or fewer than K unmasked items so that masked -1e9 entries are wanted -- fall through to the
+    block kernel.  Every variant must return the same bits."""
+    from arlib_b200 import ops
+    rng = np.random.default_rng(21)
+    U, I, d, K = 64, 8000, 64, 50
+    ue = torch.from_numpy(rng.integers(0, 2, (U, d)).astype(np.float32)).to(DEV)        # integer scores: ties everywhere
+    ie = torch.from_numpy(rng.integers(0, 2, (I, d)).astype(np.float32)).to(DEV)
+    ue[40:] = torch.randn(U - 40, d, device=DEV)
+    lists = [np.sort(rng.choice(I, rng.integers(0, 100), replace=False)) for _ in range(U)]
+    lists[50] = np.arange(I - 10)                                                        # 10 free items < K
+    lists[51] = np.arange(3, I)
+    mrp, mit = _mask_csr(U, lists)
+    outs = {}
+    for impl2 in ("2", "1", "0"):
+        monkeypatch.setenv("AGCF_STAGE2_IMPL", impl2)
+        for impl1 in (1, 0):
+            outs[(impl2, impl1)] = ops.score_topk(ue, ie, K, mask_rowptr=mrp, mask_items=mit, impl=impl1)
+    ref = outs[("0", 0)]
+    for key, got in outs.items():
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), key
+    scores = ops.score_rows(ue, torch.arange(U, dtype=torch.int32, device=DEV), ie).cpu().numpy()
+    idx = ref[1].cpu().numpy()
+    for r in (0, 7, 39, 45, 50, 51):
+        s_ = scores[r].copy(); s_[lists[r]] = -10e8
+        assert set(idx[r].tolist()) == port.topk_reference_set(K, s_)

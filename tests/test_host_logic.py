@@ -15,15 +15,18 @@ from oracle import port
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_infonce_on_cpu_tensors_is_the_reference_expression():
-    from arlib_b200.util.loss import InfoNCE
+def test_losses_refuse_cpu_tensors():
+    """util/loss.py's CPU branch of InfoNCE contradicted "no CPU fallback" -- it now raises like every
+    other entry point; so does the fused BPR + L2 op.  (The plain torch expressions bpr_loss / l2_reg_loss stay
+    device-agnostic: attacks import them for their own tensors, attack/Black/GTA.py:205.)"""
+    from arlib_b200.util.loss import InfoNCE, bpr_l2_fused, bpr_loss, l2_reg_loss
     g = torch.Generator().manual_seed(0)
     a, b = torch.randn(40, 64, generator=g), torch.randn(40, 64, generator=g)
-    a1, b1 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    a2, b2 = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    l1, l2 = InfoNCE(a1, b1, 0.2), port.infonce(a2, b2, 0.2)
-    l1.backward(); l2.backward()
-    assert torch.equal(l1, l2) and torch.equal(a1.grad, a2.grad) and torch.equal(b1.grad, b2.grad)
+    with pytest.raises(RuntimeError):
+        InfoNCE(a, b, 0.2)
+    with pytest.raises(RuntimeError):
+        bpr_l2_fused(a, b, [0, 1], [2, 3], [4, 5], 1e-4)
+    assert torch.equal(bpr_loss(a, b, a), port.bpr_loss(a, b, a)) and torch.equal(l2_reg_loss(0.1, a, b), port.l2_reg_loss(0.1, a, b))
 
 
 def test_device_only_entry_points_refuse_cpu_tensors():
@@ -106,3 +109,29 @@ def test_fusable_adam_recognises_exactly_the_plain_optimizer_over_the_models_par
     opt = torch.optim.Adam(m.parameters(), lr=0.1)
     opt.state[m.embedding_dict['user_emb']] = {'step': torch.tensor(3.0), 'exp_avg': torch.zeros(3, 4), 'exp_avg_sq': torch.zeros(3, 4)}
     assert f(opt, m) is None
+
+
+def test_device_edge_builders_equal_the_scipy_path():
+    """The scale-stress builders (device generator -> CSR -> train set; bench.py --workload c5b) on the CPU device at a
+    small shape: the CSR built from edge tensors is bit-identical to the DataLoader formula on scipy
+    (util/DataLoader.py:57-87), and the train set read off the CSR equals the one built from edge arrays."""
+    from arlib_b200.engine import DeviceTrainSet
+    from arlib_b200.graph import DeviceGraph
+    from arlib_b200.util.synth import synth_edges_device
+    U, I, E = 700, 300, 9000
+    u, i = synth_edges_device(U, I, E, seed=3, device="cpu")
+    assert u.numel() == E and int(torch.unique(u * I + i).numel()) == E
+    assert int(torch.unique(u).numel()) == U and int(torch.unique(i).numel()) == I       # coverage edges
+    g = DeviceGraph.from_device_edges(u, i, U, I)
+    adj = port.bipartite_adjacency(u.numpy(), i.numpy(), U, I)
+    ref = port.normalize_graph_mat(adj).tocsr()
+    ref.sort_indices()
+    assert np.array_equal(g.rowptr.numpy(), ref.indptr) and np.array_equal(g.col.numpy(), ref.indices)
+    assert np.array_equal(g.val.numpy().view(np.uint32), ref.data.astype(np.float32).view(np.uint32))
+    ts = DeviceTrainSet.from_graph(g, U, I)
+    ts2 = DeviceTrainSet.from_arrays(u.numpy(), i.numpy(), U, I, "cpu")
+    assert ts.n_edges == E and torch.equal(ts.rej_rowptr, ts2.rej_rowptr) and torch.equal(ts.rej_items, ts2.rej_items)
+    pairs = set(zip(ts.e_user.tolist(), ts.e_item.tolist()))
+    assert pairs == set(zip(u.tolist(), i.tolist()))
+    sub = DeviceTrainSet.from_graph(g, U, I, epoch_edges=500, seed=1)
+    assert sub.n_edges == 500 and set(zip(sub.e_user.tolist(), sub.e_item.tolist())) <= pairs

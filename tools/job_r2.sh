@@ -9,3 +9,10 @@ tail -5 gpurun_out/r2/t1_all_tests.log
 timeout 600 python bench.py --steps 200 --warmup 5 > gpurun_out/r2/b1_n1.json 2> gpurun_out/r2/b1_n1.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/r2/b1_ref.json 2> gpurun_out/r2/b1_ref.err; echo "ref rc=$?"
 cat gpurun_out/r2/b1_n1.json | head -c 3000
+# narrow-slice SpMM: lane-group kernel vs warp-cooperative kernel, one GPU
+for D in 8 16 32; do
+  for COOP in 0 1; do
+    AGCF_SPMM_COOP=$COOP SPMM_D=$D ARLIB_B200_SEGMENT=64 timeout 300 python tools/spmm_variants.py 2>&1 | tail -1 | sed "s/^/coop=$COOP /" >> gpurun_out/r2/spmm_narrow.txt
+  done
+done
+cat gpurun_out/r2/spmm_narrow.txt
