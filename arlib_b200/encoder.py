@@ -356,8 +356,12 @@ class XSimGCL_Encoder(GraphEncoderBase):
 
 
 class NGCF_Encoder(GraphEncoderBase):
-    """recommender/NGCF.py:163-212 -- two propagations per layer on the agcf SpMM, the
-    d x d weight products are plain library GEMMs (torch.mm)."""
+    """recommender/NGCF.py:163-212.  ``forward`` (the differentiable model() attacks call, and the reference-shaped
+    training loop) runs the reference's expression on torch autograd with the two propagations per layer on the agcf
+    SpMM; ``train()`` of the recommender, when it owns the optimizer, runs the fused NGCFEngine instead (one propagation
+    per layer + the fused dense kernels of csrc/ngcf.cu).  The 2L weight matrices are views of ONE packed [L, 2d, d]
+    buffer (row block k = [W1_k ; W2_k]) -- what the fused layer multiplies with -- like the two embedding tables are
+    views of one [N, d] table."""
 
     def __init__(self, data, emb_size, n_layers):
         self.layers = n_layers
@@ -366,12 +370,37 @@ class NGCF_Encoder(GraphEncoderBase):
     def _init_model(self):
         emb = super()._init_model()
         init = nn.init.xavier_uniform_
+        d = self.latent_size
+        host = []
+        for k in range(self.layers):              # host-generator draws in the reference's order: w1_k, then w2_k
+            host.append(torch.cat([init(torch.empty(d, d)), init(torch.empty(d, d))], 0))
+        packed = (torch.stack(host, 0) if host else torch.empty(0, 2 * d, d)).to(self._device())
         w = {}
         for k in range(self.layers):
-            w['w1_' + str(k)] = nn.Parameter(init(torch.empty(self.latent_size, self.latent_size)).to(self._device()))
-            w['w2_' + str(k)] = nn.Parameter(init(torch.empty(self.latent_size, self.latent_size)).to(self._device()))
+            w['w1_' + str(k)] = nn.Parameter(packed[k, :d])
+            w['w2_' + str(k)] = nn.Parameter(packed[k, d:])
         self.W = nn.ParameterDict(w)
         return emb
+
+    def weight_table(self):
+        """The packed [L, 2d, d] tensor the 2L weight parameters are views of; re-packs them into a fresh buffer first
+        if some caller broke the sharing (deepcopy, re-assignment), keeping the Parameter objects valid."""
+        d, L = self.latent_size, self.layers
+        ps = [self.W['w%d_%d' % (a, k)] for k in range(L) for a in (1, 2)]
+        if L == 0:
+            return torch.empty((0, 2 * d, d), dtype=torch.float32, device=self._device())
+        base = ps[0].data
+        ok = all(p.data.is_contiguous() and p.data.untyped_storage().data_ptr() == base.untyped_storage().data_ptr()
+                 and p.data.storage_offset() == base.storage_offset() + q * d * d for q, p in enumerate(ps))
+        if ok:
+            out = torch.empty(0, dtype=base.dtype, device=base.device)
+            out.set_(base.untyped_storage(), base.storage_offset(), (L, 2 * d, d), (2 * d * d, d, 1))
+            return out
+        packed = torch.stack([torch.cat([self.W['w1_%d' % k].data, self.W['w2_%d' % k].data], 0) for k in range(L)], 0).contiguous()
+        for k in range(L):
+            self.W['w1_%d' % k].data = packed[k, :d]
+            self.W['w2_%d' % k].data = packed[k, d:]
+        return packed
 
     def forward(self):
         import torch.nn.functional as F

@@ -397,6 +397,18 @@ class LightGCNEngine:
         self._barrier()
 
     # ------------------------------------------------------------------ running
+    def _trained_state(self):
+        """the tensors a training step modifies (what a warm-up step before a graph capture has to put back)"""
+        return [self.E0, self.m, self.v, self.step_dev]
+
+    def _snapshot(self):
+        return [t.clone() for t in self._trained_state()]
+
+    def _restore(self, snap):
+        for t, c in zip(self._trained_state(), snap):
+            t.copy_(c)
+        self._refresh_adam_coefs()
+
     def run_steps(self, first_batch=0, n_steps=None, use_graph=True):
         """Run batches [first_batch, first_batch + n_steps) of the current epoch.
         With use_graph the launch sequence is captured once per (first, n, T) and
@@ -420,10 +432,9 @@ class LightGCNEngine:
                 # set_triples (eager) before the first run_steps, which covers both.
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                state = (self.E0.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone())
+                state = self._snapshot()
                 self._launch_step(first_batch)        # eager warm-up of every kernel in the step
-                self.E0.copy_(state[0]); self.m.copy_(state[1]); self.v.copy_(state[2]); self.step_dev.copy_(state[3])
-                self._refresh_adam_coefs()
+                self._restore(state)
                 torch.cuda.synchronize()
                 with torch.cuda.graph(g):
                     for b in range(first_batch, first_batch + n_steps):
@@ -484,7 +495,7 @@ class LightGCNEngine:
         torch.cuda.synchronize()
         main = torch.cuda.current_stream()
         side = torch.cuda.Stream()
-        state = (self.E0.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone())
+        state = self._snapshot()
         slots = []
         for k in range(n_slots):
             slots.append({"batch": k, "host": torch.zeros((3, self.B), dtype=torch.int32).pin_memory(),
@@ -514,8 +525,7 @@ class LightGCNEngine:
             with torch.cuda.graph(gs):
                 step(slot)
             slot["prep"], slot["step"] = gp, gs
-        self.E0.copy_(state[0]); self.m.copy_(state[1]); self.v.copy_(state[2]); self.step_dev.copy_(state[3])
-        self._refresh_adam_coefs()
+        self._restore(state)
         torch.cuda.synchronize()
         for slot in slots:
             slot["prep_done"].record(main)
@@ -709,3 +719,83 @@ class ContrastiveEngine(LightGCNEngine):
         rec = self.out4[first_batch:first_batch + n, 1]
         cl = self.cl_rate * self.cl_out[first_batch:first_batch + n].sum(1)
         return rec, cl
+
+
+class NGCFEngine(LightGCNEngine):
+    """Fused NGCF training step (single GPU): the body of recommender/NGCF.py:48-66 with the encoder of :197-212 as a
+    fixed kernel sequence, capturable in a CUDA graph.
+
+    Per layer ONE propagation P = A E (agcf_spmm_csr_f32; the reference runs two -- A (E W1) = (A E) W1) and one fused
+    dense kernel  E' = leaky_relu([P + E | P * E] [W1 ; W2])  that also keeps the running layer mean
+    (agcf_ngcf_dense_forward); backward mirrors it (agcf_ngcf_dense_backward: dP, the direct gradient of E and the
+    weight gradient in one pass over the rows; then A dP through the same SpMM with the direct term and the mean's share
+    as addends).  Adam on the embedding table is fused into the last backward SpMM, Adam on the 2L weight matrices is
+    one agcf_adam_step_f32 over their packed buffer ``W`` ([L, 2d, d], row block k = [W1_k ; W2_k]).
+
+    launches per step: L x (SpMM + dense) + loss fwd/bwd + L x (dense + reduce + SpMM) + W transpose + 2 optimizer."""
+
+    N_PARTIALS = 148          # persistent CTAs of the backward dense kernel (one per SM): rows of the dW partial buffer
+
+    def __init__(self, graph, table, W, n_users, lr, reg, batch_size, max_triples, betas=(0.9, 0.999), adam_eps=1e-8):
+        n_layers = int(W.shape[0])
+        d = table.shape[1]
+        if d not in (32, 64) or tuple(W.shape) != (n_layers, 2 * d, d) or not W.is_contiguous():
+            raise ValueError("NGCFEngine: d in {32, 64} and W packed as [L, 2d, d]")
+        super().__init__(graph, table, n_users, n_layers, lr, reg, batch_size, max_triples, betas=betas, adam_eps=adam_eps,
+                         sparse_layers=False)
+        f = lambda: torch.empty_like(table)
+        self.W = W
+        self.Wm, self.Wv, self.dW = torch.zeros_like(W), torch.zeros_like(W), torch.zeros_like(W)
+        self.WT = torch.empty((n_layers, d, 2 * d), dtype=torch.float32, device=table.device)
+        self.dW_partial = torch.empty((self.N_PARTIALS, 2 * d * d), dtype=torch.float32, device=table.device)
+        self.P = [f() for _ in range(self.L)]            # A E_{k-1}
+        self.Ek = [f() for _ in range(self.L)]           # layer outputs E_1 .. E_L
+        self.dP, self.dEdir = f(), f()
+        self.dOut = [f(), f()]
+        self.fuse_adam = True
+        self.launches_per_step = 5 * self.L + 6
+
+    def _trained_state(self):
+        return super()._trained_state() + [self.W, self.Wm, self.Wv]
+
+    def forward_table(self, out=None, row_mask=None, worklist=None):
+        F = self.F if out is None else out
+        x = self.E0
+        for k in range(1, self.L + 1):
+            last = k == self.L
+            ops.spmm(self.g, x, Y=self.P[k - 1])
+            ops.ngcf_dense_forward(self.P[k - 1], x, self.W[k - 1], self.Ek[k - 1], acc_in=self.E0 if k == 1 else F,
+                                   acc_out=F, acc_div=float(self.L + 1) if last else 1.0)
+            x = self.Ek[k - 1]
+        return F
+
+    def _launch_step(self, b):
+        B, L = self.B, self.L
+        t0 = b * B
+        nb = min(B, self.T - t0)
+        u, i, j = self.tu[t0:], self.ti[t0:], self.tj[t0:]
+        occ = self.occ[b * 3 * B:]
+        seg_off = self.seg_off[b * (3 * B + 1):]
+        seg_node = self.seg_node[b * 3 * B:]
+        n_seg = self.n_seg[b:]
+        out4 = self.out4[b]
+        self.WT.copy_(self.W.transpose(1, 2))
+        F = self.forward_table()
+        ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)
+        # G = dLoss/dF / (L + 1): the share every layer output (and E0) receives through the mean
+        ops.bpr_backward(F, u, i, j, nb, self.U, self.reg, 1.0 / (L + 1), out4, self.coef, occ, seg_off, seg_node, n_seg, self.G)
+        d_out = self.G
+        adam = (self.E0, self.m, self.v, self.adam_coefs, self.betas[0], self.betas[1], self.adam_eps)
+        for k in range(L, 0, -1):
+            x_prev = self.E0 if k == 1 else self.Ek[k - 2]
+            ops.ngcf_dense_backward(d_out, self.Ek[k - 1], self.P[k - 1], x_prev, self.WT[k - 1], self.dP, self.dEdir,
+                                    self.dW_partial, self.dW[k - 1])
+            if k > 1:                                    # dE_{k-1} = A dP + dE_direct + G
+                nxt = self.dOut[k % 2]
+                ops.spmm(self.g, self.dP, addend=self.dEdir, acc_in=self.G, acc_out=nxt)
+                d_out = nxt
+            else:                                        # dE_0 goes straight into Adam; the batch's rows of G are re-zeroed
+                ops.spmm(self.g, self.dP, addend=self.dEdir, acc_in=self.G, adam=adam, zero_acc_in=True)
+        ops.adam_step(self.W.view(-1), self.dW.view(-1), self.Wm.view(-1), self.Wv.view(-1), self.lr, self.betas[0],
+                      self.betas[1], self.adam_eps, step_dev=self.step_dev)
+        ops.adam_coefs(self.step_dev, self.adam_coefs, self.lr, self.betas[0], self.betas[1], increment=True)

@@ -255,6 +255,34 @@ def infonce_backward(n, d, temperature, ws, grad_loss=None, scale=1.0, n_dev=Non
                "agcf_infonce_backward")
 
 
+def ngcf_dense_forward(P, E, W, Enext, acc_in=None, acc_out=None, acc_div=1.0):
+    """agcf_ngcf_dense_forward: Enext = leaky_relu([P + E | P * E] @ W, 0.01); acc_out = (acc_in + Enext) / acc_div."""
+    for t, n in ((P, "P"), (E, "E"), (W, "W"), (Enext, "Enext"), (acc_in, "acc_in"), (acc_out, "acc_out")):
+        _f32(t, n)
+    n, d = P.shape
+    if tuple(W.shape) != (2 * d, d) or tuple(E.shape) != (n, d) or tuple(Enext.shape) != (n, d):
+        raise ValueError("NGCF layer shapes: P, E, Enext [N, d]; W [2d, d]")
+    _lib.check(_lib.load().agcf_ngcf_dense_forward(P.data_ptr(), E.data_ptr(), W.data_ptr(), Enext.data_ptr(), _p(acc_in),
+                                                   _p(acc_out), float(acc_div), n, d, _lib.stream_ptr()),
+               "agcf_ngcf_dense_forward")
+
+
+def ngcf_dense_backward(dOut, Enext, P, E, WT, dP, dEdir, dW_partial, dW):
+    """agcf_ngcf_dense_backward + agcf_ngcf_reduce_wgrad: dP, dEdir [N, d] and dW [2d, d] (dW_partial: [n_partials, 2d*d])."""
+    for t, n in ((dOut, "dOut"), (Enext, "Enext"), (P, "P"), (E, "E"), (WT, "WT"), (dP, "dP"), (dEdir, "dEdir"),
+                 (dW_partial, "dW_partial"), (dW, "dW")):
+        _f32(t, n)
+    n, d = P.shape
+    if tuple(WT.shape) != (d, 2 * d) or dW_partial.shape[1] != 2 * d * d or dW.numel() != 2 * d * d:
+        raise ValueError("NGCF backward shapes: WT [d, 2d]; dW_partial [n_partials, 2d*d]; dW [2d, d]")
+    lib = _lib.load()
+    _lib.check(lib.agcf_ngcf_dense_backward(dOut.data_ptr(), Enext.data_ptr(), P.data_ptr(), E.data_ptr(), WT.data_ptr(),
+                                            dP.data_ptr(), dEdir.data_ptr(), dW_partial.data_ptr(), dW_partial.shape[0], n, d,
+                                            _lib.stream_ptr()), "agcf_ngcf_dense_backward")
+    _lib.check(lib.agcf_ngcf_reduce_wgrad(dW_partial.data_ptr(), dW_partial.shape[0], dW.data_ptr(), d, _lib.stream_ptr()),
+               "agcf_ngcf_reduce_wgrad")
+
+
 def adam_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=0, step_dev=None, peer_p=None, mc_p=None):
     lib = _lib.load()
     _f32(p, "p"); _f32(g, "g"); _f32(m, "m"); _f32(v, "v")

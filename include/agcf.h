@@ -285,6 +285,27 @@ int agcf_infonce_backward(int32_t n, const int32_t* n_dev, int32_t d, float temp
                           float* grad_view1, const int32_t* rows1, int32_t accumulate1,
                           float* grad_view2, const int32_t* rows2, int32_t accumulate2, agcf_stream_t stream);
 
+/* ------------------------------------------------------------------ NGCF layer
+ * The dense half of an NGCF layer around the propagation P = A E (agcf_spmm_csr_f32):
+ *   forward   Enext = leaky_relu([P + E | P * E] W, 0.01), W = [W1 ; W2] ([2d, d] row-major, out = in @ W);
+ *             if acc_out: acc_out = ((acc_in ? acc_in : 0) + Enext) / acc_div   (running layer mean)
+ *   backward  dZ = dOut * (Enext > 0 ? 1 : 0.01);  [dA | dB] = dZ W^T  (WT = W transposed, [d, 2d]);
+ *             dP = dA + dB * E;  dEdir = dA + dB * P;  dW_partial[b] = this CTA's share of [P + E | P * E]^T dZ
+ *             ([n_partials][2d*d]; the launch runs n_partials persistent CTAs);
+ *             the gradient of E is then A dP + dEdir (next agcf_spmm_csr_f32, addend = dEdir);
+ *   reduce    dW = sum_b dW_partial[b] in b order (deterministic).
+ * Uses A (E W1) = (A E) W1: one propagation per layer where the reference runs two.  d in {32, 64}.
+ * Replaces: the loop body of NGCF_Encoder.forward (recommender/NGCF.py:197-212: torch.mm x 2,
+ * torch.sparse.mm x 2, leaky_relu, the element-wise product / sums) and its autograd. */
+int agcf_ngcf_dense_forward(const float* P, const float* E, const float* W, float* Enext,
+                            const float* acc_in, float* acc_out, float acc_div,
+                            int32_t n_rows, int32_t d, agcf_stream_t stream);
+int agcf_ngcf_dense_backward(const float* dOut, const float* Enext, const float* P, const float* E,
+                             const float* WT, float* dP, float* dEdir, float* dW_partial,
+                             int32_t n_partials, int32_t n_rows, int32_t d, agcf_stream_t stream);
+int agcf_ngcf_reduce_wgrad(const float* dW_partial, int32_t n_partials, float* dW, int32_t d,
+                           agcf_stream_t stream);
+
 /* ------------------------------------------------------------------ optimizer
  * torch.optim.Adam step (defaults: amsgrad=False, weight_decay=0, maximize=False)
  * over n contiguous fp32 elements:

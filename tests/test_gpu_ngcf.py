@@ -1,0 +1,116 @@
+"""GPU parity of the fused NGCF layer (csrc/ngcf.cu) and the fused NGCF training step (arlib_b200.engine.NGCFEngine)
+against the reference expression recommender/NGCF.py:197-212 (through oracle.port.ngcf_forward, which is pinned to the
+live reference by tests/golden/ml100k_ngcf.npz) and against the frozen reference epoch itself."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize("d,n", [(64, 1000), (32, 333), (64, 64), (64, 1)])
+def test_dense_layer_forward_and_backward_match_autograd(d, n):
+    """E' = leaky_relu([P + E | P * E] [W1 ; W2]) and its gradients w.r.t. P, E (direct) and W, vs torch autograd in
+    float64 of the same expression."""
+    from arlib_b200 import ops
+    gen = torch.Generator().manual_seed(n + d)
+    P = torch.randn(n, d, generator=gen) * 0.3
+    E = torch.randn(n, d, generator=gen) * 0.3
+    W = torch.randn(2 * d, d, generator=gen) / d ** 0.5
+    dOut = torch.randn(n, d, generator=gen)
+    acc = torch.randn(n, d, generator=gen)
+    Pd, Ed, Wd = (t.double().requires_grad_(True) for t in (P, E, W))
+    Z = (Pd + Ed) @ Wd[:d] + (Pd * Ed) @ Wd[d:]
+    Y = F.leaky_relu(Z, 0.01)
+    Y.backward(dOut.double())
+    Pc, Ec, Wc = P.to(DEV), E.to(DEV), W.to(DEV)
+    Yc = torch.empty_like(Pc)
+    mean = torch.empty_like(Pc)
+    ops.ngcf_dense_forward(Pc, Ec, Wc, Yc, acc_in=acc.to(DEV), acc_out=mean, acc_div=3.0)
+    assert _rel(Yc, Y.detach()) < 2e-6
+    assert _rel(mean, (acc.double() + Y.detach()) / 3.0) < 2e-6
+    dP, dE = torch.empty_like(Pc), torch.empty_like(Pc)
+    part = torch.empty((148, 2 * d * d), device=DEV)
+    dW = torch.empty((2 * d, d), device=DEV)
+    ops.ngcf_dense_backward(dOut.to(DEV), Yc, Pc, Ec, Wc.t().contiguous(), dP, dE, part, dW)
+    assert _rel(dP, Pd.grad) < 3e-6 and _rel(dE, Ed.grad) < 3e-6
+    assert _rel(dW, Wd.grad) < 3e-6
+    dW2 = torch.empty_like(dW)
+    ops.ngcf_dense_backward(dOut.to(DEV), Yc, Pc, Ec, Wc.t().contiguous(), dP, dE, part, dW2)
+    assert torch.equal(dW, dW2)                          # partials are reduced in CTA order
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_ngcf_engine_reproduces_the_reference_epoch(golden, use_graph):
+    """the frozen ml-100k epoch of the UNMODIFIED reference NGCF (same init incl. W, same triples): per-batch losses
+    2e-5, every parameter 1e-4 relative, the end-of-epoch forward 1e-4"""
+    from arlib_b200.engine import NGCFEngine
+    from arlib_b200.graph import DeviceGraph
+    g = np.load(os.path.join(GOLD, "ml100k_ngcf.npz"), allow_pickle=False)
+    U, I = golden["user_names"].shape[0], golden["item_names"].shape[0]
+    adj = port.bipartite_adjacency(golden["train_u"].astype(np.int64), golden["train_i"].astype(np.int64), U, I)
+    graph = DeviceGraph.from_dataloader_adj(adj, DEV)
+    table = torch.cat([torch.from_numpy(golden["init_user_emb"]), torch.from_numpy(golden["init_item_emb"])]).to(DEV)
+    W = torch.stack([torch.cat([torch.from_numpy(g["init_w1_%d" % k]), torch.from_numpy(g["init_w2_%d" % k])], 0)
+                     for k in range(2)], 0).contiguous().to(DEV)
+    T = golden["batch_u"].shape[0]
+    eng = NGCFEngine(graph, table, W, U, 0.005, 1e-4, 2048, T)
+    # forward of the initial parameters == the reference expression (oracle, pinned)
+    fu, fi = port.ngcf_forward(port.to_torch_coo(port.normalize_graph_mat(adj)), torch.from_numpy(golden["init_user_emb"]),
+                               torch.from_numpy(golden["init_item_emb"]),
+                               [torch.from_numpy(g["init_w1_%d" % k]) for k in range(2)],
+                               [torch.from_numpy(g["init_w2_%d" % k]) for k in range(2)])
+    F0 = eng.forward_table().clone()
+    assert _rel(F0[:U], fu) < 1e-5 and _rel(F0[U:], fi) < 1e-5
+    eng.set_triples(golden["batch_u"], golden["batch_i"], golden["batch_j"])
+    losses = eng.run_steps(0, use_graph=use_graph)[:, 0].cpu().numpy()
+    np.testing.assert_allclose(losses, g["batch_loss"], rtol=2e-5)
+    errs = {"user": _rel(table[:U], g["param_user_emb"]), "item": _rel(table[U:], g["param_item_emb"])}
+    for k in range(2):
+        errs["w1_%d" % k] = _rel(W[k, :64], g["param_w1_%d" % k])
+        errs["w2_%d" % k] = _rel(W[k, 64:], g["param_w2_%d" % k])
+    print("NGCF engine vs reference epoch:", {k: "%.1e" % v for k, v in errs.items()})
+    assert max(errs.values()) < 1e-4, errs
+    Fe = eng.forward_table(out=torch.empty_like(table))
+    assert _rel(Fe[:U], g["final_user_emb"]) < 1e-4 and _rel(Fe[U:], g["final_item_emb"]) < 1e-4
+    assert int(eng.step_dev) == len(golden["batch_len"]) and int((eng.G != 0).sum()) == 0
+
+
+def test_ngcf_class_takes_the_fused_path_and_keeps_weight_views(golden_rows):
+    import copy
+    import random
+    import types
+    from arlib_b200.recommender.NGCF import NGCF
+    from arlib_b200.util.DataLoader import DataLoader
+    train, test = golden_rows
+    data = DataLoader.from_rows([list(r) for r in train[:20000]], (), test)
+    args = types.SimpleNamespace(topK="50", emb_size=64, n_layers=2, batch_size=2048, lRate=0.005, reg=1e-4, maxEpoch=2,
+                                 seed=2018, sampler="host", model_name="NGCF")
+    random.seed(3); torch.manual_seed(3)
+    a = NGCF(args, data)
+    b = copy.deepcopy(a)                                   # deepcopy must leave a trainable object (ARLib.py:241)
+    b.args = types.SimpleNamespace(**{**vars(args), "fused": False})
+    w_before = a.model.W["w2_1"].detach().clone()
+    random.seed(5); a.train(evalNum=1)
+    assert hasattr(a, "last_train_losses") and not torch.equal(a.model.W["w2_1"].detach(), w_before)
+    random.seed(5); b.train(evalNum=1)                     # the reference-shaped loop on autograd
+    assert _rel(a.model.embedding_dict["user_emb"].detach(), b.model.embedding_dict["user_emb"].detach()) < 1e-3
+    assert _rel(a.model.W["w1_0"].detach(), b.model.W["w1_0"].detach()) < 1e-3
+    _, ma = a.test(); _, mb = b.test()
+    for x, y in zip(ma[1:], mb[1:]):
+        assert abs(float(x.split(":")[1]) - float(y.split(":")[1])) < 5e-3
+    fu, fi = a.model()                                     # model() stays differentiable on the packed weights
+    (fu.sum() + fi.sum()).backward()
+    assert a.model.W["w1_0"].grad is not None and a.model.weight_table().shape == (2, 128, 64)
