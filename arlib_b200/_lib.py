@@ -80,6 +80,7 @@ SIGNATURES = {
     "agcf_increment_i32": (c_int32, [P, P]),
     "agcf_score_topk_ws_bytes": (c_int64, [I32, I32, I32, I32]),
     "agcf_score_topk": (c_int32, [P, P, I32, P, I32, I32, P, P, I32, I32, I32, P, P, P, P, I64, P]),
+    "agcf_score_group_max": (c_int32, [P, P, I32, P, I32, I32, P, P, I32, I32, P, P, I64, P]),
     "agcf_topk_merge": (c_int32, [P, P, I32, I32, I32, P, P, P]),
     "agcf_score_rows": (c_int32, [P, P, I32, P, I32, I32, P, P]),
     "agcf_rank_metrics": (c_int32, [P, I32, P, P, P, I32, P, I32, P, P, P]),

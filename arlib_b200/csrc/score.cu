@@ -1268,10 +1268,83 @@ static WsLayout ws_layout(int n_u, int n_items, int d) {
 
 using namespace agcf;
 
+// stages 0 and 1 of agcf_score_topk: mask bits, then the masked group maxima (impl 1: tcgen05 TF32 GEMM, impl 0: fp32)
+static int run_stage01(const float* Uemb, const int32_t* user_rows, int n_u, const float* Iemb, int n_items, int d,
+                       const int32_t* mask_rowptr, const int32_t* mask_items, int item_offset, int impl, const WsLayout& L,
+                       unsigned char* base, cudaStream_t st, float* margin_out) {
+  uint32_t* bits = reinterpret_cast<uint32_t*>(base + L.bits_off);
+  float* gmax = reinterpret_cast<float*>(base + L.gmax_off);
+  float* norm = reinterpret_cast<float*>(base + L.norm_off);
+  const float4* U4 = reinterpret_cast<const float4*>(Uemb);
+  const float4* I4 = reinterpret_cast<const float4*>(Iemb);
+  *margin_out = 0.f;
+  // stage 0
+  AGCF_CUDA_OK(cudaMemsetAsync(bits, 0, (size_t)n_u * L.pitch * 4, st));
+  if (mask_rowptr != nullptr) {
+    mask_bits_kernel<<<(unsigned)((n_u + 7) / 8), 256, 0, st>>>(user_rows, n_u, mask_rowptr, mask_items, n_items, item_offset, L.pitch, bits);
+    AGCF_LAUNCH_OK();
+  }
+  // stage 1
+  if (impl == 1) {
+    AGCF_CUDA_OK(cudaMemsetAsync(norm, 0, 4, st));
+#define AGCF_NORM(DD) max_row_norm_kernel<DD><<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(I4, n_items, norm);
+    switch (d) { case 32: AGCF_NORM(32) break; case 64: AGCF_NORM(64) break; case 128: AGCF_NORM(128) break; case 256: AGCF_NORM(256) break; }
+#undef AGCF_NORM
+    AGCF_LAUNCH_OK();
+    const int rc = launch_group_max_tc(Uemb, user_rows, n_u, Iemb, n_items, d, bits, L.n_groups, L.pitch, gmax,
+                                       reinterpret_cast<float*>(base + L.udense_off), st);
+    if (rc != AGCF_OK) return rc;
+    *margin_out = 2.0f * 1.01f * 0.001953125f;      // 2 * delta, delta = 1.01 * 2^-9 * |u| * max|v|
+  } else {
+    const int n_tiles = (n_items + S1_TI - 1) / S1_TI;
+    const int u_tiles = (n_u + S1_TU - 1) / S1_TU;
+    int splits = (4 * kSMs * 3 + u_tiles - 1) / u_tiles;          // aim at >= 3 waves of 4 CTAs/SM
+    if (splits < 1) splits = 1;
+    if (splits > n_tiles) splits = n_tiles;
+    if (splits > 65535) splits = 65535;
+    const int tps = (n_tiles + splits - 1) / splits;
+    splits = (n_tiles + tps - 1) / tps;
+    dim3 grid((unsigned)u_tiles, (unsigned)splits);
+#define AGCF_S1(DD)                                                                                           \
+  {                                                                                                           \
+    AGCF_CUDA_OK(cudaFuncSetAttribute(group_max_fp32_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)S1Smem<DD>::bytes));                                               \
+    group_max_fp32_kernel<DD><<<grid, 256, S1Smem<DD>::bytes, st>>>(U4, user_rows, n_u, I4, n_items, bits,    \
+                                                                    L.n_groups, L.pitch, tps, gmax);          \
+  }
+    switch (d) { case 32: AGCF_S1(32) break; case 64: AGCF_S1(64) break; case 128: AGCF_S1(128) break; case 256: AGCF_S1(256) break; }
+#undef AGCF_S1
+    AGCF_LAUNCH_OK();
+  }
+  return AGCF_OK;
+}
+
 extern "C" int64_t agcf_score_topk_ws_bytes(int32_t n_u, int32_t n_items, int32_t d, int32_t K) {
   if (n_u < 0 || n_items <= 0 || K <= 0) return AGCF_EINVAL;
   if (!supported_d(d) || K > 1024) return AGCF_EUNSUPPORTED;
   return (int64_t)ws_layout(n_u, n_items, d).total;
+}
+
+extern "C" int agcf_score_group_max(const float* Uemb, const int32_t* user_rows, int32_t n_u,
+                                    const float* Iemb, int32_t n_items, int32_t d,
+                                    const int32_t* mask_rowptr, const int32_t* mask_items, int32_t item_offset, int32_t impl,
+                                    float* gmax_out, void* ws, int64_t ws_bytes, agcf_stream_t stream) {
+  if (!Uemb || !Iemb || !ws || n_u < 0 || n_items <= 0) return AGCF_EINVAL;
+  if ((mask_rowptr == nullptr) != (mask_items == nullptr)) return AGCF_EINVAL;
+  if (!supported_d(d) || (impl != 0 && impl != 1)) return AGCF_EUNSUPPORTED;
+  if (!aligned16(Uemb) || !aligned16(Iemb) || (reinterpret_cast<uintptr_t>(ws) & 255u)) return AGCF_EINVAL;
+  if (n_u == 0) return AGCF_OK;
+  const WsLayout L = ws_layout(n_u, n_items, d);
+  if ((int64_t)L.total > ws_bytes) return AGCF_EWORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+  float margin = 0.f;
+  const int rc = run_stage01(Uemb, user_rows, n_u, Iemb, n_items, d, mask_rowptr, mask_items, item_offset, impl, L, base, st, &margin);
+  if (rc != AGCF_OK) return rc;
+  if (gmax_out != nullptr)                                            // [n_u][n_groups] dense copy of the pitched rows
+    AGCF_CUDA_OK(cudaMemcpy2DAsync(gmax_out, (size_t)L.n_groups * 4, base + L.gmax_off, (size_t)L.pitch * 4,
+                                   (size_t)L.n_groups * 4, (size_t)n_u, cudaMemcpyDeviceToDevice, st));
+  return AGCF_OK;
 }
 
 extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int32_t n_u,
@@ -1295,44 +1368,11 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   const float4* U4 = reinterpret_cast<const float4*>(Uemb);
   const float4* I4 = reinterpret_cast<const float4*>(Iemb);
 
-  // stage 0
-  AGCF_CUDA_OK(cudaMemsetAsync(bits, 0, (size_t)n_u * L.pitch * 4, st));
-  if (mask_rowptr != nullptr) {
-    mask_bits_kernel<<<(unsigned)((n_u + 7) / 8), 256, 0, st>>>(user_rows, n_u, mask_rowptr, mask_items, n_items, item_offset, L.pitch, bits);
-    AGCF_LAUNCH_OK();
-  }
-  // stage 1
   float margin_scale = 0.f;
-  if (impl == 1) {
-    AGCF_CUDA_OK(cudaMemsetAsync(norm, 0, 4, st));
-#define AGCF_NORM(DD) max_row_norm_kernel<DD><<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(I4, n_items, norm);
-    switch (d) { case 32: AGCF_NORM(32) break; case 64: AGCF_NORM(64) break; case 128: AGCF_NORM(128) break; case 256: AGCF_NORM(256) break; }
-#undef AGCF_NORM
-    AGCF_LAUNCH_OK();
-    const int rc = launch_group_max_tc(Uemb, user_rows, n_u, Iemb, n_items, d, bits, L.n_groups, L.pitch, gmax,
-                                       reinterpret_cast<float*>(base + L.udense_off), st);
+  {
+    const int rc = run_stage01(Uemb, user_rows, n_u, Iemb, n_items, d, mask_rowptr, mask_items, item_offset, impl, L, base, st,
+                               &margin_scale);
     if (rc != AGCF_OK) return rc;
-    margin_scale = 2.0f * 1.01f * 0.001953125f;      // 2 * delta, delta = 1.01 * 2^-9 * |u| * max|v|
-  } else {
-    const int n_tiles = (n_items + S1_TI - 1) / S1_TI;
-    const int u_tiles = (n_u + S1_TU - 1) / S1_TU;
-    int splits = (4 * kSMs * 3 + u_tiles - 1) / u_tiles;          // aim at >= 3 waves of 4 CTAs/SM
-    if (splits < 1) splits = 1;
-    if (splits > n_tiles) splits = n_tiles;
-    if (splits > 65535) splits = 65535;
-    const int tps = (n_tiles + splits - 1) / splits;
-    splits = (n_tiles + tps - 1) / tps;
-    dim3 grid((unsigned)u_tiles, (unsigned)splits);
-#define AGCF_S1(DD)                                                                                           \
-  {                                                                                                           \
-    AGCF_CUDA_OK(cudaFuncSetAttribute(group_max_fp32_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                      (int)S1Smem<DD>::bytes));                                               \
-    group_max_fp32_kernel<DD><<<grid, 256, S1Smem<DD>::bytes, st>>>(U4, user_rows, n_u, I4, n_items, bits,    \
-                                                                    L.n_groups, L.pitch, tps, gmax);          \
-  }
-    switch (d) { case 32: AGCF_S1(32) break; case 64: AGCF_S1(64) break; case 128: AGCF_S1(128) break; case 256: AGCF_S1(256) break; }
-#undef AGCF_S1
-    AGCF_LAUNCH_OK();
   }
   // stage 2
   Stage2Params p;

@@ -243,7 +243,10 @@ class GraphEncoderBase(nn.Module):
         adjacency (fractional weights allowed) and make it the propagation matrix."""
         if ui_adj.dtype != 'float32':
             ui_adj = ui_adj.astype('float32')
-        self._graph = DeviceGraph.from_ui_adj(ui_adj, self._device())
+        # same pattern as the previous call (PGA's per-batch loop): the device indices, the work plan and the COO index
+        # view are re-used, only the weights are re-normalized (DeviceGraph.normalized)
+        self._graph = DeviceGraph.from_ui_adj(ui_adj, self._device(), reuse=getattr(self, "_uiadj_graph", None))
+        self._uiadj_graph = self._graph
         self._adj_tensor = None
 
     # parameters --------------------------------------------------------------

@@ -82,6 +82,7 @@ class DeviceGraph:
         self.n_local_rows = self.r1 - self.r0        # rows this graph computes (all, or one rank's partition)
         self._coo_idx = None
         self._scratch = {}
+        self._host_pattern = None                    # (indptr, indices) host copies, kept by the _init_uiAdj builder
         self._build_plan()
 
     def _build_plan(self):
@@ -183,9 +184,16 @@ class DeviceGraph:
         return cls._from_csr_host(csr, device)
 
     @classmethod
-    def normalized(cls, adj, d_row, d_col, device="cuda"):
+    def normalized(cls, adj, d_row, d_col, device="cuda", reuse=None):
         """values = fl(fl(d_row[i]*w)*d_col[j]) computed ON DEVICE from the raw
-        weights of ``adj`` (scipy, canonical CSR) and host-computed degree vectors."""
+        weights of ``adj`` (scipy, canonical CSR) and host-computed degree vectors.
+
+        ``reuse``: a graph built by an earlier call.  If the sparsity PATTERN is the same (row pointers and column
+        indices equal -- checked against host copies kept for this purpose) the new graph shares the device index
+        arrays, the SpMM work plan and the COO index view of the old one; only the weights are uploaded and
+        re-normalized.  That is the repeated ``_init_uiAdj`` of the white-box attack loops (attack/White/PGA.py:93-97:
+        once per 128-item batch, fake rows with the same dense pattern and new fractional values).  Same bits as a
+        full rebuild (the values come from the same kernel on the same inputs)."""
         csr = sp.csr_matrix(adj)
         csr.sum_duplicates()
         csr.sort_indices()
@@ -194,7 +202,15 @@ class DeviceGraph:
         dr = torch.from_numpy(np.ascontiguousarray(d_row, dtype=np.float32)).to(dev)
         dc = torch.from_numpy(np.ascontiguousarray(d_col, dtype=np.float32)).to(dev)
         val = torch.empty_like(w)
-        g = cls._from_csr_host(csr, device, values=val)
+        g = None
+        if reuse is not None and reuse._host_pattern is not None and reuse.device == dev and reuse.n_rows == csr.shape[0] \
+                and reuse.nnz == csr.nnz and reuse.r0 == 0 and reuse.r1 == reuse.n_rows:
+            hp, hi = reuse._host_pattern
+            if np.array_equal(hp, csr.indptr) and np.array_equal(hi, csr.indices):
+                g = reuse.with_values(val)
+        if g is None:
+            g = cls._from_csr_host(csr, device, values=val)
+            g._host_pattern = (csr.indptr.copy(), csr.indices.copy())
         lib = _lib.load()
         _lib.check(lib.agcf_norm_adj_csr(g.rowptr.data_ptr(), g.col.data_ptr(), w.data_ptr(), dr.data_ptr(),
                                          dc.data_ptr(), val.data_ptr(), g.n_rows, g.nnz, _lib.stream_ptr()),
@@ -202,13 +218,20 @@ class DeviceGraph:
         g.refresh_plan_values()
         return g
 
+    def with_values(self, val):
+        """A graph with the same pattern and plan (all index arrays shared) and another value array."""
+        import copy
+        g = copy.copy(self)
+        g.val = val
+        return g
+
     @classmethod
-    def from_ui_adj(cls, ui_adj, device="cuda"):
+    def from_ui_adj(cls, ui_adj, device="cuda", reuse=None):
         """``_init_uiAdj`` (recommender/LightGCN.py:212-215): 1/np.sqrt of row AND
         column sums, no inf guard, fractional weights allowed."""
         d_row = np.array((1 / np.sqrt(ui_adj.sum(1)))).flatten()
         d_col = np.array((1 / np.sqrt(ui_adj.sum(0)))).flatten()
-        return cls.normalized(ui_adj, d_row, d_col, device)
+        return cls.normalized(ui_adj, d_row, d_col, device, reuse=reuse)
 
     @classmethod
     def from_dataloader_adj(cls, adj, device="cuda"):

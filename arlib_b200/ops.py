@@ -323,6 +323,26 @@ def score_topk(user_emb, item_emb, K, user_rows=None, mask_rowptr=None, mask_ite
     return out_val, out_idx
 
 
+def score_group_max(user_emb, item_emb, user_rows=None, mask_rowptr=None, mask_items=None, item_offset=0, impl=1, n_u=None,
+                    ws=None, want_output=True):
+    """agcf_score_group_max: stages 0 + 1 of the top-K alone -> [n_u, ceil(I / 32)] masked group maxima (or None)."""
+    lib = _lib.load()
+    _f32(user_emb, "user_emb"); _f32(item_emb, "item_emb"); _i32(user_rows, "user_rows")
+    if n_u is None:
+        n_u = user_rows.numel() if user_rows is not None else user_emb.shape[0]
+    n_items, d = item_emb.shape
+    need = int(lib.agcf_score_topk_ws_bytes(n_u, n_items, d, 1))
+    if need < 0:
+        _lib.check(need, "agcf_score_topk_ws_bytes")
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=user_emb.device)
+    out = torch.empty((n_u, (n_items + 31) // 32), dtype=torch.float32, device=user_emb.device) if want_output else None
+    _lib.check(lib.agcf_score_group_max(user_emb.data_ptr(), _p(user_rows), n_u, item_emb.data_ptr(), n_items, d,
+                                        _p(mask_rowptr), _p(mask_items), int(item_offset), int(impl), _p(out), ws.data_ptr(),
+                                        ws.numel(), _lib.stream_ptr()), "agcf_score_group_max")
+    return out
+
+
 def topk_merge(vals, idx):
     """agcf_topk_merge: vals/idx [P, n_u, K] -> [n_u, K]."""
     lib = _lib.load()

@@ -447,11 +447,12 @@ def run_ours(args):
     peak = peaks.get("hbm_gbs", 6650.0)
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     achieved = b_spmm / (spmm_avg_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json"))).get(args.workload)
-    except Exception:
-        pass
+    traffic = None                       # dram bytes of one launch from the ncu --set full capture; only valid for the
+    if world == 1:                       # single-GPU full-width kernel it was captured on (null otherwise)
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "spmm_traffic.json"))).get(args.workload)
+        except Exception:
+            pass
     roofline = {"kernel": "spmm_csr_kernel<%d>" % eng.d, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": b_spmm, "avg_launch_ms": spmm_avg_ms,
@@ -526,13 +527,40 @@ def run_ours(args):
                               impl=int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1")), return_flags=True)
     cand_groups = float(cg.float().mean().item())
     flops = 2.0 * n_test * I * d
-    tpeak = peaks.get("bf16_tflops", 1590.0)
+    # the one dense contraction on its own (stage 0 + 1: mask bits, row gather, tcgen05 TF32 group-max GEMM) per user chunk
+    from arlib_b200.evaluator import USER_CHUNK
+    s1_ms = None
+    if int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1")) == 1 and world == 1:
+        Fu, Fi = F[:U].contiguous(), F[U:].contiguous()
+        chunks_u = [ev.user_rows[lo:lo + USER_CHUNK].contiguous() for lo in range(0, n_test, USER_CHUNK)]
+
+        def stage1():
+            for rows_ in chunks_u:
+                ops.score_group_max(Fu, Fi, user_rows=rows_, mask_rowptr=ev.mask_rowptr, mask_items=ev.mask_items, impl=1,
+                                    ws=ev._ws, want_output=False)
+        stage1(); stage1()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            stage1()
+        e1.record()
+        torch.cuda.synchronize()
+        s1_ms = e0.elapsed_time(e1) / 5
+    # dense TF32 peak: half the measured BF16 figure (kind::tf32 issues K = 8 per instruction where kind::f16 issues 16)
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    tf32_peak = bf16_peak / 2
     evald = {"users_per_s": n_test / (ev_ms * 1e-3), "unit": "users/s", "n_users": n_test, "ms": ev_ms,
              "e2e_users_per_s": n_test / ev_e2e_s,
              "impl": "tcgen05-tf32 + exact fp32 rescore" if int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1")) == 1 else "fp32 cuda-core",
-             "roofline": {"bound": "tensor", "achieved": flops / (ev_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
-                          "frac": flops / (ev_ms * 1e-3) / 1e12 / tpeak, "traffic": None,
-                          "note": "whole eval pipeline (mask bits + group-max GEMM + select/rescore + metrics)"},
+             "roofline": {"kernel": "group_max_tc_kernel<%d> (+ mask bits, row gather)" % d, "bound": "tensor",
+                          "achieved": None if s1_ms is None else flops / (s1_ms * 1e-3) / 1e12, "peak": tf32_peak,
+                          "unit": "TFLOP/s", "frac": None if s1_ms is None else flops / (s1_ms * 1e-3) / 1e12 / tf32_peak,
+                          "traffic": None, "ms": s1_ms,
+                          "peak_kind": "TF32 dense = measured BF16 peak / 2 (MEASURED_PEAKS.json bf16_tflops)",
+                          "pipeline_tflops": flops / (ev_ms * 1e-3) / 1e12,
+                          "note": "K = d = %d: one 128 x 256 accumulator tile is 8 MMAs (~1 024 clk) but 128 KB of TMEM to read "
+                                  "back at 64 B/clk/SM (~2 048 clk): the epilogue's TMEM read path caps the tensor pipe at ~50 %% "
+                                  "for this contraction (DESIGN.md 4.3); ncu sm__pipe_tensor_cycles_active in profiles/" % d},
              "candidate_groups_mean": cand_groups, "measure": [m.strip() for m in measure],
              "sharding": "single GPU" if world == 1 else ("user-sharded x%d, results all-gathered" % world
                                                           if eval_shard == "users" else "item-sharded x%d + top-K merge" % world)}

@@ -348,6 +348,16 @@ int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int32_t n_u,
                     float* out_val, int32_t* out_idx, int32_t* out_flags,
                     void* ws, int64_t ws_bytes, agcf_stream_t stream);
 
+/* Stages 0 + 1 of agcf_score_topk alone: gmax_out[u][g] (nullable; [n_u][ceil(n_items/32)] floats) = the maximum
+ * of the MASKED scores of user u over the 32 items of group g -- impl 1: the tcgen05 TF32 GEMM (approximate, within
+ * 1.01 * 2^-9 * |u| * max|v|), impl 0: exact fp32.  Same workspace as agcf_score_topk (agcf_score_topk_ws_bytes).
+ * The measurable unit of the one dense contraction of the path (bench.py times it on its own; tests check the TF32
+ * error bound the exactness proof of the top-K relies on). */
+int agcf_score_group_max(const float* Uemb, const int32_t* user_rows, int32_t n_u,
+                         const float* Iemb, int32_t n_items, int32_t d,
+                         const int32_t* mask_rowptr, const int32_t* mask_items, int32_t item_offset, int32_t impl,
+                         float* gmax_out, void* ws, int64_t ws_bytes, agcf_stream_t stream);
+
 /* merge P per-shard top-K lists (vals/idx: [P, n_u, K]) into one, same ordering */
 int agcf_topk_merge(const float* vals, const int32_t* idx, int32_t P, int32_t n_u, int32_t K,
                     float* out_val, int32_t* out_idx, agcf_stream_t stream);

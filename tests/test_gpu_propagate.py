@@ -312,3 +312,51 @@ def test_narrow_rows_cooperative_kernel(d, segment):
     out = out.cpu()
     torch.testing.assert_close(out[torch.from_numpy(live)], ref[torch.from_numpy(live)], rtol=1e-5, atol=2e-6)
     assert bool((out[~torch.from_numpy(live)] == 7.0).all())
+
+
+def test_init_uiadj_same_pattern_reuses_the_plan_and_is_bit_equal():
+    """SURVEY.md 8f-3 / attack/White/PGA.py:93-97: _init_uiAdj is re-entered once per 128-item batch with the same
+    pattern (dense fractional fake rows) and new weights: the device indices and the SpMM plan are re-used, the values
+    are bit-equal to a full rebuild; another pattern rebuilds."""
+    from arlib_b200.encoder import LGCN_Encoder
+    from arlib_b200.graph import DeviceGraph
+    U, I, d = 120, 150, 64
+    u, i = _rand_graph(U, I, 2500, 6)
+    data = _Data(U, I, u, i)
+    enc = LGCN_Encoder(data, d, 2)
+    rng = np.random.default_rng(1)
+    n = U + I
+
+    have = set(zip(u.tolist(), i.tolist()))
+    new_u, new_i = next((a, b) for a in range(U) for b in range(I) if (a, b) not in have)
+
+    def adjacency(weights_seed, extra=False):
+        w = np.random.default_rng(weights_seed).random(u.shape[0]).astype(np.float32)
+        w[::9] = 1e-7
+        uu, ii = (np.concatenate([u, [new_u]]), np.concatenate([i, [new_i]])) if extra else (u, i)
+        ww = np.concatenate([w, [0.5]]).astype(np.float32) if extra else w
+        half = sp.csr_matrix((ww, (uu, ii + U)), shape=(n, n), dtype=np.float32)
+        return half + half.T
+
+    a1, a2 = adjacency(1), adjacency(2)
+    enc._init_uiAdj(a1)
+    g1 = enc._graph
+    enc._init_uiAdj(a2)
+    g2 = enc._graph
+    assert g2 is not g1 and g2.vrows.data_ptr() == g1.vrows.data_ptr() and g2.col.data_ptr() == g1.col.data_ptr()
+    full = DeviceGraph.from_ui_adj(a2, _dev())
+    assert torch.equal(g2.val, full.val) and not torch.equal(g2.val, g1.val)
+    ref = port.to_torch_coo(port.init_uiadj_norm(a2)).coalesce()
+    assert np.array_equal(g2.val.cpu().numpy().view(np.uint32), ref.values().numpy().view(np.uint32))
+    X = torch.randn(n, d, device=_dev())
+    Y1, Y2 = torch.empty_like(X), torch.empty_like(X)
+    from arlib_b200 import ops
+    ops.spmm(g2, X, Y=Y1); ops.spmm(full, X, Y=Y2)
+    assert torch.equal(Y1, Y2)
+    enc.sparse_norm_adj.requires_grad = True               # the COO view follows the new values
+    assert torch.equal(enc.sparse_norm_adj.coalesce().values().detach(), g2.val)
+    a3 = adjacency(3, extra=True)                          # one more edge: another pattern -> rebuilt
+    enc._init_uiAdj(a3)
+    assert enc._graph.nnz == g2.nnz + 2 and enc._graph.vrows.data_ptr() != g2.vrows.data_ptr()
+    full3 = DeviceGraph.from_ui_adj(a3, _dev())
+    assert torch.equal(enc._graph.val, full3.val) and torch.equal(enc._graph.col, full3.col)

@@ -321,3 +321,27 @@ def test_item_compacting_stage2_with_heavy_ties_and_few_free_items(monkeypatch):
     for r in (0, 7, 39, 45, 50, 51):
         s_ = scores[r].copy(); s_[lists[r]] = -10e8
         assert set(idx[r].tolist()) == port.topk_reference_set(K, s_)
+
+
+def test_group_max_stage_alone_and_the_tf32_error_bound():
+    """agcf_score_group_max: stage 1 on its own.  impl 0 equals the masked fp32 group maxima of the exact scores bit for
+    bit; impl 1 (tcgen05 TF32) stays within delta = 1.01 * 2^-9 * |u| * max|v| of them -- the premise of the top-K
+    exactness proof in csrc/score.cu."""
+    from arlib_b200 import ops
+    rng = np.random.default_rng(4)
+    U, I, d = 300, 5000, 64
+    ue = torch.from_numpy(rng.standard_normal((U, d)).astype(np.float32)).to(DEV)
+    ie = torch.from_numpy((rng.standard_normal((I, d)) * (1 + 2 * rng.random((I, 1)) ** 3)).astype(np.float32)).to(DEV)
+    lists = [np.sort(rng.choice(I, rng.integers(0, 80), replace=False)) for _ in range(U)]
+    mrp, mit = _mask_csr(U, lists)
+    g0 = ops.score_group_max(ue, ie, mask_rowptr=mrp, mask_items=mit, impl=0)
+    g1 = ops.score_group_max(ue, ie, mask_rowptr=mrp, mask_items=mit, impl=1)
+    exact = ops.score_rows(ue, torch.arange(U, dtype=torch.int32, device=DEV), ie)
+    for r, l in enumerate(lists):
+        exact[r, torch.from_numpy(l.astype(np.int64)).to(DEV)] = -1.0e9
+    pad = (-I) % 32
+    ref = torch.cat([exact, torch.full((U, pad), -3.4e38, device=DEV)], 1).view(U, -1, 32).max(2).values
+    assert g0.shape == ref.shape and torch.equal(g0, ref)
+    delta = 1.01 * 2.0 ** -9 * ue.norm(dim=1, keepdim=True) * ie.norm(dim=1).max()
+    assert bool(((g1 - ref).abs() <= delta).all())
+    assert float((g1 - ref).abs().max()) > 0                     # it IS approximate: stage 2 is what makes the result exact
