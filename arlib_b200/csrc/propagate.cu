@@ -699,8 +699,11 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
   if (blocks > 0x7fffffffLL) return AGCF_EUNSUPPORTED;
   const bool cmask = p.col_mask != nullptr && p.noise == nullptr && !p.noise_main && p.aux_Y[0] == nullptr && p.aux_Y[1] == nullptr;
   if constexpr (D <= 16) {
-    // narrow column slices: the warp-cooperative scheme (AGCF_SPMM_COOP=0 keeps the lane-group kernel for A/B runs)
-    static const bool coop = [] { const char* e = getenv("AGCF_SPMM_COOP"); return e == nullptr || atoi(e) != 0; }();
+    // narrow column slices: the warp-cooperative scheme, OFF by default (AGCF_SPMM_COOP=1 selects it).  Measured on B200
+    // at the Gowalla shape (profiles/r2_summary.md): 31.0 vs 26.7 us at d = 8, 35.0 vs 24.8 us at d = 16 -- it does cut
+    // the L1 wavefronts per non-zero, but a warp now walks its 16 items one after the other, and with ~1 wave of CTAs per
+    // launch the launch lasts as long as that serial chain of 16 dependent index -> gather -> reduce round trips.
+    static const bool coop = [] { const char* e = getenv("AGCF_SPMM_COOP"); return e != nullptr && atoi(e) != 0; }();
     if (coop && p.sched == nullptr && (p.col_mask == nullptr || cmask)) {
       const bool noise = p.noise != nullptr || p.noise_main || p.aux_Y[0] != nullptr || p.aux_Y[1] != nullptr;
       if (cmask) {

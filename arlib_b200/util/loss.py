@@ -41,7 +41,7 @@ class _BprL2(torch.autograd.Function):
         dev = F_.device
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
         coef = torch.empty(max(nb, 1), dtype=torch.float32, device=dev)
-        ws = torch.empty(ops.bpr_ws_bytes(nb), dtype=torch.uint8, device=dev)
+        ws = torch.zeros(ops.bpr_ws_bytes(nb), dtype=torch.uint8, device=dev)      # its ticket word must be 0 on entry
         ops.bpr_forward(F_, u, i, j, nb, n_users, float(reg), out4, coef, ws)
         ctx.save_for_backward(F_, u, i, j, out4, coef)
         ctx.reg, ctx.n_users = float(reg), n_users

@@ -452,12 +452,14 @@ class SimGCLTrainer(_BprTrainerBase):
     positive items.  ``noise()`` returns the next U[0,1) tensor [N, d] (the reference calls torch.rand_like once per
     perturbed layer, pass 1 layers 1..L then pass 2 layers 1..L)."""
 
-    def __init__(self, norm_adj, user_emb, item_emb, n_layers, eps, cl_rate, lr, reg, noise, tau=0.2):
-        self.adj = to_torch_coo(norm_adj)
-        self.user_emb = torch.nn.Parameter(user_emb.clone())
-        self.item_emb = torch.nn.Parameter(item_emb.clone())
+    def __init__(self, norm_adj, user_emb, item_emb, n_layers, eps, cl_rate, lr, reg, noise, tau=0.2, dtype=torch.float32):
+        # dtype = float64: the same loop in double precision -- the yardstick for how well conditioned "parameters after
+        # an epoch of Adam" is (tests); the reference itself is float32
+        self.adj = to_torch_coo(norm_adj).to(dtype)
+        self.user_emb = torch.nn.Parameter(user_emb.clone().to(dtype))
+        self.item_emb = torch.nn.Parameter(item_emb.clone().to(dtype))
         self.n_layers, self.eps, self.cl_rate, self.reg, self.tau = n_layers, eps, cl_rate, reg, tau
-        self.noise = noise
+        self.noise = (lambda: noise().to(dtype)) if dtype != torch.float32 else noise
         self.opt = torch.optim.Adam([self.user_emb, self.item_emb], lr=lr)
 
     def forward(self, perturbed=False):
@@ -480,12 +482,14 @@ class XSimGCLTrainer(_BprTrainerBase):
     """recommender/XSimGCL.py:46-80 with XSimGCL_Encoder.forward (:205-223) and cal_cl_loss (:39-44): ONE perturbed
     pass gives the rec view and the layer_cl view; InfoNCE(tau = 0.1)."""
 
-    def __init__(self, norm_adj, user_emb, item_emb, n_layers, eps, cl_rate, layer_cl, lr, reg, noise, tau=0.1):
-        self.adj = to_torch_coo(norm_adj)
-        self.user_emb = torch.nn.Parameter(user_emb.clone())
-        self.item_emb = torch.nn.Parameter(item_emb.clone())
+    def __init__(self, norm_adj, user_emb, item_emb, n_layers, eps, cl_rate, layer_cl, lr, reg, noise, tau=0.1,
+                 dtype=torch.float32):
+        self.adj = to_torch_coo(norm_adj).to(dtype)
+        self.user_emb = torch.nn.Parameter(user_emb.clone().to(dtype))
+        self.item_emb = torch.nn.Parameter(item_emb.clone().to(dtype))
         self.n_layers, self.eps, self.cl_rate, self.layer_cl = n_layers, eps, cl_rate, layer_cl
-        self.reg, self.tau, self.noise = reg, tau, noise
+        self.reg, self.tau = reg, tau
+        self.noise = (lambda: noise().to(dtype)) if dtype != torch.float32 else noise
         self.opt = torch.optim.Adam([self.user_emb, self.item_emb], lr=lr)
 
     def forward(self, perturbed=False):
