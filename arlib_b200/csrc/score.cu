@@ -920,80 +920,104 @@ __global__ void __launch_bounds__(256) s2_select_kernel(const Stage2Params p) {
 // kernel like the candidate-group overflows.  Bit-identical results (tests run all stage-2 variants).
 constexpr int kS2ItemCap = 128;
 
+// Re-scoring as a register-tiled product: a CTA owns (group, slice) and walks the group's users in tiles of 128.  The
+// group's 32 item rows and the tile's 128 user rows are staged in shared memory; thread (tu, ti) computes a 4 x 4 block
+// of (user, item) scores: per float4 step of k it reads 4 + 4 vectors and issues 64 FMAs (the warp-per-pair
+// kernel above reads 5 vectors per 16 FMAs and sits on the shared-memory bandwidth).  Every score is still ONE chain
+// acc = fmaf(u[k], v[k], acc), k ascending from 0 -- the bits of exact_dot.
+constexpr int kS2TU = 128;                 // users per tile
+
 template <int D>
 __global__ void __launch_bounds__(256) s2_rescore_items_kernel(const Stage2Params p) {
   constexpr int LD = D + 4, V4 = D / 4;
   extern __shared__ __align__(16) unsigned char dyn[];
-  float* tile = reinterpret_cast<float*>(dyn);                       // [32][LD]
-  float* urow_all = tile + kGroup * LD;                              // [8 warps][PB][D]
+  float* tile = reinterpret_cast<float*>(dyn);                       // [32][LD] item rows of the group
+  float* urows = tile + kGroup * LD;                                 // [kS2TU][LD] user rows of the tile
+  int* u_r = reinterpret_cast<int*>(urows + kS2TU * LD);             // [kS2TU] user position r (-1: none)
+  uint32_t* u_word = reinterpret_cast<uint32_t*>(u_r + kS2TU);       // [kS2TU] train-item mask word of (user, group)
+  float* u_keep = reinterpret_cast<float*>(u_word + kS2TU);          // [kS2TU] T_u
   const int g = blockIdx.x, slice = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
   const int cnt = p.g_count[g];
-  if (slice * 8 >= cnt) return;
+  if (slice * kS2TU >= cnt) return;                                  // nothing for this slice (uniform per CTA)
   const int32_t* my_pairs = p.pairs + (size_t)g * p.n_u;
   const int rows_here = min(kGroup, p.n_items - g * kGroup);
   const float4* src = p.Iemb + (size_t)g * kGroup * V4;
-  for (int f = threadIdx.x; f < kGroup * V4; f += 256) {
+  for (int f = tid; f < kGroup * V4; f += 256) {
     const int row = f / V4, c4 = f - row * V4;
     const float4 v = row < rows_here ? __ldg(src + f) : make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(tile + row * LD + 4 * c4) = v;
   }
-  __syncthreads();
-  constexpr int PB = AGCF_S2_PB;
-  float* urows = urow_all + warp * PB * D;
-  const float* mine_row = tile + lane * LD;
-  const int stride = kS2Slices * 8;
-  const unsigned int lt_mask = (1u << lane) - 1u;
-  for (int q0 = slice * 8 + warp; q0 < cnt; q0 += PB * stride) {
-    int pr[PB];
-    uint32_t word[PB];
-    float keep_from[PB];
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < PB; ++j) {
-      const int q = q0 + j * stride;
-      pr[j] = q < cnt ? my_pairs[q] : -1;
-      word[j] = 0u;
-      keep_from[j] = 0.f;
-      if (pr[j] >= 0) {
-        const int r = pr[j] >> 8;
-        const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
-        for (int k = lane; k < V4; k += 32) reinterpret_cast<float4*>(urows + j * D)[k] = __ldg(p.Uemb + (size_t)uid * V4 + k);
-        word[j] = __ldg(p.bits + (size_t)r * p.pitch + g);
-        keep_from[j] = __ldg(p.u_thr + r);
+  // thread (tu, ti): users tu + 32 a, items ti + 8 b (a, b < 4) -- the threads of a warp read CONSECUTIVE tile rows, whose
+  // stride of LD = D + 4 floats puts them 4 banks apart: conflict-free LDS.128
+  const int tu = tid >> 3, ti = tid & 7;
+  for (int t0 = slice * kS2TU; t0 < cnt; t0 += kS2Slices * kS2TU) {
+    __syncthreads();                                                 // the previous tile's rows are no longer read
+    if (tid < kS2TU) {
+      const int q = t0 + tid;
+      int r = -1;
+      uint32_t word = 0u;
+      float keep_from = 0.f;
+      if (q < cnt) {
+        r = my_pairs[q] >> 8;
+        word = __ldg(p.bits + (size_t)r * p.pitch + g);
+        keep_from = __ldg(p.u_thr + r);
       }
+      u_r[tid] = r; u_word[tid] = word; u_keep[tid] = keep_from;
     }
-    __syncwarp();
-    float sc[PB];
+    for (int f = tid; f < kS2TU * V4; f += 256) {
+      const int row = f / V4, c4 = f - row * V4;
+      const int q = t0 + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < cnt) {
+        const int r = my_pairs[q] >> 8;
+        const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
+        v = __ldg(p.Uemb + (size_t)uid * V4 + c4);
+      }
+      *reinterpret_cast<float4*>(urows + row * LD + 4 * c4) = v;
+    }
+    __syncthreads();
+    float acc[4][4];
 #pragma unroll
-    for (int j = 0; j < PB; ++j) sc[j] = 0.f;
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
 #pragma unroll 4
     for (int k4 = 0; k4 < V4; ++k4) {
-      const float4 v = *reinterpret_cast<const float4*>(mine_row + 4 * k4);
+      float4 uv[4], iv[4];
 #pragma unroll
-      for (int j = 0; j < PB; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(urows + j * D + 4 * k4);
-        sc[j] = fmaf(w.x, v.x, sc[j]);
-        sc[j] = fmaf(w.y, v.y, sc[j]);
-        sc[j] = fmaf(w.z, v.z, sc[j]);
-        sc[j] = fmaf(w.w, v.w, sc[j]);
-      }
+      for (int a = 0; a < 4; ++a) uv[a] = *reinterpret_cast<const float4*>(urows + (tu + 32 * a) * LD + 4 * k4);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) iv[b] = *reinterpret_cast<const float4*>(tile + (ti + 8 * b) * LD + 4 * k4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          float s_ = acc[a][b];
+          s_ = fmaf(uv[a].x, iv[b].x, s_);
+          s_ = fmaf(uv[a].y, iv[b].y, s_);
+          s_ = fmaf(uv[a].z, iv[b].z, s_);
+          s_ = fmaf(uv[a].w, iv[b].w, s_);
+          acc[a][b] = s_;
+        }
     }
 #pragma unroll
-    for (int j = 0; j < PB; ++j) {
-      if (pr[j] < 0) continue;                                       // warp-uniform
-      float v = sc[j];
-      if ((word[j] >> lane) & 1u) v = kMasked;
-      const bool keep = lane < rows_here && v >= keep_from[j];
-      const unsigned int b = __ballot_sync(0xffffffffu, keep);
-      if (b == 0u) continue;
-      const int r = pr[j] >> 8;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(p.u_cnt + r, __popc(b));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (keep) {
-        const int pos = base + __popc(b & lt_mask);
-        if (pos < p.cap_items) p.u_items[(size_t)r * p.cap_items + pos] = make_int2(g * kGroup + lane, __float_as_int(v));
+    for (int a = 0; a < 4; ++a) {
+      const int lu = tu + 32 * a;
+      const int r = u_r[lu];
+      if (r < 0) continue;
+      const uint32_t word = u_word[lu];
+      const float keep_from = u_keep[lu];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int it = ti + 8 * b;
+        if (it >= rows_here) continue;
+        float v = acc[a][b];
+        if ((word >> it) & 1u) v = kMasked;
+        if (v >= keep_from) {                                        // ~3 % of the scores survive
+          const int pos = atomicAdd(p.u_cnt + r, 1);
+          if (pos < p.cap_items) p.u_items[(size_t)r * p.cap_items + pos] = make_int2(g * kGroup + it, __float_as_int(v));
+        }
       }
     }
   }
@@ -1423,11 +1447,12 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_select_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel)); \
     s2_candidates_kernel<DD><<<warp_grid, 256, 0, st>>>(p);                                                      \
     if (items) {                                                                                                 \
-      if (dyn_r > 48 * 1024)                                                                                     \
-        AGCF_CUDA_OK(cudaFuncSetAttribute(s2_rescore_items_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_r)); \
+      const size_t dyn_ri = ((size_t)(kGroup + kS2TU) * (DD + 4) + 3 * kS2TU) * 4;   /* item tile + user tile + per-user words */ \
+      if (dyn_ri > 48 * 1024)                                                                                    \
+        AGCF_CUDA_OK(cudaFuncSetAttribute(s2_rescore_items_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_ri)); \
       if (dyn_sel_items > 48 * 1024)                                                                             \
         AGCF_CUDA_OK(cudaFuncSetAttribute(s2_select_items_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel_items)); \
-      s2_rescore_items_kernel<DD><<<dim3((unsigned)L.n_groups, kS2Slices), 256, dyn_r, st>>>(p);                 \
+      s2_rescore_items_kernel<DD><<<dim3((unsigned)L.n_groups, kS2Slices), 256, dyn_ri, st>>>(p);                \
       s2_select_items_kernel<DD><<<warp_grid, 256, dyn_sel_items, st>>>(p);                                      \
     } else {                                                                                                     \
       s2_rescore_kernel<DD><<<dim3((unsigned)L.n_groups, kS2Slices), 256, dyn_r, st>>>(p);                       \

@@ -88,10 +88,14 @@ def test_ngcf_engine_reproduces_the_reference_epoch(golden, use_graph):
     assert int(eng.step_dev) == len(golden["batch_len"]) and int((eng.G != 0).sum()) == 0
 
 
-def test_ngcf_class_takes_the_fused_path_and_keeps_weight_views(golden_rows):
+def test_ngcf_class_takes_the_fused_path_and_keeps_weight_views(golden_rows, monkeypatch):
+    """two epochs through the drop-in class on a 20 000-row subset: the fused engine (default) and the reference-shaped
+    loop (args.fused = False, after a deepcopy that un-packs the weight views) both follow the oracle's loop
+    (oracle.port.NGCFTrainer on the very batches the host sampler produced)"""
     import copy
     import random
     import types
+    import arlib_b200.util.sampler as sampler_mod
     from arlib_b200.recommender.NGCF import NGCF
     from arlib_b200.util.DataLoader import DataLoader
     train, test = golden_rows
@@ -102,12 +106,31 @@ def test_ngcf_class_takes_the_fused_path_and_keeps_weight_views(golden_rows):
     a = NGCF(args, data)
     b = copy.deepcopy(a)                                   # deepcopy must leave a trainable object (ARLib.py:241)
     b.args = types.SimpleNamespace(**{**vars(args), "fused": False})
-    w_before = a.model.W["w2_1"].detach().clone()
+    init = {n: p.detach().cpu().clone() for n, p in a.model.named_parameters()}
+    norm_adj = data.norm_adj.copy()
+    batches = []
+    real = sampler_mod.next_batch_pairwise
+
+    def recording(d, bs):
+        for bt in real(d, bs):
+            batches.append(tuple(list(x) for x in bt))
+            yield bt
+    monkeypatch.setattr(sampler_mod, "next_batch_pairwise", recording)
     random.seed(5); a.train(evalNum=1)
-    assert hasattr(a, "last_train_losses") and not torch.equal(a.model.W["w2_1"].detach(), w_before)
+    seen_a = list(batches)
+    del batches[:]
     random.seed(5); b.train(evalNum=1)                     # the reference-shaped loop on autograd
-    assert _rel(a.model.embedding_dict["user_emb"].detach(), b.model.embedding_dict["user_emb"].detach()) < 1e-3
-    assert _rel(a.model.W["w1_0"].detach(), b.model.W["w1_0"].detach()) < 1e-3
+    assert hasattr(a, "last_train_losses") and len(seen_a) == len(batches) == 20
+    assert all(x == y for x, y in zip(seen_a, batches))    # same seed, same in-place shuffles: the same triples
+    tr = port.NGCFTrainer(norm_adj, init["embedding_dict.user_emb"], init["embedding_dict.item_emb"],
+                          [init["W.w1_%d" % k] for k in range(2)], [init["W.w2_%d" % k] for k in range(2)], 0.005, 1e-4)
+    for bt in seen_a:
+        tr.step(*bt)
+    for name, rec in (("fused", a), ("reference-shaped", b)):
+        eu = _rel(rec.model.embedding_dict["user_emb"].detach(), tr.user_emb.detach())
+        ew = _rel(rec.model.W["w1_0"].detach(), tr.w1[0].detach())
+        print("NGCF class, 2 epochs, %s path vs oracle: user %.2e w1_0 %.2e" % (name, eu, ew))
+        assert eu < 1e-4 and ew < 1e-4, name
     _, ma = a.test(); _, mb = b.test()
     for x, y in zip(ma[1:], mb[1:]):
         assert abs(float(x.split(":")[1]) - float(y.split(":")[1])) < 5e-3
