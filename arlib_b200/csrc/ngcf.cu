@@ -128,7 +128,7 @@ struct BwdSmem {
 };
 
 template <int D>
-__global__ void __launch_bounds__(256, 1) dense_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Enext,
+__global__ void __launch_bounds__(256, 2) dense_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ Enext,
                                                            const float* __restrict__ P, const float* __restrict__ E,
                                                            const float* __restrict__ WT, float* __restrict__ dP,
                                                            float* __restrict__ dEdir, float* __restrict__ dWpart, int N) {

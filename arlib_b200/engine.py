@@ -734,7 +734,7 @@ class NGCFEngine(LightGCNEngine):
 
     launches per step: L x (SpMM + dense) + loss fwd/bwd + L x (dense + reduce + SpMM) + W transpose + 2 optimizer."""
 
-    N_PARTIALS = 148          # persistent CTAs of the backward dense kernel (one per SM): rows of the dW partial buffer
+    N_PARTIALS = 296          # persistent CTAs of the backward dense kernel (two per SM): rows of the dW partial buffer
 
     def __init__(self, graph, table, W, n_users, lr, reg, batch_size, max_triples, betas=(0.9, 0.999), adam_eps=1e-8):
         n_layers = int(W.shape[0])

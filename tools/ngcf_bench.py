@@ -45,7 +45,7 @@ def t(fn, n=50):
     return e0.elapsed_time(e1) / n * 1e3
 fwd_us = t(lambda: ops.ngcf_dense_forward(P, X, W[0], Y))
 dP, dE = torch.empty_like(P), torch.empty_like(P)
-part, dW = torch.empty((148, 2 * d * d), device=dev), torch.empty((2 * d, d), device=dev)
+part, dW = torch.empty((296, 2 * d * d), device=dev), torch.empty((2 * d, d), device=dev)
 WT = W[0].t().contiguous()
 bwd_us = t(lambda: ops.ngcf_dense_backward(P, Y, P, X, WT, dP, dE, part, dW))
 spmm_us = t(lambda: ops.spmm(g, X, Y=Y))
