@@ -306,6 +306,8 @@ struct Stage2Params {
   int32_t* u_cnt;              // [n_u] kept (item, score) entries (zeroed by the caller); > cap_items = overflow
   int2* u_items;               // [n_u][cap_items] {item, score bits}, unordered
   int cap_items;
+  const float4* Udense;        // nullable: the user rows gathered for the tcgen05 stage 1 ([n_u][D], row r = user r of the
+                               // call) -- the same bits as Uemb[user_rows[r]] without the index hop
 };
 
 template <int D>
@@ -971,8 +973,12 @@ __global__ void __launch_bounds__(256) s2_rescore_items_kernel(const Stage2Param
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (q < cnt) {
         const int r = my_pairs[q] >> 8;
-        const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
-        v = __ldg(p.Uemb + (size_t)uid * V4 + c4);
+        if (p.Udense != nullptr) {
+          v = __ldg(p.Udense + (size_t)r * V4 + c4);
+        } else {
+          const int uid = p.user_rows != nullptr ? p.user_rows[r] : r;
+          v = __ldg(p.Uemb + (size_t)uid * V4 + c4);
+        }
       }
       *reinterpret_cast<float4*>(urows + row * LD + 4 * c4) = v;
     }
@@ -1419,6 +1425,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   p.g_count = reinterpret_cast<int32_t*>(base + L.gcount_off);
   p.pairs = reinterpret_cast<int32_t*>(base + L.pairs_off);
   p.u_thr = nullptr; p.u_cnt = nullptr; p.u_items = nullptr; p.cap_items = kS2ItemCap;
+  p.Udense = (impl == 1 && user_rows != nullptr && d <= 128) ? reinterpret_cast<const float4*>(base + L.udense_off) : nullptr;
   int kpow2 = 1;
   while (kpow2 < K) kpow2 <<= 1;
   const size_t dyn = (size_t)kpow2 * 8;
