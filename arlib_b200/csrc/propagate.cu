@@ -399,35 +399,6 @@ __device__ __forceinline__ void spmm_accumulate_masked(const SpmmParams& p, int 
   }
 }
 
-// Sum of a row's partial sums in segment order (deterministic).  The partials of a batch of segments are loaded TOGETHER
-// and then added in order: one load per iteration made a hub row's combine a chain of nseg dependent L2 round trips -- 52 x
-// ~800 cycles for the 3 318-entry row of the Gowalla-shaped graph cut into 64-entry segments, which alone set the ~27 us
-// floor under every narrow-slice launch (ncu: sm__cycles_active max 52 k of 60 k cycles, profiles/r2_summary.md).  Not
-// inlined: the batch of landing registers must not raise the register allocation of the gather loop.
-template <typename C>
-__device__ __noinline__ void spmm_combine_partials(const float4* __restrict__ base, int nseg, int gl, float4 (&acc)[C::VPL]) {
-  constexpr int NB = C::VPL == 1 ? 8 : (C::VPL == 2 ? 4 : 2);
-#pragma unroll
-  for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int kk = 0; kk < nseg; kk += NB) {
-    float4 part[NB][C::VPL];
-#pragma unroll
-    for (int q = 0; q < NB; ++q) {
-      const int ks = kk + q < nseg ? kk + q : nseg - 1;            // clamp: the surplus loads are discarded below
-      const float4* src = base + (size_t)ks * C::V4;
-#pragma unroll
-      for (int v = 0; v < C::VPL; ++v) part[q][v] = __ldcg(src + v * C::LPR + gl);
-    }
-#pragma unroll
-    for (int q = 0; q < NB; ++q) {
-      if (kk + q < nseg) {
-#pragma unroll
-        for (int v = 0; v < C::VPL; ++v) acc[v] = add4(acc[v], part[q][v]);
-      }
-    }
-  }
-}
-
 // the end of a work item, shared by the two accumulation schemes below: rows cut into several segments combine
 // through the partial-sum scratch (every segment stores its partial sum, the one that arrives last -- a ticket per
 // row -- adds them in segment order: deterministic, no floating-point atomics), then the fused epilogue
@@ -453,7 +424,13 @@ __device__ __forceinline__ void spmm_finish_item(const SpmmParams& p, bool valid
       do_epilogue = old == nseg - 1;                       // the last segment to arrive finishes the row
       if (do_epilogue) {
         __threadfence();
-        spmm_combine_partials<C>(p.partial + (size_t)pb * C::V4, nseg, gl, acc);
+#pragma unroll
+        for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kk = 0; kk < nseg; ++kk) {                // segment order: deterministic
+          const float4* part = p.partial + ((size_t)pb + kk) * C::V4;
+#pragma unroll
+          for (int v = 0; v < C::VPL; ++v) acc[v] = add4(acc[v], __ldcg(part + v * C::LPR + gl));
+        }
         if (gl == 0) p.tickets[pb] = 0;                    // ready for the next launch
       }
     }
