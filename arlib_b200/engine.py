@@ -214,6 +214,7 @@ class LightGCNEngine:
         # per-batch work lists: the last forward layer runs the batch's own plan (its <= 3B rows cut into short
         # segments) instead of testing every item of the static plan against the bitmap
         self.wl = None
+        self.wl_segment = 32 if self.d <= 8 else self.WL_SEGMENT          # narrow slices: shorter items (graph.default_segment)
         if self.sparse_layers and flag("ARLIB_B200_WORKLISTS"):
             self._init_worklists(nbmax, dev)
         # Adam fused into the epilogue of the last backward SpMM (own rows == all rows: not in "rows" mode,
@@ -239,7 +240,7 @@ class LightGCNEngine:
         g = self.g
         rp = g.rowptr.long()
         deg = rp[g.r0 + 1:g.r1 + 1] - rp[g.r0:g.r1]
-        seg = self.WL_SEGMENT
+        seg = self.wl_segment
         nseg = torch.where(deg > seg, (deg + seg - 1) // seg, torch.ones_like(deg))
         if nseg.numel() == 0 or int(nseg.max()) >= (1 << 15):
             return
@@ -316,7 +317,7 @@ class LightGCNEngine:
             nb = (n + self.B - 1) // self.B
             w = self.wl
             ops.spmm_batch_worklists(self.seg_node[b0 * 3 * self.B:], self.n_seg[b0:], nb, 3 * self.B, self.g.rowptr,
-                                     self.g.r0, self.g.r1, self.WL_SEGMENT, self.WL_SEGMENT,
+                                     self.g.r0, self.g.r1, self.wl_segment, self.wl_segment,
                                      w["vrows"][b0:], w["vpart"][b0:], w["count"][b0:])
 
     # --------------------------------------------------------------- one step

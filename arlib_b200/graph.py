@@ -35,7 +35,9 @@ PERSISTENT_ENV = os.environ.get("ARLIB_B200_PERSISTENT", "0")
 
 def default_segment(local_nnz, d=64):
     """(split_above, segment): rows with more than split_above non-zeros are cut into segments of `segment`."""
-    if d <= 32:
+    if d <= 8:
+        seg = 32          # d = 8 column slices (8 GPUs): 23.6 us per full launch vs 26.7 us with 64 (profiles/r2_summary.md)
+    elif d <= 32:
         seg = 64
     elif local_nnz >= 1_500_000:
         seg = 256
