@@ -188,7 +188,7 @@ struct BprWs {                 // layout of the workspace
 // double accumulators and writes out4 = {loss, bpr term, ||F[u_.]||_F, ||F[i_.]||_F}.  Deterministic.
 template <int NRED>
 __device__ __forceinline__ void bpr_finalize(float (&red)[3][NRED], int nb, float reg, float* __restrict__ out4,
-                                             BprWs* __restrict__ ws) {
+                                             BprWs* __restrict__ ws, int32_t* __restrict__ bump = nullptr) {
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < 3) {
@@ -226,6 +226,7 @@ __device__ __forceinline__ void bpr_finalize(float (&red)[3][NRED], int nb, floa
     out4[2] = nu;
     out4[3] = ni;
     ws->ticket = 0u;
+    if (bump != nullptr) *bump += 1;       // every block of this launch read the counter before it took its ticket
   }
 }
 
@@ -287,7 +288,10 @@ __global__ void __launch_bounds__(256) bpr_forward_kernel(const float4* __restri
 // it needs (ld.relaxed.sys, L1 bypassed) -- it waits exactly as long as the slowest rank is behind, per triple.
 // The buffer is double-buffered on the parity of the step: a writer can reach step s + 2 (the next use of the same
 // half) only after its own finish(s + 1), which needed every reader's partial(s + 1), which that reader launched
-// after its finish(s) had read the half.
+// after its finish(s) had read the half.  "Step" here is the EXCHANGE COUNTER (a device int32 both kernels read; the
+// last block of bpr_finish advances it), not the optimizer's step: a stamp must never be used twice -- an engine that
+// restores its optimizer step after a warm-up launch (CUDA-graph capture) would otherwise let a fast rank read the
+// warm-up's words of a slow peer as if they were the step's.
 struct XchgPeers {
   int n;
   unsigned long long* p[AGCF_MAX_PEERS];
@@ -316,7 +320,7 @@ template <int D>
 __global__ void __launch_bounds__(256) bpr_partial_kernel(const float4* __restrict__ F, const int32_t* __restrict__ u,
                                                           const int32_t* __restrict__ i, const int32_t* __restrict__ j,
                                                           int nb, int n_users, int rank, int cap,
-                                                          const int32_t* __restrict__ step_dev, XchgPeers x) {
+                                                          const int32_t* __restrict__ xchg_ctr, XchgPeers x) {
   using C = RowCfg2<D>;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gl = lane & (C::LPR - 1), grp = lane / C::LPR;
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(256) bpr_partial_kernel(const float4* __restri
   su = group_sum<C::LPR>(su);
   si = group_sum<C::LPR>(si);
   if (valid && gl < 4) {                                     // LPR >= 2 everywhere: 2 or 4 lanes share the stores
-    const uint32_t step = step_dev != nullptr ? (uint32_t)__ldg(step_dev) : 0u;
+    const uint32_t step = xchg_ctr != nullptr ? (uint32_t)*reinterpret_cast<const volatile int32_t*>(xchg_ctr) : 0u;
     const size_t off = ((((size_t)(step & 1u) * AGCF_MAX_PEERS + rank) * cap + t) << 2);
     constexpr int STRIDE = C::LPR < 4 ? C::LPR : 4;
 #pragma unroll
@@ -356,12 +360,12 @@ __global__ void __launch_bounds__(256) bpr_partial_kernel(const float4* __restri
 }
 
 __global__ void __launch_bounds__(256) bpr_finish_kernel(const unsigned long long* __restrict__ xchg, int world, int cap, int nb,
-                                                         float reg, const int32_t* __restrict__ step_dev,
+                                                         float reg, int32_t* __restrict__ xchg_ctr,
                                                          float* __restrict__ out4, float* __restrict__ coef,
                                                          BprWs* __restrict__ ws) {
   __shared__ float red[3][256];
   const int t = blockIdx.x * 256 + threadIdx.x;
-  const uint32_t step = step_dev != nullptr ? (uint32_t)__ldg(step_dev) : 0u;
+  const uint32_t step = xchg_ctr != nullptr ? (uint32_t)*reinterpret_cast<const volatile int32_t*>(xchg_ctr) : 0u;
   float l = 0.f, su = 0.f, si = 0.f;
   if (t < nb) {
     float dpos = 0.f, dneg = 0.f;
@@ -388,7 +392,7 @@ __global__ void __launch_bounds__(256) bpr_finish_kernel(const unsigned long lon
   }
   red[0][threadIdx.x] = l; red[1][threadIdx.x] = su; red[2][threadIdx.x] = si;
   __syncthreads();
-  bpr_finalize<256>(red, nb, reg, out4, ws);
+  bpr_finalize<256>(red, nb, reg, out4, ws, xchg_ctr);
 }
 
 // ================================================================= BPR backward
@@ -688,7 +692,7 @@ extern "C" int64_t agcf_bpr_xchg_bytes(int32_t cap) {
 
 extern "C" int agcf_bpr_partial(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
                                 int32_t nb, int32_t n_users, int32_t d, int32_t rank, int32_t cap,
-                                const int32_t* step_dev, void* const* xchg_all_host, int32_t world,
+                                const int32_t* xchg_ctr, void* const* xchg_all_host, int32_t world,
                                 agcf_stream_t stream) {
   if (!F || !u || !i || !j || nb <= 0 || n_users < 0 || !xchg_all_host) return AGCF_EINVAL;
   if (world < 1 || world > AGCF_MAX_PEERS || rank < 0 || rank >= world || nb > cap) return AGCF_EINVAL;
@@ -705,7 +709,7 @@ extern "C" int agcf_bpr_partial(const float* F, const int32_t* u, const int32_t*
 #define AGCF_BPRP(DD)                                                                              \
   {                                                                                                \
     const unsigned blocks = (unsigned)((nb + RowCfg2<DD>::RPB - 1) / RowCfg2<DD>::RPB);             \
-    bpr_partial_kernel<DD><<<blocks, 256, 0, st>>>(F4, u, i, j, nb, n_users, rank, cap, step_dev, x); \
+    bpr_partial_kernel<DD><<<blocks, 256, 0, st>>>(F4, u, i, j, nb, n_users, rank, cap, xchg_ctr, x); \
   }
   switch (d) {
     case 8: AGCF_BPRP(8) break;
@@ -721,12 +725,12 @@ extern "C" int agcf_bpr_partial(const float* F, const int32_t* u, const int32_t*
 }
 
 extern "C" int agcf_bpr_finish(const void* xchg, int32_t world, int32_t cap, int32_t nb, float reg,
-                               const int32_t* step_dev, float* out4, float* coef, void* ws, agcf_stream_t stream) {
+                               int32_t* xchg_ctr, float* out4, float* coef, void* ws, agcf_stream_t stream) {
   if (!xchg || !out4 || !coef || !ws || nb <= 0 || nb > cap || world < 1 || world > AGCF_MAX_PEERS) return AGCF_EINVAL;
   if (!aligned16(xchg) || !aligned16(ws)) return AGCF_EINVAL;
   const unsigned blocks = (unsigned)((nb + 255) / 256);
   bpr_finish_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(xchg), world, cap, nb, reg,
-                                                              step_dev, out4, coef, reinterpret_cast<BprWs*>(ws));
+                                                              xchg_ctr, out4, coef, reinterpret_cast<BprWs*>(ws));
   AGCF_LAUNCH_OK();
   return AGCF_OK;
 }

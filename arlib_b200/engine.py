@@ -166,6 +166,9 @@ class LightGCNEngine:
             bufs = comm.allocate({"xchg": ((nbytes,), torch.uint8)})
             self.xchg = bufs["xchg"]
             self.xchg.zero_()
+            # the exchange's own counter (stamps / parity of the words): advanced by bpr_finish, NEVER restored with the
+            # optimizer state -- a stamp is used once
+            self.xchg_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
             self._xchg_all = comm.all_ptrs("xchg")
             torch.cuda.synchronize()
             comm.barrier()
@@ -214,7 +217,8 @@ class LightGCNEngine:
         # per-batch work lists: the last forward layer runs the batch's own plan (its <= 3B rows cut into short
         # segments) instead of testing every item of the static plan against the bitmap
         self.wl = None
-        self.wl_segment = 32 if self.d <= 8 else self.WL_SEGMENT          # narrow slices: shorter items (graph.default_segment)
+        # narrow slices: shorter items (graph.default_segment); ARLIB_B200_WL_SEGMENT overrides
+        self.wl_segment = self.WL_SEGMENT if (_os.environ.get('ARLIB_B200_WL_SEGMENT') or self.d > 8) else 32
         if self.sparse_layers and flag("ARLIB_B200_WORKLISTS"):
             self._init_worklists(nbmax, dev)
         # Adam fused into the epilogue of the last backward SpMM (own rows == all rows: not in "rows" mode,
@@ -360,8 +364,8 @@ class LightGCNEngine:
         if self.mode == "dshard":
             # the step's only exchange: 32 B per triple to every peer, stamped with the step -- bpr_finish spins on
             # the words it needs, no barrier launch (csrc/bpr.cu)
-            ops.bpr_partial(F, u, i, j, nb, self.U, self.comm.rank, self.B, self.step_dev, self._xchg_all)
-            ops.bpr_finish(self.xchg, self.comm.world, self.B, nb, self.reg, self.step_dev, out4, self.coef, self.ws)
+            ops.bpr_partial(F, u, i, j, nb, self.U, self.comm.rank, self.B, self.xchg_ctr, self._xchg_all)
+            ops.bpr_finish(self.xchg, self.comm.world, self.B, nb, self.reg, self.xchg_ctr, out4, self.coef, self.ws)
         else:
             ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)
         ops.bpr_backward(F, u, i, j, nb, self.U, self.reg, 1.0, out4, self.coef, occ, seg_off, seg_node, n_seg, self.G)

@@ -221,19 +221,22 @@ int agcf_bpr_forward(const float* F, const int32_t* u, const int32_t* i, const i
  * of `world` device pointers, own buffer included, peer-mapped over NVLink; agcf_bpr_xchg_bytes(cap)
  * bytes each, cap >= nb, ZERO before the first use).  agcf_bpr_finish sums the shares in rank order --
  * the same bits on every rank -- and produces out4 / coef exactly like agcf_bpr_forward.
- * No barrier between the two calls: every value travels as one 64-bit word {step + 1 : 32 | float : 32}
+ * No barrier between the two calls: every value travels as one 64-bit word {*xchg_ctr + 1 : 32 | float : 32}
  * (a single-copy-atomic store), and agcf_bpr_finish spins until the words it needs carry the current
- * step's stamp (it gives up with a NaN loss after 4 s if a rank never shows up).  The buffer is
- * double-buffered on the parity of *step_dev (device step counter; every rank must advance it once per
- * step; NULL = a single use of a zeroed buffer).  This is the ONLY exchange of a d-sharded training
- * step: 32*nb bytes per peer. */
+ * stamp (it gives up with a NaN loss after 4 s if a rank never shows up).  xchg_ctr is a device int32
+ * EXCHANGE COUNTER private to the buffer: both calls read it, the buffer is double-buffered on its
+ * parity, and agcf_bpr_finish advances it by one when its last block retires -- so no stamp is ever
+ * used twice, whatever the caller does to its optimizer step (warm-up launches before a CUDA-graph
+ * capture, restores).  Every rank must issue the same sequence of partial / finish pairs.  NULL = a
+ * single use of a zeroed buffer.  This is the ONLY exchange of a d-sharded training step: 32*nb
+ * bytes per peer. */
 int64_t agcf_bpr_xchg_bytes(int32_t cap);
 int agcf_bpr_partial(const float* F, const int32_t* u, const int32_t* i, const int32_t* j,
                      int32_t nb, int32_t n_users, int32_t d, int32_t rank, int32_t cap,
-                     const int32_t* step_dev, void* const* xchg_all_host, int32_t world,
+                     const int32_t* xchg_ctr, void* const* xchg_all_host, int32_t world,
                      agcf_stream_t stream);
 int agcf_bpr_finish(const void* xchg, int32_t world, int32_t cap, int32_t nb, float reg,
-                    const int32_t* step_dev, float* out4, float* coef, void* ws, agcf_stream_t stream);
+                    int32_t* xchg_ctr, float* out4, float* coef, void* ws, agcf_stream_t stream);
 
 /* Backward of the above into the dense gradient of F, atomic-free: one
  * half-warp per node segment sums that node's contributions in occurrence order
