@@ -370,6 +370,11 @@ class LightGCNEngine:
             ops.bpr_forward(F, u, i, j, nb, self.U, self.reg, out4, self.coef, self.ws)
         ops.bpr_backward(F, u, i, j, nb, self.U, self.reg, 1.0, out4, self.coef, occ, seg_off, seg_node, n_seg, self.G)
         H = self.G
+        # first backward layer: only the batch's gradient rows of H are non-zero.  The column-masked kernel skips the others
+        # (27 vs 44 us at d = 64); on 8-column slices its extra bitmap round trip per chunk costs more than the zero rows it
+        # avoids (26.4 vs 23.4 us, profiles/r2_summary.md section 5), so there the plain kernel gathers the zeros
+        if mask is not None and self.d <= 8:
+            mask = None
         for k in range(L, 0, -1):
             if k > 1:
                 nxt = self.bw[k % 2]
