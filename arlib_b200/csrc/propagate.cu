@@ -426,10 +426,29 @@ __device__ __forceinline__ void spmm_finish_item(const SpmmParams& p, bool valid
         __threadfence();
 #pragma unroll
         for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int kk = 0; kk < nseg; ++kk) {                // segment order: deterministic
-          const float4* part = p.partial + ((size_t)pb + kk) * C::V4;
+        if constexpr (C::LPR <= 8) {
+          // narrow column slices: the launch is ONE wave of CTAs, and the per-CTA timeline (profiles/r2_spmm_cta_timeline_d8.txt)
+          // shows its length is the longest dependency chain -- chunks per item x ~1.9 us, plus THIS loop for the hub row:
+          // one L2 round trip per segment when the loads are issued one at a time (52 segments of 64 entries for the
+          // 3 318-entry row: ~18 us of a 26.7 us launch).  Eight partials are loaded together and added in segment order.
+          constexpr int NB = 8;
+          for (int kk = 0; kk < nseg; kk += NB) {
+            float4 part[NB];
 #pragma unroll
-          for (int v = 0; v < C::VPL; ++v) acc[v] = add4(acc[v], __ldcg(part + v * C::LPR + gl));
+            for (int q = 0; q < NB; ++q) {
+              const int ks = kk + q < nseg ? kk + q : nseg - 1;          // clamp: the surplus loads are discarded below
+              part[q] = __ldcg(p.partial + ((size_t)pb + ks) * C::V4 + gl);
+            }
+#pragma unroll
+            for (int q = 0; q < NB; ++q)
+              if (kk + q < nseg) acc[0] = add4(acc[0], part[q]);
+          }
+        } else {
+          for (int kk = 0; kk < nseg; ++kk) {                // segment order: deterministic
+            const float4* part = p.partial + ((size_t)pb + kk) * C::V4;
+#pragma unroll
+            for (int v = 0; v < C::VPL; ++v) acc[v] = add4(acc[v], __ldcg(part + v * C::LPR + gl));
+          }
         }
         if (gl == 0) p.tickets[pb] = 0;                    // ready for the next launch
       }

@@ -23,7 +23,7 @@ for model in models:
     import importlib
     cls = getattr(importlib.import_module("arlib_b200.recommender." + model), model)
     args = types.SimpleNamespace(topK="50", emb_size=64, n_layers=2, batch_size=2048, lRate=0.005, reg=1e-4, maxEpoch=1,
-                                 seed=2018, sampler="device", model_name=model)
+                                 seed=2018, sampler="device", model_name=model, fused=False)   # the reference-shaped loop
     torch.manual_seed(2018)
     rec = cls(args, data)
     m = rec.model.cuda()
