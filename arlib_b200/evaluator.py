@@ -132,10 +132,8 @@ class FullRankEvaluator:
                 ops._lib.check(int(need), "agcf_score_topk_ws_bytes")
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
-            v, i = ops.score_topk(user_emb, item_emb, K, user_rows=self.user_rows[lo:hi], mask_rowptr=self.mask_rowptr,
-                                  mask_items=self.mask_items, impl=impl, ws=self._ws)
-            vals[lo:hi] = v
-            idx[lo:hi] = i
+            ops.score_topk(user_emb, item_emb, K, user_rows=self.user_rows[lo:hi], mask_rowptr=self.mask_rowptr,
+                           mask_items=self.mask_items, impl=impl, ws=self._ws, out=(vals[lo:hi], idx[lo:hi]))
         return vals, idx
 
     def topk_sharded(self, user_emb, item_emb, K, rank, world, impl=None):
@@ -156,9 +154,8 @@ class FullRankEvaluator:
         idx = torch.empty((n, K), dtype=torch.int32, device=self.device)
         for lo in range(0, n, USER_CHUNK):                   # the stage-2 workspace grows with the users of a call
             hi = min(n, lo + USER_CHUNK)
-            v, i = ops.score_topk(ue, block, K, user_rows=self.user_rows[lo:hi], mask_rowptr=self.mask_rowptr,
-                                  mask_items=self.mask_items, item_offset=i0, impl=impl)
-            vals[lo:hi], idx[lo:hi] = v, i
+            ops.score_topk(ue, block, K, user_rows=self.user_rows[lo:hi], mask_rowptr=self.mask_rowptr,
+                           mask_items=self.mask_items, item_offset=i0, impl=impl, out=(vals[lo:hi], idx[lo:hi]))
         all_v = torch.empty((world, n, K), dtype=torch.float32, device=self.device)
         all_i = torch.empty((world, n, K), dtype=torch.int32, device=self.device)
         dist.all_gather_into_tensor(all_v, vals)
@@ -189,9 +186,8 @@ class FullRankEvaluator:
                 ops._lib.check(int(need), "agcf_score_topk_ws_bytes")
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
-            v, i = ops.score_topk(ue, ie, K, user_rows=self.user_rows[a:b], mask_rowptr=self.mask_rowptr,
-                                  mask_items=self.mask_items, impl=impl, ws=self._ws)
-            vals[a - lo:b - lo], idx[a - lo:b - lo] = v, i
+            ops.score_topk(ue, ie, K, user_rows=self.user_rows[a:b], mask_rowptr=self.mask_rowptr,
+                           mask_items=self.mask_items, impl=impl, ws=self._ws, out=(vals[a - lo:b - lo], idx[a - lo:b - lo]))
         if not gather:
             return vals[:hi - lo], idx[:hi - lo], (lo, hi)
         all_v = torch.empty((world * per, K), dtype=torch.float32, device=self.device)
@@ -203,9 +199,15 @@ class FullRankEvaluator:
     def per_user_metrics(self, idx, cutoffs):
         """[n_users, n_cutoffs, 3] float64 (hits, dcg, idcg) on device."""
         K = idx.shape[1]
-        inv_log = torch.tensor([1.0 / math.log(r + 2) for r in range(max(K, max(cutoffs)))], dtype=torch.float64,
-                               device=self.device)
-        cut = torch.tensor(list(cutoffs), dtype=torch.int32, device=self.device)
+        key = (K, tuple(int(c) for c in cutoffs))
+        consts = self.__dict__.setdefault("_metric_consts", {})
+        if key not in consts:
+            # built once per (K, cutoffs): torch.tensor(list, device=cuda) is a synchronous pageable copy, and one per
+            # call drained the launch queue in front of every evaluation
+            inv_log = torch.tensor([1.0 / math.log(r + 2) for r in range(max(K, max(cutoffs)))], dtype=torch.float64,
+                                   device=self.device)
+            consts[key] = (torch.tensor(list(key[1]), dtype=torch.int32, device=self.device), inv_log)
+        cut, inv_log = consts[key]
         return ops.rank_metrics(idx, self.t_rowptr, self.t_items, self.test_total, cut, inv_log)
 
     # ------------------------------------------------------------- reference API

@@ -297,9 +297,10 @@ def increment(counter):
 
 
 def score_topk(user_emb, item_emb, K, user_rows=None, mask_rowptr=None, mask_items=None, item_offset=0, impl=0,
-               n_u=None, ws=None, return_flags=False):
+               n_u=None, ws=None, return_flags=False, out=None):
     """agcf_score_topk over users ``user_rows`` (or the first n_u rows).  Returns
-    (values [n_u,K] fp32, item ids [n_u,K] int32) sorted by (score desc, id asc)."""
+    (values [n_u,K] fp32, item ids [n_u,K] int32) sorted by (score desc, id asc); ``out`` = (values, ids) to write into
+    (contiguous [n_u, K] blocks, e.g. row slices of the caller's result tensors: no copy afterwards)."""
     lib = _lib.load()
     _f32(user_emb, "user_emb"); _f32(item_emb, "item_emb"); _i32(user_rows, "user_rows")
     _i32(mask_rowptr, "mask_rowptr"); _i32(mask_items, "mask_items")
@@ -311,8 +312,14 @@ def score_topk(user_emb, item_emb, K, user_rows=None, mask_rowptr=None, mask_ite
         _lib.check(need, "agcf_score_topk_ws_bytes")
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=user_emb.device)
-    out_val = torch.empty((n_u, K), dtype=torch.float32, device=user_emb.device)
-    out_idx = torch.empty((n_u, K), dtype=torch.int32, device=user_emb.device)
+    if out is not None:
+        out_val, out_idx = out
+        _f32(out_val, "out values"); _i32(out_idx, "out ids")
+        if tuple(out_val.shape) != (n_u, K) or tuple(out_idx.shape) != (n_u, K):
+            raise ValueError("score_topk: out blocks must be [%d, %d]" % (n_u, K))
+    else:
+        out_val = torch.empty((n_u, K), dtype=torch.float32, device=user_emb.device)
+        out_idx = torch.empty((n_u, K), dtype=torch.int32, device=user_emb.device)
     flags = torch.empty(n_u, dtype=torch.int32, device=user_emb.device) if return_flags else None
     _lib.check(lib.agcf_score_topk(user_emb.data_ptr(), _p(user_rows), n_u, item_emb.data_ptr(), n_items, d,
                                    _p(mask_rowptr), _p(mask_items), int(K), int(item_offset), int(impl),
