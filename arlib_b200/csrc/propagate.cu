@@ -427,10 +427,17 @@ __device__ __forceinline__ void spmm_finish_item(const SpmmParams& p, bool valid
 #pragma unroll
         for (int v = 0; v < C::VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (C::LPR <= 8) {
-          // narrow column slices: the launch is ONE wave of CTAs, and the per-CTA timeline (profiles/r2_spmm_cta_timeline_d8.txt)
-          // shows its length is the longest dependency chain -- chunks per item x ~1.9 us, plus THIS loop for the hub row:
-          // one L2 round trip per segment when the loads are issued one at a time (52 segments of 64 entries for the
-          // 3 318-entry row: ~18 us of a 26.7 us launch).  Eight partials are loaded together and added in segment order.
+          // narrow column slices: the launch is ONE wave of CTAs, so a hub row's combine is not hidden behind other CTAs:
+          // eight partials are loaded together (one L2 round trip per batch instead of one per segment) and added in
+          // segment order.  Measured neutral (24.1 vs 23.6 us at d = 8).  What the per-CTA timelines
+          // (profiles/r2_spmm_cta_timeline_d8_seg{32,64}.txt) show instead: a warp needs ~4.5 us per 16-entry chunk
+          // whatever else is resident -- the ~8 000 row sectors the SM's lane groups keep in flight queue at ~1 sector
+          // per clock -- so an item's duration is its length x the groups resident, and the launch lasts as long as the
+          // longest items' chains.  Tried against that and all SLOWER than one bundle per warp on hardware-scheduled
+          // CTAs (profiles/r2_spmm_{interleave,warp_sched,vecidx}_experiment.txt, r2_spmm_narrow_matrix.txt): bundles
+          // dealt round-robin to the CTAs (d = 8: 29.4 vs 26.4 us), warps that take bundles from a device counter
+          // (28.9 vs 23.9), 5 / 6 CTAs per SM at 48 / 40 registers (26.8 / 30.9 vs 24.0), 16-entry segments (30.6);
+          // 16-byte index loads on 4-entry-aligned item starts gain 4-14 % (22.6 vs 26.2 at 64-entry segments).
           constexpr int NB = 8;
           for (int kk = 0; kk < nseg; kk += NB) {
             float4 part[NB];

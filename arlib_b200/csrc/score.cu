@@ -471,20 +471,11 @@ __device__ __forceinline__ uint32_t warp_radix_select(unsigned int* hist, int n,
     for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0u;
     __syncwarp();
     const uint32_t pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-    // scores of one user cluster in a few bins (in the first pass nearly all 1 281 group maxima share the top byte):
-    // lanes with the same bin are found with match.any and ONE of them adds their count -- a 32-way conflicting shared
-    // atomic per trip otherwise
-    for (int base = 0; base < n; base += 32) {
-      const int k = base + lane;
-      uint32_t key = 0u;
-      bool on = false;
-      if (k < n) {
-        key = f2key(vals[k]);
-        on = (key & pmask) == prefix;
-      }
-      const unsigned int bin = on ? ((key >> shift) & 255u) : (256u + (unsigned int)lane);
-      const unsigned int peers = __match_any_sync(0xffffffffu, bin);
-      if (on && lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned int)__popc(peers));
+    // (lanes of equal bin combined through match.any before the atomic was measured 4.5x SLOWER for the whole kernel --
+    // 392 vs 87 us per chunk, profiles/r2_launches_eval.csv: MATCH.ANY serialises over the distinct values of a warp)
+    for (int k = lane; k < n; k += 32) {
+      const uint32_t key = f2key(vals[k]);
+      if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncwarp();
     unsigned int mine = 0u;

@@ -509,7 +509,7 @@ def run_ours(args):
         vals, idx = ev.topk(F[:U], F[U:], TOPK)
     barrier()
     e0.record()
-    reps = 3
+    reps = 10
     for _ in range(reps):
         vals, idx = ev.topk(F[:U], F[U:], TOPK)
         per = ev.per_user_metrics(idx, [TOPK])

@@ -213,7 +213,7 @@ int main(int argc, char** argv) {
     run<64, 4, 4, 16>(X, n_rows, enc, 3, skew, d_sums);
     run<64, 3, 8, 16>(X, n_rows, enc, 2, skew, d_sums);
     run<64, 6, 8, 16>(X, n_rows, enc, 1, skew, d_sums);
-    run<64, 4, 16, 16>(X, n_rows, enc, 1, skew, d_sums);
+    run<64, 3, 16, 16>(X, n_rows, enc, 1, skew, d_sums);
   }
   // narrow column slices of the d-sharded layout: 32-byte rows, the same table seen as 8 x as many rows
   fill_kernel<<<1024, 256>>>(X, (long long)bytes / 4, 8);
