@@ -308,6 +308,8 @@ struct Stage2Params {
   int cap_items;
   const float4* Udense;        // nullable: the user rows gathered for the tcgen05 stage 1 ([n_u][D], row r = user r of the
                                // call) -- the same bits as Uemb[user_rows[r]] without the index hop
+  int cand_stage;              // s2_candidates: > 0 = every warp keeps its user's row of group maxima in shared memory
+                               // (cand_stage floats per warp, dynamic) for the five passes over it
 };
 
 template <int D>
@@ -693,6 +695,7 @@ __global__ void __launch_bounds__(32 * S2W<D>::WPC) topk_select_warp_kernel(cons
 // Results are bit-identical to the warp kernel (tests run both).
 template <int D>
 __global__ void __launch_bounds__(256) s2_candidates_kernel(const Stage2Params p) {
+  extern __shared__ __align__(16) float s2c_rows[];                  // [8][cand_stage] when cand_stage > 0
   __shared__ unsigned int hist_all[8][256];
   __shared__ float urow_all[8][D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -706,6 +709,15 @@ __global__ void __launch_bounds__(256) s2_candidates_kernel(const Stage2Params p
     __syncwarp();
     for (int k = lane; k < D / 4; k += 32) reinterpret_cast<float4*>(urow)[k] = __ldg(p.Uemb + (size_t)uid * (D / 4) + k);
     __syncwarp();
+    if (p.cand_stage > 0) {
+      // the radix select sweeps the row four times and the compaction once more: 5 x n_u x n_groups x 4 B from L2
+      // (420 MB per 16 384-user chunk at 1 281 groups) -- one sweep into shared memory, the rest from there
+      float* srow = s2c_rows + (size_t)warp * p.cand_stage;
+      const float4* g4 = reinterpret_cast<const float4*>(grow);      // pitch is a multiple of 8 words: rows are 32-byte aligned
+      for (int k = lane; k < (p.n_groups + 3) / 4; k += 32) reinterpret_cast<float4*>(srow)[k] = __ldcs(g4 + k);
+      __syncwarp();
+      grow = srow;
+    }
     const unsigned int R = (unsigned int)min(p.K, p.n_groups);
     float thr = key2f(warp_radix_select(hist, p.n_groups, R, lane, grow));
     float keep_from = thr;                                           // tau itself when stage 1 is exact
@@ -931,8 +943,11 @@ constexpr int kS2ItemCap = 128;
 // acc = fmaf(u[k], v[k], acc), k ascending from 0 -- the bits of exact_dot.
 constexpr int kS2TU = 128;                 // users per tile
 
+#ifndef AGCF_S2RI_MINB
+#define AGCF_S2RI_MINB 4          // 64 registers, no spills: 4 CTAs / SM measured faster than 3 at 80 (profiles/r2_summary.md)
+#endif
 template <int D>
-__global__ void __launch_bounds__(256) s2_rescore_items_kernel(const Stage2Params p) {
+__global__ void __launch_bounds__(256, AGCF_S2RI_MINB) s2_rescore_items_kernel(const Stage2Params p) {
   constexpr int LD = D + 4, V4 = D / 4;
   extern __shared__ __align__(16) unsigned char dyn[];
   float* tile = reinterpret_cast<float*>(dyn);                       // [32][LD] item rows of the group
@@ -1410,7 +1425,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   Stage2Params p;
   p.Uemb = U4; p.user_rows = user_rows; p.n_u = n_u; p.Iemb = I4; p.n_items = n_items;
   p.bits = bits; p.gmax = gmax; p.n_groups = L.n_groups; p.pitch = L.pitch; p.K = K; p.item_offset = item_offset;
-  p.margin_scale = margin_scale; p.max_item_norm = norm;
+  p.margin_scale = margin_scale; p.max_item_norm = norm; p.cand_stage = 0;
   p.out_val = out_val; p.out_idx = out_idx; p.out_flags = out_flags;
   p.cand_groups = reinterpret_cast<int32_t*>(base + L.groups_off);
   p.cand_val = reinterpret_cast<float*>(base + L.cval_off);
@@ -1447,6 +1462,12 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
     const size_t dyn_sel = 8 * (1024 + (size_t)kpow2 * 8);
     const size_t dyn_sel_items = 8 * (1024 + (size_t)kpow2 * 8 + (size_t)kS2ItemCap * 16);
     if (dyn_sel_items > 200 * 1024) return AGCF_EUNSUPPORTED;
+    // the group-maxima row of a warp's user staged in shared memory while 8 rows fit next to the static 10 KB
+    // (two CTAs per SM at least): up to ~2 800 groups = 90 k items; wider item tables read the row from L2 as before
+    static const bool stage_env = [] { const char* e = getenv("AGCF_S2_CAND_STAGE"); return e == nullptr || atoi(e) != 0; }();
+    const int stage_words = (L.n_groups + 3) / 4 * 4;
+    p.cand_stage = (stage_env && (size_t)stage_words * 4 * 8 <= 96 * 1024) ? stage_words : 0;
+    const size_t dyn_cand = (size_t)p.cand_stage * 4 * 8;
 #define AGCF_S2G(DD)                                                                                             \
   {                                                                                                              \
     const size_t dyn_r = ((size_t)kGroup * (DD + 4) + 8 * AGCF_S2_PB * DD) * 4;   /* tile + 8 warps x PB user rows */ \
@@ -1454,7 +1475,9 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_rescore_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_r)); \
     if (dyn_sel > 48 * 1024)                                                                                     \
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_select_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel)); \
-    s2_candidates_kernel<DD><<<warp_grid, 256, 0, st>>>(p);                                                      \
+    if (dyn_cand > 48 * 1024)                                                                                    \
+      AGCF_CUDA_OK(cudaFuncSetAttribute(s2_candidates_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_cand)); \
+    s2_candidates_kernel<DD><<<warp_grid, 256, dyn_cand, st>>>(p);                                               \
     if (items) {                                                                                                 \
       const size_t dyn_ri = ((size_t)(kGroup + kS2TU) * (DD + 4) + 3 * kS2TU) * 4;   /* item tile + user tile + per-user words */ \
       if (dyn_ri > 48 * 1024)                                                                                    \

@@ -12,13 +12,13 @@ ue, ie = xavier_tables(U, I, d)
 ue, ie = ue.to(dev), ie.to(dev)
 ev = FullRankEvaluator.from_arrays(U, I, D["tu"], D["ti"], D["su"], D["si"], dev)
 for impl in (1, 0):
-    for _ in range(2): ev.topk(ue, ie, 50, impl=impl)
+    for _ in range(5): ev.topk(ue, ie, 50, impl=impl)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter(); a.record()
-    for _ in range(5): v, i = ev.topk(ue, ie, 50, impl=impl)
+    for _ in range(20): v, i = ev.topk(ue, ie, 50, impl=impl)
     b.record(); torch.cuda.synchronize()
-    print("impl %d ctas/sm %s: %.2f ms per eval (device), %.2f ms wall, %d users" % (impl, os.environ.get("AGCF_STAGE2_CTAS_PER_SM", "8"), a.elapsed_time(b) / 5, (time.perf_counter() - t0) * 200, ev.user_rows.numel()))
+    print("impl %d ctas/sm %s: %.2f ms per eval (device), %.2f ms wall, %d users" % (impl, os.environ.get("AGCF_STAGE2_CTAS_PER_SM", "8"), a.elapsed_time(b) / 20, (time.perf_counter() - t0) * 50, ev.user_rows.numel()))
 # heavy-tailed item norms (what training produces): does the TF32 margin admit too many groups?
 torch.manual_seed(0)
 scale = 1.0 + 20.0 * torch.rand(I, 1, device=dev) ** 8
