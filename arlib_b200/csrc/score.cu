@@ -1475,7 +1475,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_rescore_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_r)); \
     if (dyn_sel > 48 * 1024)                                                                                     \
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_select_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_sel)); \
-    if (dyn_cand > 48 * 1024)                                                                                    \
+    if (dyn_cand + 12 * 1024 > 48 * 1024)   /* static 10 KB + dynamic beyond the 48 KB default */                \
       AGCF_CUDA_OK(cudaFuncSetAttribute(s2_candidates_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_cand)); \
     s2_candidates_kernel<DD><<<warp_grid, 256, dyn_cand, st>>>(p);                                               \
     if (items) {                                                                                                 \

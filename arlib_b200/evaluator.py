@@ -18,7 +18,9 @@ import torch
 from . import ops
 from .util.metrics import format_measure
 
-USER_CHUNK = int(os.environ.get("ARLIB_B200_EVAL_CHUNK", "16384"))
+# users per agcf_score_topk call (the stage-2 workspace grows with it: ~1.2 GB at 32 768 users x 41 k items).  Measured on B200
+# at the Gowalla shape (27 324 test users, profiles/r2_summary.md): one call 1.04 ms, two calls of <= 16 384 users 1.15 ms
+USER_CHUNK = int(os.environ.get("ARLIB_B200_EVAL_CHUNK", "32768"))
 # stage-1 implementation of agcf_score_topk: 1 = TF32 tcgen05 GEMM (d <= 128), 0 = fp32 CUDA-core GEMM
 DEFAULT_IMPL = int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1"))
 

@@ -14,11 +14,18 @@ ev = FullRankEvaluator.from_arrays(U, I, D["tu"], D["ti"], D["su"], D["si"], dev
 for impl in (1, 0):
     for _ in range(5): ev.topk(ue, ie, 50, impl=impl)
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter(); a.record()
-    for _ in range(20): v, i = ev.topk(ue, ie, 50, impl=impl)
-    b.record(); torch.cuda.synchronize()
-    print("impl %d ctas/sm %s: %.2f ms per eval (device), %.2f ms wall, %d users" % (impl, os.environ.get("AGCF_STAGE2_CTAS_PER_SM", "8"), a.elapsed_time(b) / 20, (time.perf_counter() - t0) * 50, ev.user_rows.numel()))
+    reps = 20 if impl == 1 else 5
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    t0 = time.perf_counter(); evs[0].record()
+    for k in range(reps):
+        v, i = ev.topk(ue, ie, 50, impl=impl)
+        evs[k + 1].record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / reps * 1e3
+    per = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(reps))
+    print("impl %d ctas/sm %s: %.2f ms per eval (device, mean of %d; median %.2f, min %.2f, max %.2f), %.2f ms wall, %d users"
+          % (impl, os.environ.get("AGCF_STAGE2_CTAS_PER_SM", "8"), evs[0].elapsed_time(evs[-1]) / reps, reps, per[reps // 2], per[0], per[-1],
+             wall, ev.user_rows.numel()))
 # heavy-tailed item norms (what training produces): does the TF32 margin admit too many groups?
 torch.manual_seed(0)
 scale = 1.0 + 20.0 * torch.rand(I, 1, device=dev) ** 8

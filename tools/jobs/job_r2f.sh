@@ -7,4 +7,4 @@ for D in 8 16; do
 done
 ARLIB_B200_EVAL_CHUNK=32768 timeout 300 python tools/eval_bench.py > $O/eval_bench_chunk32768.txt 2>&1; head -1 $O/eval_bench_chunk32768.txt
 timeout 300 python tools/eval_bench.py > $O/eval_bench.txt 2>&1; head -1 $O/eval_bench.txt
-bash tools/job_r2b.sh
+bash tools/jobs/job_r2b.sh
