@@ -97,6 +97,7 @@ __device__ __forceinline__ bool bit_set(const uint32_t* __restrict__ m, int k) {
 #ifndef AGCF_SPMM_LPR64
 #define AGCF_SPMM_LPR64 16
 #endif
+#define AGCF_SPMM_CM_THREADS_MAX 256               // largest CTA any SpMM kernel is launched with
 constexpr int default_lpr(int d) { return d == 128 ? AGCF_SPMM_LPR128 : (d == 64 ? AGCF_SPMM_LPR64 : (d / 4 < 32 ? d / 4 : 32)); }
 
 template <int D, int LPR_ = default_lpr(D)>
@@ -250,9 +251,44 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
 // For narrow rows (d/4 < 16 lanes, the d-sharded multi-GPU tables) EPL > 1 keeps CH at 16.
 // one chunk held in registers (lane gl owns entries k * LPR + gl): broadcast every entry to the lane group and
 // gather-accumulate its row of X; slots with col < 0 (row end, masked column) are predicated off
+// Rows of two float4 per lane (d = 128 / 256): the (col, val) pairs of a lane group's chunk reach its lanes through shared
+// memory instead of 2 shuffles per entry -- every lane stores its pair (one STS.64 per warp), one LDS.128 then hands TWO
+// entries to the whole group (the address is uniform per group: a broadcast).  Shuffles and shared loads are both
+// wavefronts of the LSU data pipe, which the profile shows ~70 % busy with the gathers' data returns; per 32 entries of a
+// warp this is 9 wavefronts instead of 32 and the chunk loop 125 instead of 205 instructions.  Same values, same order:
+// bit-identical.  Measured on B200 (profiles/r2_summary.md section 9): Amazon-book shape d = 128 233 -> 209 us per full
+// launch, 61 -> 51 us row-masked; at d = 64 (one float4 per lane) the extra STS -> LDS hop in front of every chunk's
+// gathers costs more than the shuffles did (46.8 vs 43.6 us), so those rows keep the shuffles.
+template <typename C>
+constexpr bool spmm_smem_bcast() { return C::EPL == 1 && C::VPL >= 2 && C::LPR >= 16; }
+
 template <typename C, bool PACKED>
 __device__ __forceinline__ void spmm_consume_chunk(const SpmmParams& p, const int (&c)[C::EPL], const float (&v)[C::EPL],
                                                    int gl, float4 (&acc)[C::VPL]) {
+  if constexpr (spmm_smem_bcast<C>()) {
+    __shared__ __align__(16) int2 s_bcast[(AGCF_SPMM_CM_THREADS_MAX / 32) * 32];
+    int2* mine = s_bcast + (threadIdx.x & ~31);
+    const int lane = threadIdx.x & 31;
+    __syncwarp();                                          // the previous chunk's pairs are no longer read
+    mine[lane] = make_int2(c[0], __float_as_int(v[0]));
+    __syncwarp();
+    const int4* row = reinterpret_cast<const int4*>(mine + (lane & ~(C::LPR - 1)));
+#pragma unroll
+    for (int t2 = 0; t2 < C::CH / 2; ++t2) {
+      const int4 two = row[t2];                            // entries 2 t2 and 2 t2 + 1 of this group's chunk
+      if (two.x >= 0) {
+        const float4* xr = p.X + (size_t)two.x * C::V4 + gl;
+#pragma unroll
+        for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], __int_as_float(two.y), ld_gather_f4(xr + vv * C::LPR));
+      }
+      if (two.z >= 0) {
+        const float4* xr = p.X + (size_t)two.z * C::V4 + gl;
+#pragma unroll
+        for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], __int_as_float(two.w), ld_gather_f4(xr + vv * C::LPR));
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < C::EPL; ++k) {
 #pragma unroll
@@ -760,10 +796,24 @@ static int launch_spmm(const SpmmParams& p, cudaStream_t st) {
     AGCF_LAUNCH_OK();
     return AGCF_OK;
   }
+  // CTA size of the plain launches: 4 warps (the kernel derives its slots from blockDim; AGCF_SPMM_THREADS = 64 / 128 /
+  // 256 for tuning).  Same warps per SM as 8-warp CTAs, but a CTA's slot is handed on as soon as ITS four warps are done:
+  // measured on B200 (profiles/r2_summary.md section 9) 44.0 -> 43.2 us at d = 64, 30.8 -> 28.9 at d = 32, 24.7 -> 23.1 at
+  // d = 16, 234.9 -> 231.6 at d = 128 (Amazon-book shape); 64 threads measured the same as 128
+  static const int csr_threads = [] {
+    const char* e = getenv("AGCF_SPMM_THREADS");
+    const int t = e != nullptr ? atoi(e) : 128;
+    return (t == 64 || t == 128 || t == 256) ? t : 128;
+  }();
+  if (p.sched == nullptr && csr_threads != C::THREADS) {
+    const long long rpb = (long long)(csr_threads / 32) * C::RPW;
+    blocks = ((long long)p.n_v + rpb - 1) / rpb;
+  }
+  const int threads = p.sched == nullptr ? csr_threads : C::THREADS;
   if (p.noise != nullptr || p.noise_main || p.aux_Y[0] != nullptr || p.aux_Y[1] != nullptr)
-    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), true><<<(unsigned)blocks, threads, 0, st>>>(p);
   else
-    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), false><<<(unsigned)blocks, C::THREADS, 0, st>>>(p);
+    spmm_csr_kernel<D, LPR, AGCF_SPMM_MINB(D), false><<<(unsigned)blocks, threads, 0, st>>>(p);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
 }

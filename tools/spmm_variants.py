@@ -15,6 +15,10 @@ N = U + I
 dev = torch.device("cuda:0")
 half = sp.csr_matrix((np.ones(E, dtype=np.float32), (D["tu"], D["ti"] + U)), shape=(N, N), dtype=np.float32)
 g = DeviceGraph.from_dataloader_adj(half + half.T, dev)
+if os.environ.get("SPMM_HOTCOL"):
+    # diagnostic: every gather reads row (k mod HOTCOL) -- the whole gather stream hits L1 / a few L2 lines, what is left
+    # is the kernel's non-gather work (descriptors, index stream, shuffles, combine, epilogue)
+    g.col.copy_(torch.arange(g.nnz, device=dev, dtype=torch.int32) % int(os.environ["SPMM_HOTCOL"]))
 X = torch.randn(N, d, device=dev)
 Y = torch.empty_like(X); A = torch.empty_like(X)
 # a batch-like node mask: 2048 edges -> users, pos items; 2048 uniform neg items
