@@ -466,9 +466,11 @@ def run_ours(args):
                               "peak": L2_GATHER_PEAK_GBS, "unit": "GB/s",
                               "frac": eng.g.local_nnz * (8 + 4 * eng.d) / (spmm_avg_ms * 1e-3) / 1e9 / L2_GATHER_PEAK_GBS,
                               "peak_kind": "measured: tools/l2_gather_peak.cu, power-law 256-byte row gathers from an "
-                                           "L2-resident table (profiles/r1_l2_gather_peak.txt)"},
-                "note": "table (%.1f MB) is L2-resident and no on-chip store holds it: the binding resource is the L2->SM "
-                        "gather path (nnz*(8+4d) = %.0f MB per launch), not DRAM; see DESIGN.md 4.1"
+                                           "L2-resident table (profiles/r1_l2_gather_peak.txt, re-measured r2_l2_gather_peak.txt: 18 404)"},
+                "note": "table (%.1f MB) is L2-resident and no on-chip store holds it: the launch moves nnz*(8+4d) = %.0f MB "
+                        "from L2, not from DRAM; a launch whose gathers all hit one cached row takes as long "
+                        "(profiles/r2_summary.md 9): the LSU data pipe and the per-item dependent chain at 32 warps / SM are "
+                        "what the time is made of, the L2-gather figure is what the memory system could deliver; DESIGN.md 4.1"
                         % (N * d * 4 / 1e6, g.nnz * (8 + 4 * d) / 1e6)}
 
     # ---- end to end through the public step API with HOST triples (pinned), loss read back
