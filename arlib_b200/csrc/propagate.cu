@@ -249,25 +249,48 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
 // and every entry is broadcast by shuffle; the CH slots are fully unrolled and predicated, so up to CH
 // independent row gathers are in flight per lane while the next chunk's indices are already loading.
 // For narrow rows (d/4 < 16 lanes, the d-sharded multi-GPU tables) EPL > 1 keeps CH at 16.
-// Shared-memory index broadcast (wide rows, one entry per lane and chunk): the (col, val) pairs of a lane group's chunk
-// reach its lanes through shared memory instead of 2 shuffles per entry -- every lane stores its pair (one STS.64 per
-// warp), one LDS.128 then hands TWO entries to the whole group (the address is uniform per group: a broadcast).
-// Shuffles and shared loads are both wavefronts of the LSU data pipe, which the profile shows ~70 % busy with the
-// gathers' data returns; per 32 entries of a warp this is 9 wavefronts instead of 32 and the chunk loop 125 instead of
-// 205 instructions.  The pairs of chunk k + 1 are stored at the END of chunk k's iteration (two buffers), so the
-// STS -> LDS hop is never in front of a chunk's gathers.  Same values, same order: bit-identical.
-// AGCF_SPMM_SMEM_BCAST_MIN_VPL: float4 per lane from which on the scheme is used (measured, profiles/r2_summary.md 9).
-#ifndef AGCF_SPMM_SMEM_BCAST_MIN_VPL
-#define AGCF_SPMM_SMEM_BCAST_MIN_VPL 2
-#endif
+// one chunk held in registers (lane gl owns entries k * LPR + gl): broadcast every entry to the lane group and
+// gather-accumulate its row of X; slots with col < 0 (row end, masked column) are predicated off
+// Rows of two float4 per lane (d = 128 / 256): the (col, val) pairs of a lane group's chunk reach its lanes through shared
+// memory instead of 2 shuffles per entry -- every lane stores its pair (one STS.64 per warp), one LDS.128 then hands TWO
+// entries to the whole group (the address is uniform per group: a broadcast).  Shuffles and shared loads are both
+// wavefronts of the LSU data pipe, which the profile shows ~70 % busy with the gathers' data returns; per 32 entries of a
+// warp this is 9 wavefronts instead of 32 and the chunk loop 125 instead of 205 instructions.  Same values, same order:
+// bit-identical.  Measured on B200 (profiles/r2_summary.md section 9): Amazon-book shape d = 128 233 -> 209 us per full
+// launch, 61 -> 51 us row-masked, 1.10 -> 1.053 ms per training step; at d = 64 (one float4 per lane) it is slower than
+// the shuffles (46.8 vs 43.6 us), so those rows keep them.  A double-buffered form that stores chunk k + 1's pairs at the
+// end of chunk k's iteration (the STS -> LDS hop off the gather path) measured WORSE at both widths (d = 128: 214 us and
+// 1.097 ms per step; d = 64: 45.2 us): the next chunk's index registers stay live across the gathers and spill.
 template <typename C>
-constexpr bool spmm_smem_bcast() { return C::EPL == 1 && C::VPL >= AGCF_SPMM_SMEM_BCAST_MIN_VPL && C::LPR >= 16; }
+constexpr bool spmm_smem_bcast() { return C::EPL == 1 && C::VPL >= 2 && C::LPR >= 16; }
 
-// one chunk: gather-accumulate the rows of X named by the entries; slots with col < 0 (row end, masked column) are
-// predicated off.  Shuffle form: lane gl owns entries k * LPR + gl of the chunk and broadcasts them to its group.
 template <typename C, bool PACKED>
 __device__ __forceinline__ void spmm_consume_chunk(const SpmmParams& p, const int (&c)[C::EPL], const float (&v)[C::EPL],
                                                    int gl, float4 (&acc)[C::VPL]) {
+  if constexpr (spmm_smem_bcast<C>()) {
+    __shared__ __align__(16) int2 s_bcast[(AGCF_SPMM_CM_THREADS_MAX / 32) * 32];
+    int2* mine = s_bcast + (threadIdx.x & ~31);
+    const int lane = threadIdx.x & 31;
+    __syncwarp();                                          // the previous chunk's pairs are no longer read
+    mine[lane] = make_int2(c[0], __float_as_int(v[0]));
+    __syncwarp();
+    const int4* row = reinterpret_cast<const int4*>(mine + (lane & ~(C::LPR - 1)));
+#pragma unroll
+    for (int t2 = 0; t2 < C::CH / 2; ++t2) {
+      const int4 two = row[t2];                            // entries 2 t2 and 2 t2 + 1 of this group's chunk
+      if (two.x >= 0) {
+        const float4* xr = p.X + (size_t)two.x * C::V4 + gl;
+#pragma unroll
+        for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], __int_as_float(two.y), ld_gather_f4(xr + vv * C::LPR));
+      }
+      if (two.z >= 0) {
+        const float4* xr = p.X + (size_t)two.z * C::V4 + gl;
+#pragma unroll
+        for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], __int_as_float(two.w), ld_gather_f4(xr + vv * C::LPR));
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < C::EPL; ++k) {
 #pragma unroll
@@ -282,26 +305,6 @@ __device__ __forceinline__ void spmm_consume_chunk(const SpmmParams& p, const in
           else fma4(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
         }
       }
-    }
-  }
-}
-
-// shared-memory form: `row` = this lane group's CH pairs of the chunk
-template <typename C>
-__device__ __forceinline__ void spmm_consume_chunk_smem(const SpmmParams& p, const int4* __restrict__ row, int gl,
-                                                        float4 (&acc)[C::VPL]) {
-#pragma unroll
-  for (int t2 = 0; t2 < C::CH / 2; ++t2) {
-    const int4 two = row[t2];                              // entries 2 t2 and 2 t2 + 1
-    if (two.x >= 0) {
-      const float4* xr = p.X + (size_t)two.x * C::V4 + gl;
-#pragma unroll
-      for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], __int_as_float(two.y), ld_gather_f4(xr + vv * C::LPR));
-    }
-    if (two.z >= 0) {
-      const float4* xr = p.X + (size_t)two.z * C::V4 + gl;
-#pragma unroll
-      for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], __int_as_float(two.w), ld_gather_f4(xr + vv * C::LPR));
     }
   }
 }
@@ -328,22 +331,6 @@ __device__ __forceinline__ void spmm_accumulate_chunks(const SpmmParams& p, int 
   };
   load_chunk(first);
   int off = first;
-  if constexpr (spmm_smem_bcast<C>()) {
-    __shared__ __align__(16) int2 s_bcast[(AGCF_SPMM_CM_THREADS_MAX / 32) * 2 * 32];   // [warp][buffer][lane]
-    const int lane = threadIdx.x & 31;
-    int2* mine = s_bcast + (threadIdx.x >> 5) * 64;
-    const int grp_base = lane & ~(C::LPR - 1);
-    __syncwarp();                                          // an earlier work item of this warp is done with the buffers
-    mine[lane] = make_int2(c_next[0], __float_as_int(v_next[0]));
-    for (int it = 0; it < iters; ++it, off += stride) {
-      const int b = (it & 1) * 32;
-      load_chunk(off + stride);                            // the next chunk's indices: in flight during the gathers
-      __syncwarp();                                        // chunk `it` is in buffer b; the reads of chunk it - 1 are over
-      spmm_consume_chunk_smem<C>(p, reinterpret_cast<const int4*>(mine + b + grp_base), gl, acc);
-      mine[(b ^ 32) + lane] = make_int2(c_next[0], __float_as_int(v_next[0]));
-    }
-    return;
-  }
   for (int it = 0; it < iters; ++it, off += stride) {
     int c[C::EPL];
     float v[C::EPL];
