@@ -260,9 +260,14 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
 // launch, 61 -> 51 us row-masked, 1.10 -> 1.053 ms per training step; at d = 64 (one float4 per lane) it is slower than
 // the shuffles (46.8 vs 43.6 us), so those rows keep them.  A double-buffered form that stores chunk k + 1's pairs at the
 // end of chunk k's iteration (the STS -> LDS hop off the gather path) measured WORSE at both widths (d = 128: 214 us and
-// 1.097 ms per step; d = 64: 45.2 us): the next chunk's index registers stay live across the gathers and spill.
+// 1.097 ms per step; d = 64: 45.2 us): the next chunk's index registers stay live across the gathers and spill.  Columns
+// and values in separate shared arrays (four entries per LDS.128, the column quad dead once its gathers are issued)
+// measured equal stand-alone and slower in the step at both widths (profiles/r2_spmm_smem_split.txt).
+#ifndef AGCF_SPMM_SMEM_BCAST_MIN_VPL
+#define AGCF_SPMM_SMEM_BCAST_MIN_VPL 2
+#endif
 template <typename C>
-constexpr bool spmm_smem_bcast() { return C::EPL == 1 && C::VPL >= 2 && C::LPR >= 16; }
+constexpr bool spmm_smem_bcast() { return C::EPL == 1 && C::VPL >= AGCF_SPMM_SMEM_BCAST_MIN_VPL && C::LPR >= 16; }
 
 template <typename C, bool PACKED>
 __device__ __forceinline__ void spmm_consume_chunk(const SpmmParams& p, const int (&c)[C::EPL], const float (&v)[C::EPL],
