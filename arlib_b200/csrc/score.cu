@@ -1214,28 +1214,48 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const float* __restrict
 }
 
 // ---------------------------------------------------------------------- metrics
-__global__ void __launch_bounds__(128) rank_metrics_kernel(const int32_t* __restrict__ topk_idx, int K,
+// One WARP per user: the K ids of a user are read coalesced, every lane runs the binary search of its id, and the hits are
+// collected with a ballot; lane 0 then adds inv_log[k] over the set bits in ASCENDING k -- the same fp64 summation order as a
+// sequential loop over k (the metric strings are compared character by character with the reference's).  A thread per user
+// walked its 50 ids one dependent search after the other behind strided loads: ~0.15 ms of the 1.2 ms evaluation.
+__global__ void __launch_bounds__(256) rank_metrics_kernel(const int32_t* __restrict__ topk_idx, int K,
                                                            const int32_t* __restrict__ t_rowptr, const int32_t* __restrict__ t_items,
                                                            const int32_t* __restrict__ test_total, int n_u,
                                                            const int32_t* __restrict__ cutoffs, int nc,
                                                            const double* __restrict__ inv_log, double* __restrict__ out) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_u) return;
+  const int r = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (r >= n_u) return;                                              // warp-uniform
   const int s = t_rowptr[r], e = t_rowptr[r + 1];
   for (int c = 0; c < nc; ++c) {
     const int n = min(cutoffs[c], K);
     double hits = 0.0, dcg = 0.0, idcg = 0.0;
-    for (int k = 0; k < n; ++k) {
-      const int it = topk_idx[(size_t)r * K + k];
-      if (it < 0) continue;
-      int lo = s, hi = e;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (t_items[mid] < it) lo = mid + 1; else hi = mid; }
-      if (lo < e && t_items[lo] == it) { hits += 1.0; dcg += inv_log[k]; }
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      bool hit = false;
+      if (k < n) {
+        const int it = topk_idx[(size_t)r * K + k];
+        if (it >= 0) {
+          int lo = s, hi = e;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (t_items[mid] < it) lo = mid + 1; else hi = mid; }
+          hit = lo < e && t_items[lo] == it;
+        }
+      }
+      unsigned int m = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) {
+        while (m != 0u) {
+          const int b = __ffs(m) - 1;
+          hits += 1.0;
+          dcg += inv_log[base + b];
+          m &= m - 1u;
+        }
+      }
     }
-    const int ni = min(test_total[r], cutoffs[c]);
-    for (int k = 0; k < ni; ++k) idcg += inv_log[k];
-    double* o = out + ((size_t)r * nc + c) * 3;
-    o[0] = hits; o[1] = dcg; o[2] = idcg;
+    if (lane == 0) {
+      const int ni = min(test_total[r], cutoffs[c]);
+      for (int k = 0; k < ni; ++k) idcg += inv_log[k];
+      double* o = out + ((size_t)r * nc + c) * 3;
+      o[0] = hits; o[1] = dcg; o[2] = idcg;
+    }
   }
 }
 
@@ -1554,8 +1574,8 @@ extern "C" int agcf_rank_metrics(const int32_t* topk_idx, int32_t K, const int32
                                  const double* inv_log, double* out, agcf_stream_t stream) {
   if (!topk_idx || !t_rowptr || !test_total || !cutoffs || !inv_log || !out || K <= 0 || n_u < 0 || nc <= 0) return AGCF_EINVAL;
   if (n_u == 0) return AGCF_OK;
-  rank_metrics_kernel<<<(unsigned)((n_u + 127) / 128), 128, 0, (cudaStream_t)stream>>>(topk_idx, K, t_rowptr, t_items, test_total,
-                                                                                        n_u, cutoffs, nc, inv_log, out);
+  rank_metrics_kernel<<<(unsigned)((n_u + 7) / 8), 256, 0, (cudaStream_t)stream>>>(topk_idx, K, t_rowptr, t_items, test_total,
+                                                                                    n_u, cutoffs, nc, inv_log, out);
   AGCF_LAUNCH_OK();
   return AGCF_OK;
 }
