@@ -230,13 +230,15 @@ __device__ __forceinline__ void spmm_epilogue(const SpmmParams& p, int row, bool
         }
       }
       if (p.adam_p != nullptr) {
-        float4 pp = p.adam_p[at], mm = p.adam_m[at], vv = p.adam_v[at];
+        // the moments are touched once per step: evict-first loads / stores, so that 36 MB of them do not push the layer
+        // tables out of L2 (0.2499 -> 0.2480 ms per step at C2, two runs each); the parameters are read again right away
+        float4 pp = p.adam_p[at], mm = __ldcs(p.adam_m + at), vv = __ldcs(p.adam_v + at);
         const float w1 = 1.f - p.beta1, w2 = 1.f - p.beta2;
         adam_update(pp.x, o.x, mm.x, vv.x, w1, w2, p.beta2, step_size, bc2_sqrt, p.adam_eps);
         adam_update(pp.y, o.y, mm.y, vv.y, w1, w2, p.beta2, step_size, bc2_sqrt, p.adam_eps);
         adam_update(pp.z, o.z, mm.z, vv.z, w1, w2, p.beta2, step_size, bc2_sqrt, p.adam_eps);
         adam_update(pp.w, o.w, mm.w, vv.w, w1, w2, p.beta2, step_size, bc2_sqrt, p.adam_eps);
-        p.adam_p[at] = pp; p.adam_m[at] = mm; p.adam_v[at] = vv;
+        p.adam_p[at] = pp; __stcs(p.adam_m + at, mm); __stcs(p.adam_v + at, vv);
       }
     }
   }
