@@ -26,8 +26,10 @@ def _mask_csr(U, lists):
 
 
 @pytest.mark.parametrize("U,I,d,K", [(70, 1000, 64, 50), (130, 333, 32, 10), (64, 4100, 128, 50), (5, 31, 64, 3),
-                                      (33, 2049, 256, 100), (40, 70000, 32, 20)])
+                                      (33, 2049, 256, 100), (40, 70000, 32, 20), (24, 100001, 64, 50)])
 def test_topk_exact_scores_and_sets(U, I, d, K):
+    # (70 000 items: the candidate selection keeps a user's 2 188 group maxima in shared memory; 100 001 items: 3 126
+    # groups no longer fit eight to a CTA and are read from L2 in every pass -- csrc/score.cu, cand_stage)
     from arlib_b200 import ops
     rng = np.random.default_rng(U + I)
     ue = torch.randn(U, d)
