@@ -11,6 +11,8 @@ batches), then the step graph(s).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -198,6 +200,9 @@ class LightGCNEngine:
         self.m = torch.zeros_like(table)
         self.v = torch.zeros_like(table)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        # side stream of the step-counter / Adam-coefficient kernel (_fork_coefs); ARLIB_B200_COEF_STREAM=0: in line
+        self._coef_stream = torch.cuda.Stream(device=dev) if os.environ.get("ARLIB_B200_COEF_STREAM", "1") == "1" else None
+        self._coefs_forked = False
         self.T = 0
         self.cap = int(max_triples)
         nbmax = (self.cap + self.B - 1) // self.B
@@ -259,6 +264,24 @@ class LightGCNEngine:
     def _worklist(self, b):
         w = self.wl
         return None if w is None else (w["vrows"][b], w["vpart"][b], w["count"][b:b + 1], w["partial"], w["tickets"])
+
+    def _fork_coefs(self):
+        """Step counter + 1 and the NEXT step's Adam coefficients on a side stream (a parallel branch of a captured
+        graph): the one-thread kernel only has to be done before the next step's LAST launch, so the next step's
+        propagation does not queue behind it (3.7 us + a launch boundary per step on the main chain otherwise)."""
+        if self._coef_stream is None:
+            ops.adam_coefs(self.step_dev, self.adam_coefs, self.lr, self.betas[0], self.betas[1], increment=True)
+            return
+        cur = torch.cuda.current_stream()
+        self._coef_stream.wait_stream(cur)          # after this step's Adam launch has read the coefficients
+        with torch.cuda.stream(self._coef_stream):
+            ops.adam_coefs(self.step_dev, self.adam_coefs, self.lr, self.betas[0], self.betas[1], increment=True)
+        self._coefs_forked = True
+
+    def _join_coefs(self):
+        if self._coefs_forked:
+            torch.cuda.current_stream().wait_stream(self._coef_stream)
+            self._coefs_forked = False
 
     def _refresh_adam_coefs(self):
         """coefs of the NEXT step from the device step counter (after construction / a restore of step_dev)"""
@@ -385,6 +408,7 @@ class LightGCNEngine:
             elif self.fuse_adam:
                 # dE0 = (G + A H) / (L + 1) never reaches memory: the epilogue applies Adam to the row and puts the
                 # batch's rows of G back to zero (not when L == 1: G is then also the gathered operand)
+                self._join_coefs()                  # this step's Adam coefficients (side branch of the previous step)
                 ops.spmm(self.g, H, acc_in=self.G, acc_div=float(L + 1), col_mask=mask if k == L else None,
                          adam=(self.E0, self.m, self.v, self.adam_coefs, self.betas[0], self.betas[1], self.adam_eps),
                          zero_acc_in=L > 1)
@@ -394,7 +418,7 @@ class LightGCNEngine:
         if self.fuse_adam:
             if L == 1:
                 ops.zero_rows(seg_node, n_seg, 3 * nb, self.G)
-            ops.adam_coefs(self.step_dev, self.adam_coefs, self.lr, self.betas[0], self.betas[1], increment=True)
+            self._fork_coefs()
             return
         ops.zero_rows(seg_node, n_seg, 3 * nb, self.G)
         # owner-computes: Adam on this rank's rows; the updated rows are stored into every peer's E0
@@ -432,6 +456,7 @@ class LightGCNEngine:
         if not use_graph or (self.comm is not None and not self.dist_graphs):
             for b in range(first_batch, first_batch + n_steps):
                 self._launch_step(b)
+            self._join_coefs()
         else:
             key = (first_batch, n_steps, self.T)
             g = self._graphs.get(key)
@@ -444,11 +469,13 @@ class LightGCNEngine:
                 g = torch.cuda.CUDAGraph()
                 state = self._snapshot()
                 self._launch_step(first_batch)        # eager warm-up of every kernel in the step
+                self._join_coefs()
                 self._restore(state)
                 torch.cuda.synchronize()
                 with torch.cuda.graph(g):
                     for b in range(first_batch, first_batch + n_steps):
                         self._launch_step(b)
+                    self._join_coefs()               # every branch of the capture ends in the capturing stream
                 self._graphs[key] = g
                 # capture does not execute: fall through to the replay below
             g.replay()
@@ -473,6 +500,7 @@ class LightGCNEngine:
             self.T = nb
             self._group(0, nb)
             self._launch_step(0)
+            self._join_coefs()
             if self._loss_eager is None:
                 self._loss_eager = torch.empty(4, dtype=torch.float32).pin_memory()
             self._loss_eager.copy_(self.out4[0], non_blocking=True)
@@ -522,6 +550,7 @@ class LightGCNEngine:
         def step(slot):
             self.T = slot["batch"] * self.B + nb
             self._launch_step(slot["batch"])
+            self._join_coefs()
             slot["loss"].copy_(self.out4[slot["batch"]], non_blocking=True)
 
         prep(slots[0]); step(slots[0])              # eager warm-up (module loading, func attributes) on zeros
