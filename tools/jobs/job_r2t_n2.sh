@@ -8,4 +8,4 @@ timeout 600 $TR --master-port 29611 bench.py --gpus 2 --steps 500 --warmup 5 --n
 ARLIB_B200_DIST=rows timeout 600 $TR --master-port 29612 bench.py --gpus 2 --steps 500 --warmup 5 --no-cpu-baseline > $O/bench_n2_rows.json 2> $O/bench_n2_rows.err; echo rc=$?
 for f in bench_n2_dshard bench_n2_rows; do python -c "
 import json;d=json.loads(open('$O/$f.json').read().strip().splitlines()[-1]);print('$f',d['value'],d['ms_per_step'],d['e2e']['value'],d['eval']['ms'],d['roofline']['avg_launch_ms'])"; done
-tail -3 $O/*.err
+for f in $O/*.err; do tail -2 $f; done
