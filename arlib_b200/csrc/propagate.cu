@@ -296,20 +296,20 @@ __device__ __forceinline__ void spmm_consume_chunk(const SpmmParams& p, const in
         for (int vv = 0; vv < C::VPL; ++vv) fma4_packed(acc[vv], __int_as_float(two.w), ld_gather_f4(xr + vv * C::LPR));
       }
     }
-    return;
-  }
+  } else {
 #pragma unroll
-  for (int k = 0; k < C::EPL; ++k) {
+    for (int k = 0; k < C::EPL; ++k) {
 #pragma unroll
-    for (int t = 0; t < C::LPR; ++t) {
-      const int ct = __shfl_sync(0xffffffffu, c[k], t, C::LPR);
-      const float vt = __shfl_sync(0xffffffffu, v[k], t, C::LPR);
-      if (ct >= 0) {
-        const float4* xr = p.X + (size_t)ct * C::V4 + gl;
+      for (int t = 0; t < C::LPR; ++t) {
+        const int ct = __shfl_sync(0xffffffffu, c[k], t, C::LPR);
+        const float vt = __shfl_sync(0xffffffffu, v[k], t, C::LPR);
+        if (ct >= 0) {
+          const float4* xr = p.X + (size_t)ct * C::V4 + gl;
 #pragma unroll
-        for (int vv = 0; vv < C::VPL; ++vv) {
-          if (PACKED) fma4_packed(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
-          else fma4(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
+          for (int vv = 0; vv < C::VPL; ++vv) {
+            if (PACKED) fma4_packed(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
+            else fma4(acc[vv], vt, ld_gather_f4(xr + vv * C::LPR));
+          }
         }
       }
     }
