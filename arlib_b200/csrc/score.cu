@@ -941,6 +941,11 @@ constexpr int kS2ItemCap = 128;
 // of (user, item) scores: per float4 step of k it reads 4 + 4 vectors and issues 64 FMAs (the warp-per-pair
 // kernel above reads 5 vectors per 16 FMAs and sits on the shared-memory bandwidth).  Every score is still ONE chain
 // acc = fmaf(u[k], v[k], acc), k ascending from 0 -- the bits of exact_dot.
+// (A software-pipelined form -- a CTA owns several tiles of a group, the next tile's user rows travel global -> shared with
+// cp.async while the current one is computed, pair ids / mask words / T_u loaded one tile further ahead -- was built, passed
+// the bit-identity tests and measured SLOWER: 1.14-1.18 vs 1.05 ms per evaluation at the Gowalla shape, 5.52 vs 5.18 ms at the
+// Amazon-book shape (profiles/r2_eval_rescore_pipelined_experiment.txt): its two 35 KB buffers leave 2 CTAs per SM where this
+// kernel runs 4, and 32 resident warps hide the load -> barrier -> compute chain better than the pipeline does.)
 constexpr int kS2TU = 128;                 // users per tile
 
 #ifndef AGCF_S2RI_MINB
