@@ -1343,16 +1343,16 @@ using namespace agcf;
 // stages 0 and 1 of agcf_score_topk: mask bits, then the masked group maxima (impl 1: tcgen05 TF32 GEMM, impl 0: fp32)
 static int run_stage01(const float* Uemb, const int32_t* user_rows, int n_u, const float* Iemb, int n_items, int d,
                        const int32_t* mask_rowptr, const int32_t* mask_items, int item_offset, int impl, const WsLayout& L,
-                       unsigned char* base, cudaStream_t st, float* margin_out) {
+                       unsigned char* base, cudaStream_t st, float* margin_out, bool keep_mask_bits = false) {
   uint32_t* bits = reinterpret_cast<uint32_t*>(base + L.bits_off);
   float* gmax = reinterpret_cast<float*>(base + L.gmax_off);
   float* norm = reinterpret_cast<float*>(base + L.norm_off);
   const float4* U4 = reinterpret_cast<const float4*>(Uemb);
   const float4* I4 = reinterpret_cast<const float4*>(Iemb);
   *margin_out = 0.f;
-  // stage 0
-  AGCF_CUDA_OK(cudaMemsetAsync(bits, 0, (size_t)n_u * L.pitch * 4, st));
-  if (mask_rowptr != nullptr) {
+  // stage 0 (skipped when the caller vouches for the bits of the previous call: AGCF_TOPK_KEEP_MASK_BITS)
+  if (!keep_mask_bits) AGCF_CUDA_OK(cudaMemsetAsync(bits, 0, (size_t)n_u * L.pitch * 4, st));
+  if (mask_rowptr != nullptr && !keep_mask_bits) {
     mask_bits_kernel<<<(unsigned)((n_u + 7) / 8), 256, 0, st>>>(user_rows, n_u, mask_rowptr, mask_items, n_items, item_offset, L.pitch, bits);
     AGCF_LAUNCH_OK();
   }
@@ -1427,6 +1427,8 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
                                void* ws, int64_t ws_bytes, agcf_stream_t stream) {
   if (!Uemb || !Iemb || !out_val || !out_idx || !ws || n_u < 0 || n_items <= 0 || K <= 0) return AGCF_EINVAL;
   if ((mask_rowptr == nullptr) != (mask_items == nullptr)) return AGCF_EINVAL;
+  const bool keep_mask_bits = (impl & AGCF_TOPK_KEEP_MASK_BITS) != 0;
+  impl &= ~AGCF_TOPK_KEEP_MASK_BITS;
   if (!supported_d(d) || K > 1024 || (impl != 0 && impl != 1)) return AGCF_EUNSUPPORTED;
   if (!aligned16(Uemb) || !aligned16(Iemb) || (reinterpret_cast<uintptr_t>(ws) & 255u)) return AGCF_EINVAL;
   if (n_u == 0) return AGCF_OK;
@@ -1443,7 +1445,7 @@ extern "C" int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int3
   float margin_scale = 0.f;
   {
     const int rc = run_stage01(Uemb, user_rows, n_u, Iemb, n_items, d, mask_rowptr, mask_items, item_offset, impl, L, base, st,
-                               &margin_scale);
+                               &margin_scale, keep_mask_bits);
     if (rc != AGCF_OK) return rc;
   }
   // stage 2

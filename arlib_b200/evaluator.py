@@ -132,11 +132,24 @@ class FullRankEvaluator:
             need = ops._lib.load().agcf_score_topk_ws_bytes(hi - lo, item_emb.shape[0], item_emb.shape[1], K)
             if need < 0:
                 ops._lib.check(int(need), "agcf_score_topk_ws_bytes")
-            if self._ws is None or self._ws.numel() < need:
-                self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+            ws, keep = self._workspace(lo, hi, item_emb, int(need))
             ops.score_topk(user_emb, item_emb, K, user_rows=self.user_rows[lo:hi], mask_rowptr=self.mask_rowptr,
-                           mask_items=self.mask_items, impl=impl, ws=self._ws, out=(vals[lo:hi], idx[lo:hi]))
+                           mask_items=self.mask_items, impl=impl, ws=ws, out=(vals[lo:hi], idx[lo:hi]), keep_mask_bits=keep)
         return vals, idx
+
+    def _workspace(self, lo, hi, item_emb, need):
+        """(workspace of the user chunk that starts at ``lo``, keep_mask_bits).  Every chunk owns its workspace, so the
+        train-item mask bits stage 0 leaves there survive until the chunk's next evaluation: keep_mask_bits is True when
+        the LAST call on that workspace scored exactly these users against an item table of this shape (the masks and
+        user_rows of an evaluator never change) -- then the memset + bit scatter are skipped (AGCF_TOPK_KEEP_MASK_BITS)."""
+        chunks = self.__dict__.setdefault("_ws_chunks", {})
+        ws, old_key = chunks.get(lo, (None, None))
+        if ws is None or ws.numel() < need:
+            ws, old_key = torch.empty(need, dtype=torch.uint8, device=self.device), None
+        key = (int(hi), int(item_emb.shape[0]), int(item_emb.shape[1]), int(ws.data_ptr()))
+        chunks[lo] = (ws, key)
+        self._ws = ws                                  # (bench.py times the scoring stage alone on it)
+        return ws, key == old_key
 
     def topk_sharded(self, user_emb, item_emb, K, rank, world, impl=None):
         """Item-sharded scoring: this rank scores every test user against its
@@ -186,10 +199,10 @@ class FullRankEvaluator:
             need = ops._lib.load().agcf_score_topk_ws_bytes(b - a, ie.shape[0], ie.shape[1], K)
             if need < 0:
                 ops._lib.check(int(need), "agcf_score_topk_ws_bytes")
-            if self._ws is None or self._ws.numel() < need:
-                self._ws = torch.empty(int(need), dtype=torch.uint8, device=self.device)
+            ws, keep = self._workspace(a, b, ie, int(need))
             ops.score_topk(ue, ie, K, user_rows=self.user_rows[a:b], mask_rowptr=self.mask_rowptr,
-                           mask_items=self.mask_items, impl=impl, ws=self._ws, out=(vals[a - lo:b - lo], idx[a - lo:b - lo]))
+                           mask_items=self.mask_items, impl=impl, ws=ws, out=(vals[a - lo:b - lo], idx[a - lo:b - lo]),
+                           keep_mask_bits=keep)
         if not gather:
             return vals[:hi - lo], idx[:hi - lo], (lo, hi)
         all_v = torch.empty((world * per, K), dtype=torch.float32, device=self.device)

@@ -297,10 +297,12 @@ def increment(counter):
 
 
 def score_topk(user_emb, item_emb, K, user_rows=None, mask_rowptr=None, mask_items=None, item_offset=0, impl=0,
-               n_u=None, ws=None, return_flags=False, out=None):
+               n_u=None, ws=None, return_flags=False, out=None, keep_mask_bits=False):
     """agcf_score_topk over users ``user_rows`` (or the first n_u rows).  Returns
     (values [n_u,K] fp32, item ids [n_u,K] int32) sorted by (score desc, id asc); ``out`` = (values, ids) to write into
-    (contiguous [n_u, K] blocks, e.g. row slices of the caller's result tensors: no copy afterwards)."""
+    (contiguous [n_u, K] blocks, e.g. row slices of the caller's result tensors: no copy afterwards).
+    ``keep_mask_bits``: ``ws`` still holds the mask bits of the previous call on it with the same users / items / mask
+    (AGCF_TOPK_KEEP_MASK_BITS, include/agcf.h): the memset + bit scatter of stage 0 are skipped."""
     lib = _lib.load()
     _f32(user_emb, "user_emb"); _f32(item_emb, "item_emb"); _i32(user_rows, "user_rows")
     _i32(mask_rowptr, "mask_rowptr"); _i32(mask_items, "mask_items")
@@ -322,7 +324,8 @@ def score_topk(user_emb, item_emb, K, user_rows=None, mask_rowptr=None, mask_ite
         out_idx = torch.empty((n_u, K), dtype=torch.int32, device=user_emb.device)
     flags = torch.empty(n_u, dtype=torch.int32, device=user_emb.device) if return_flags else None
     _lib.check(lib.agcf_score_topk(user_emb.data_ptr(), _p(user_rows), n_u, item_emb.data_ptr(), n_items, d,
-                                   _p(mask_rowptr), _p(mask_items), int(K), int(item_offset), int(impl),
+                                   _p(mask_rowptr), _p(mask_items), int(K), int(item_offset),
+                                   int(impl) | (0x100 if keep_mask_bits else 0),
                                    out_val.data_ptr(), out_idx.data_ptr(), _p(flags), ws.data_ptr(), ws.numel(),
                                    _lib.stream_ptr()), "agcf_score_topk")
     if return_flags:

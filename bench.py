@@ -541,11 +541,14 @@ def run_ours(args):
     if int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1")) == 1 and world == 1:
         Fu, Fi = F[:U].contiguous(), F[U:].contiguous()
         chunks_u = [ev.user_rows[lo:lo + USER_CHUNK].contiguous() for lo in range(0, n_test, USER_CHUNK)]
+        # a workspace of its own: the evaluator's per-chunk workspaces keep their mask bits between evaluations
+        ws_s1 = torch.empty(int(ops._lib.load().agcf_score_topk_ws_bytes(max(c.numel() for c in chunks_u), I, d, 1)),
+                            dtype=torch.uint8, device=dev)
 
         def stage1():
             for rows_ in chunks_u:
                 ops.score_group_max(Fu, Fi, user_rows=rows_, mask_rowptr=ev.mask_rowptr, mask_items=ev.mask_items, impl=1,
-                                    ws=ev._ws, want_output=False)
+                                    ws=ws_s1, want_output=False)
         stage1(); stage1()
         torch.cuda.synchronize()
         e0.record()

@@ -341,8 +341,13 @@ int agcf_adam_coefs(int32_t* step_dev, int32_t increment, float lr, float beta1,
  *   (impl=0) that only emits per-32-item group maxima; stage 2 selects candidate
  *   groups with a rigorous error margin; stage 3 re-scores candidates in exact
  *   fp32 -- so the result does not depend on impl.
+ *   impl | AGCF_TOPK_KEEP_MASK_BITS: the caller guarantees that the workspace still holds the train-item mask bits of
+ *   the PREVIOUS call on it with the same user_rows / n_u / n_items / d / item_offset / mask arrays (test() masks the
+ *   same training items in every evaluation): stage 0 -- a memset of n_u * ceil(n_items / 32) words and the bit scatter,
+ *   ~6 % of an evaluation at the Gowalla shape -- is skipped.  Nothing else in the workspace survives a call.
  * Replaces: recommender/LightGCN.py:86-90 (predict) + :148-156 (test loop) +
  * util/algorithm.py:155-167 (find_k_largest). */
+#define AGCF_TOPK_KEEP_MASK_BITS 0x100
 int64_t agcf_score_topk_ws_bytes(int32_t n_u, int32_t n_items, int32_t d, int32_t K);
 int agcf_score_topk(const float* Uemb, const int32_t* user_rows, int32_t n_u,
                     const float* Iemb, int32_t n_items, int32_t d,

@@ -347,3 +347,27 @@ def test_group_max_stage_alone_and_the_tf32_error_bound():
     delta = 1.01 * 2.0 ** -9 * ue.norm(dim=1, keepdim=True) * ie.norm(dim=1).max()
     assert bool(((g1 - ref).abs() <= delta).all())
     assert float((g1 - ref).abs().max()) > 0                     # it IS approximate: stage 2 is what makes the result exact
+
+
+def test_evaluator_keeps_the_mask_bits_between_evaluations():
+    """FullRankEvaluator re-uses its workspace: from the second evaluation on stage 0 (memset + train-item bit scatter) is
+    skipped (AGCF_TOPK_KEEP_MASK_BITS).  Every evaluation must still equal a call on a fresh workspace, also after a
+    call with other users / another table shape went through the same workspace in between."""
+    from arlib_b200 import ops
+    from arlib_b200.evaluator import FullRankEvaluator
+    rng = np.random.default_rng(11)
+    U, I, d, K = 700, 3000, 64, 50
+    tu = rng.integers(0, U, 20000); ti = rng.integers(0, I, 20000)
+    su = rng.integers(0, U, 2000); si = rng.integers(0, I, 2000)
+    ev = FullRankEvaluator.from_arrays(U, I, tu, ti, su, si, torch.device(DEV))
+    for trial in range(4):
+        ue = torch.randn(U, d, device=DEV); ie = torch.randn(I, d, device=DEV)
+        v, i = ev.topk(ue, ie, K)
+        v0, i0 = ops.score_topk(ue, ie, K, user_rows=ev.user_rows, mask_rowptr=ev.mask_rowptr, mask_items=ev.mask_items, impl=1)
+        assert torch.equal(i, i0) and torch.equal(v, v0), trial
+        if trial == 1:
+            # another shape through the same workspace: the key changes, the next evaluation rebuilds its bits
+            ie2 = torch.randn(I - 500, d, device=DEV)
+            v2, i2 = ev.topk(ue, ie2, K)
+            w2, j2 = ops.score_topk(ue, ie2, K, user_rows=ev.user_rows, mask_rowptr=ev.mask_rowptr, mask_items=ev.mask_items, impl=1)
+            assert torch.equal(i2, j2) and torch.equal(v2, w2)
