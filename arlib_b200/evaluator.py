@@ -18,9 +18,28 @@ import torch
 from . import ops
 from .util.metrics import format_measure
 
-# users per agcf_score_topk call (the stage-2 workspace grows with it: ~1.2 GB at 32 768 users x 41 k items).  Measured on B200
-# at the Gowalla shape (27 324 test users, profiles/r2_summary.md): one call 1.04 ms, two calls of <= 16 384 users 1.15 ms
-USER_CHUNK = int(os.environ.get("ARLIB_B200_EVAL_CHUNK", "32768"))
+# users per agcf_score_topk call.  ARLIB_B200_EVAL_CHUNK fixes it; by default it is what a ~4 GB workspace holds for the
+# item table at hand (the stage-2 workspace grows with users x item groups: ~40 KB per user at 41 k items -> every named
+# shape goes through ONE call; ~380 KB per user at 1 M items -> ~10 k users per call).  Measured on B200
+# (profiles/r2_summary.md): Gowalla shape, 27 324 test users: one call 1.04 ms, two calls of <= 16 384 users 1.15 ms;
+# Amazon-book shape, 51 551 users: one call 4.77 ms, two calls 4.97 ms.
+_CHUNK_ENV = os.environ.get("ARLIB_B200_EVAL_CHUNK")
+USER_CHUNK = int(_CHUNK_ENV) if _CHUNK_ENV else 32768      # (kept for callers that slice by a fixed chunk)
+WS_BUDGET_BYTES = 4 << 30
+
+
+def user_chunk(n_items, d, K):
+    """Users per call for an [n_items, d] item table (see above)."""
+    if _CHUNK_ENV:
+        return int(_CHUNK_ENV)
+    lib = ops._lib.load()
+    a, b = int(lib.agcf_score_topk_ws_bytes(1024, n_items, d, K)), int(lib.agcf_score_topk_ws_bytes(2048, n_items, d, K))
+    if a < 0 or b <= a:
+        return 32768
+    per_user = (b - a) / 1024.0
+    return int(min(131072, max(4096, (WS_BUDGET_BYTES // per_user) // 1024 * 1024)))
+
+
 # stage-1 implementation of agcf_score_topk: 1 = TF32 tcgen05 GEMM (d <= 128), 0 = fp32 CUDA-core GEMM
 DEFAULT_IMPL = int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1"))
 
@@ -127,8 +146,9 @@ class FullRankEvaluator:
         n = self.user_rows.numel()
         vals = torch.empty((n, K), dtype=torch.float32, device=self.device)
         idx = torch.empty((n, K), dtype=torch.int32, device=self.device)
-        for lo in range(0, n, USER_CHUNK):
-            hi = min(n, lo + USER_CHUNK)
+        chunk = user_chunk(item_emb.shape[0], item_emb.shape[1], K)
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
             need = ops._lib.load().agcf_score_topk_ws_bytes(hi - lo, item_emb.shape[0], item_emb.shape[1], K)
             if need < 0:
                 ops._lib.check(int(need), "agcf_score_topk_ws_bytes")
@@ -167,8 +187,9 @@ class FullRankEvaluator:
         ue = user_emb.detach().contiguous()
         vals = torch.empty((n, K), dtype=torch.float32, device=self.device)
         idx = torch.empty((n, K), dtype=torch.int32, device=self.device)
-        for lo in range(0, n, USER_CHUNK):                   # the stage-2 workspace grows with the users of a call
-            hi = min(n, lo + USER_CHUNK)
+        chunk = user_chunk(block.shape[0], block.shape[1], K)
+        for lo in range(0, n, chunk):                        # the stage-2 workspace grows with the users of a call
+            hi = min(n, lo + chunk)
             ops.score_topk(ue, block, K, user_rows=self.user_rows[lo:hi], mask_rowptr=self.mask_rowptr,
                            mask_items=self.mask_items, item_offset=i0, impl=impl, out=(vals[lo:hi], idx[lo:hi]))
         all_v = torch.empty((world, n, K), dtype=torch.float32, device=self.device)
@@ -194,8 +215,9 @@ class FullRankEvaluator:
         ue, ie = user_emb.detach().contiguous(), item_emb.detach().contiguous()
         vals = torch.full((per, K), float("-inf"), dtype=torch.float32, device=self.device)
         idx = torch.full((per, K), -1, dtype=torch.int32, device=self.device)
-        for a in range(lo, hi, USER_CHUNK):
-            b = min(hi, a + USER_CHUNK)
+        chunk = user_chunk(ie.shape[0], ie.shape[1], K)
+        for a in range(lo, hi, chunk):
+            b = min(hi, a + chunk)
             need = ops._lib.load().agcf_score_topk_ws_bytes(b - a, ie.shape[0], ie.shape[1], K)
             if need < 0:
                 ops._lib.check(int(need), "agcf_score_topk_ws_bytes")

@@ -536,7 +536,8 @@ def run_ours(args):
     cand_groups = float(cg.float().mean().item())
     flops = 2.0 * n_test * I * d
     # the one dense contraction on its own (stage 0 + 1: mask bits, row gather, tcgen05 TF32 group-max GEMM) per user chunk
-    from arlib_b200.evaluator import USER_CHUNK
+    from arlib_b200.evaluator import user_chunk
+    USER_CHUNK = user_chunk(I, d, TOPK)
     s1_ms = None
     if int(os.environ.get("ARLIB_B200_SCORE_IMPL", "1")) == 1 and world == 1:
         Fu, Fi = F[:U].contiguous(), F[U:].contiguous()
