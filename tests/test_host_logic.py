@@ -135,3 +135,19 @@ def test_device_edge_builders_equal_the_scipy_path():
     assert pairs == set(zip(u.tolist(), i.tolist()))
     sub = DeviceTrainSet.from_graph(g, U, I, epoch_edges=500, seed=1)
     assert sub.n_edges == 500 and set(zip(sub.e_user.tolist(), sub.e_item.tolist())) <= pairs
+
+
+def test_evaluation_user_chunk_follows_the_workspace_budget():
+    """users per agcf_score_topk call = what a ~4 GB workspace holds for the item table (evaluator.user_chunk): every named
+    shape in one call, a 1 M-item table in ~10 k-user calls; bounded below and above; the workspace of a chunk fits the budget."""
+    from arlib_b200 import _lib
+    from arlib_b200.evaluator import user_chunk, WS_BUDGET_BYTES
+    lib = _lib.load()
+    sizes = [(1682, 64), (3706, 64), (40981, 64), (38048, 64), (91599, 128), (1000000, 128)]
+    chunks = [user_chunk(i, d, 50) for i, d in sizes]
+    assert all(4096 <= c <= 131072 and c % 1024 == 0 for c in chunks)
+    assert chunks[2] >= 29858 and chunks[4] >= 52643          # Gowalla / Amazon-book: all users in one call
+    assert chunks[5] < chunks[4] < chunks[2] <= chunks[0]      # more items -> fewer users per call
+    for (i, d), c in zip(sizes, chunks):
+        if c > 4096:
+            assert lib.agcf_score_topk_ws_bytes(c, i, d, 50) <= WS_BUDGET_BYTES * 1.02
